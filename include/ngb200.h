@@ -1,0 +1,142 @@
+/*
+ * ngb200.h -- C ABI of libngb200.so, the B200 (sm_100a) kernel library behind neograd's tensor-op hot path.
+ *
+ * The reference (pranftw/neograd v0.0.4) has no FFI: its extension point is the Python `Operation`
+ * protocol (README.md:44-52, neograd/autograd/ops/operation.py:83-117).  Each entry point below replaces the
+ * NumPy expression inside one `Operation.forward()` / grad_fn body; the citation after each declaration is the
+ * reference line whose arithmetic it reproduces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer to float32 unless stated otherwise;
+ *   - `stream` is a cudaStream_t passed as void*; calls enqueue work and never synchronise the stream;
+ *   - the library never takes ownership of caller memory; it owns one internal scratch arena per device
+ *     (split-K partials, reduction partials), sized by ngb_init();
+ *   - return value: 0 = NGB_OK, otherwise an ngb_status; ngb_last_error() gives the message (thread local);
+ *   - shapes are int64 arrays, row-major (C order), exactly NumPy's `.shape`;
+ *   - conv / pool outputs and upstream gradients use "neograd order": output position (p,q) of the textbook
+ *     (Ho,Wo) map is stored at flat index q*Ho+p of the (Ho,Wo)-shaped result (conv.py:39-47 vs 149-151).
+ */
+#ifndef NGB200_H_
+#define NGB200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NGB_ABI_VERSION 1
+
+typedef void* ngb_stream_t;
+
+typedef enum {
+  NGB_OK = 0,
+  NGB_ERR_INVALID = 1,      /* bad argument (maps to ValueError on the Python side) */
+  NGB_ERR_CUDA = 2,         /* CUDA runtime / driver failure */
+  NGB_ERR_UNSUPPORTED = 3,  /* shape outside what the kernels implement */
+  NGB_ERR_SCRATCH = 4       /* internal scratch arena too small (call ngb_init with a larger size) */
+} ngb_status;
+
+typedef enum { NGB_ADD = 0, NGB_SUB = 1, NGB_MUL = 2, NGB_DIV = 3, NGB_POW = 4, NGB_SECOND = 5 } ngb_binary_op;
+typedef enum { NGB_EXP = 0, NGB_LOG = 1, NGB_RELU = 2, NGB_LEAKY_RELU = 3, NGB_SIGMOID = 4, NGB_TANH = 5 } ngb_unary_op;
+
+/* GEMM engine selection for ngb_gemm */
+typedef enum {
+  NGB_GEMM_AUTO = 0,   /* tcgen05 TF32 when the shape/alignment qualifies, else SIMT fp32 */
+  NGB_GEMM_SIMT = 1,   /* fp32 FMA on CUDA cores (exact fp32 products) */
+  NGB_GEMM_TCGEN05 = 2 /* force the tcgen05/TMEM/TMA TF32 kernel; NGB_ERR_UNSUPPORTED if not eligible */
+} ngb_gemm_engine;
+
+/* ---- library ---------------------------------------------------------------------------------------------- */
+int ngb_abi_version(void);
+const char* ngb_last_error(void);
+/* Allocates the per-device scratch arena (bytes; 0 = default 64 MiB). Idempotent; must run before graph capture. */
+int ngb_init(int64_t scratch_bytes);
+int ngb_shutdown(void);
+/* Which engine ngb_gemm(NGB_GEMM_AUTO) would pick: returns NGB_GEMM_SIMT or NGB_GEMM_TCGEN05. */
+int ngb_gemm_query(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc);
+/* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
+int64_t ngb_launch_count(void);
+
+/* ---- Dot: neograd/autograd/ops/basics.py:180-207 ---------------------------------------------------------- */
+/* C[M,N] (row-major, ldc) = op(A)[M,K] * op(B)[K,N] (+ C if accumulate).  transA=0: A is M x K (lda); transA=1: A is
+ * stored K x M.  transB likewise.  fwd: np.dot(A,B) basics.py:194; dgrad: np.dot(ug, B.T) :206 (transB=1);
+ * wgrad: np.dot(A.T, ug) :207 (transA=1). */
+int ngb_gemm(int engine, int transA, int transB, int64_t M, int64_t N, int64_t K,
+             const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
+             int accumulate, ngb_stream_t stream);
+
+/* ---- Conv3D / Conv2D: neograd/autograd/ops/conv.py:121-343 ------------------------------------------------- */
+/* x (N,C,H,W), w (O,C,KH,KW), b (O) -> y (N,O,Ho,Wo) in neograd order.  neograd's single-channel Conv2D
+ * (conv.py:131-152) is the C=O=1 case with a one-element bias. */
+int ngb_conv_fprop(const float* x, const float* w, const float* b, float* y,
+                   int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                   int64_t pad, int64_t stride, ngb_stream_t stream);                       /* conv.py:245-269 */
+int ngb_conv_dgrad(const float* ug, const float* w, float* dx,
+                   int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                   int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);       /* conv.py:299-309 */
+int ngb_conv_wgrad(const float* ug, const float* x, float* dw,
+                   int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                   int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);       /* conv.py:311-321 */
+int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo,
+                   int accumulate, ngb_stream_t stream);                                    /* conv.py:323-327, 198-199 */
+
+/* ---- MaxPool2D / MaxPool3D: neograd/autograd/ops/conv.py:362-542 ------------------------------------------- */
+/* x (outer,H,W) with outer = N or N*C.  y and idx (uint8, position of the FIRST maximum inside the zero-padded
+ * window, row-major in the window; np.argmax conv.py:424/523) are (outer,Ho,Wo) in neograd order.  idx may be NULL. */
+int ngb_maxpool_fwd(const float* x, float* y, uint8_t* idx, int64_t outer, int64_t H, int64_t W,
+                    int64_t KH, int64_t KW, int64_t pad, int64_t stride, ngb_stream_t stream);  /* conv.py:384-402 */
+/* dx (outer,H,W): each cell takes the value the LAST window covering it (fragment order: W outer, H inner) assigned,
+ * i.e. ug if the cell is that window's argmax else 0 (assignment semantics conv.py:427/526); uncovered cells = 0. */
+int ngb_maxpool_bwd(const float* ug, const uint8_t* idx, float* dx, int64_t outer, int64_t H, int64_t W,
+                    int64_t KH, int64_t KW, int64_t pad, int64_t stride, int accumulate,
+                    ngb_stream_t stream);                                                   /* conv.py:404-431 */
+
+/* ---- broadcasting elementwise ops + unbroadcast: basics.py:6-339, utils.py:34-78, tensor.py:93-100 -------- */
+/* out = a (op) b with NumPy broadcasting.  A NULL operand pointer means "use the scalar immediate". */
+int ngb_ew_binary_fwd(int op, const float* a, float a_scalar, const int64_t* a_shape, int a_rank,
+                      const float* b, float b_scalar, const int64_t* b_shape, int b_rank,
+                      float* out, ngb_stream_t stream);                                     /* basics.py:20,63,107,150,313 */
+/* Fused: g = dLocal(op, side; a, b) * ug over the broadcast shape, summed over the axes along which operand `side`
+ * was broadcast (utils.py:73-78), written (accumulate=0) or added (accumulate=1) to grad (operand-shaped). */
+int ngb_ew_binary_bwd(int op, int side, const float* ug,
+                      const float* a, float a_scalar, const int64_t* a_shape, int a_rank,
+                      const float* b, float b_scalar, const int64_t* b_shape, int b_rank,
+                      float* grad, int accumulate, ngb_stream_t stream);                    /* basics.py:32-33,76-77,119-120,163-164,325-327 */
+int ngb_ew_unary_fwd(int op, float alpha, const float* x, float* out, int64_t n, ngb_stream_t stream);
+                                                                                            /* basics.py:236,274; activations.py:20,54,86,205 */
+int ngb_ew_unary_bwd(int op, float alpha, const float* x, const float* ug, float* out, int64_t n,
+                     int accumulate, ngb_stream_t stream);                                  /* basics.py:246,284; activations.py:31,62-63,94-95,216 */
+/* out = sum of x over the axes whose bit is set in axis_mask (bit d = axis d); out has the remaining dims. */
+int ngb_reduce_sum(const float* x, const int64_t* shape, int rank, uint32_t axis_mask, float* out,
+                   int accumulate, ngb_stream_t stream);                                    /* basics.py:369; utils.py:75 */
+
+/* ---- small dense helpers used by the host engine ----------------------------------------------------------- */
+int ngb_fill(float* dst, float value, int64_t n, ngb_stream_t stream);
+int ngb_axpy(float* dst, const float* src, float alpha, int64_t n, ngb_stream_t stream);  /* dst += alpha*src; tensor.py:301 */
+int ngb_transpose2d(const float* src, float* dst, int64_t rows, int64_t cols, ngb_stream_t stream); /* basics.py:417 */
+
+/* ---- SoftmaxCE: neograd/nn/loss.py:124-172 ----------------------------------------------------------------- */
+/* logits/targets viewed as (outer, L, inner); softmax along L.  loss (1 float) = -(1/num_examples) * sum t*log(p+eps). */
+int ngb_softmax_ce_fwd(const float* logits, const float* targets, int64_t outer, int64_t L, int64_t inner,
+                       float inv_num_examples, float epsilon, float* loss, ngb_stream_t stream);   /* loss.py:153-157 */
+/* dlogits = (ug[0] * inv_num_examples) * (softmax(logits) - targets); ug is a device scalar (may be NULL = 1). */
+int ngb_softmax_ce_bwd(const float* logits, const float* targets, const float* ug, int64_t outer, int64_t L,
+                       int64_t inner, float inv_num_examples, float* dlogits, int accumulate,
+                       ngb_stream_t stream);                                                /* loss.py:167-170 */
+
+/* ---- optimizers: neograd/nn/optim.py ------------------------------------------------------------------------ */
+/* One fused pass over a flat parameter arena.  g is multiplied by grad_scale first (1/world for data parallel). */
+int ngb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
+                  float epsilon, float inv_bias_corr1, float inv_bias_corr2, float grad_scale,
+                  ngb_stream_t stream);                                                     /* optim.py:168-179, 191-197 */
+int ngb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, ngb_stream_t stream);  /* optim.py:42-47 */
+int ngb_momentum_step(float* p, const float* g, float* m, int64_t n, float lr, float beta, float grad_scale,
+                      ngb_stream_t stream);                                                 /* optim.py:63-70, 86-92 */
+int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, float lr, float beta, float epsilon,
+                     float grad_scale, ngb_stream_t stream);                                /* optim.py:112-118, 134-140 */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NGB200_H_ */

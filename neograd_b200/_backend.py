@@ -1,0 +1,110 @@
+"""ctypes binding of libngb200.so (C ABI declared in include/ngb200.h).
+
+There is no CPU fallback: if the shared library is missing the import of `neograd_b200` fails loudly,
+and any kernel call without a CUDA device raises.  PyTorch is used only for device memory, streams and
+torch.distributed (plumbing); every arithmetic kernel on the hot path lives in the shared library.
+"""
+import ctypes
+import os
+from ctypes import c_float, c_int, c_int64, c_uint32, c_void_p, c_char_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, 'lib', 'libngb200.so')
+
+# enums of include/ngb200.h
+ADD, SUB, MUL, DIV, POW, SECOND = range(6)
+EXP, LOG, RELU, LEAKY_RELU, SIGMOID, TANH = range(6)
+GEMM_AUTO, GEMM_SIMT, GEMM_TCGEN05 = range(3)
+OK, ERR_INVALID, ERR_CUDA, ERR_UNSUPPORTED, ERR_SCRATCH = range(5)
+
+
+class NgbError(RuntimeError):
+  pass
+
+
+def _load():
+  if not os.path.exists(LIB_PATH):
+    raise ImportError(
+      f"neograd_b200: {LIB_PATH} is missing. Build it with `make -C neograd_b200/csrc` "
+      "(or `python -c 'import __graft_entry__ as g; g.build()'`). There is no CPU fallback.")
+  return ctypes.CDLL(LIB_PATH)
+
+
+lib = _load()
+
+_i64p = POINTER(c_int64)
+_P = c_void_p
+_S = c_void_p  # stream
+
+# name -> argtypes, exactly the prototypes of include/ngb200.h (checked by tests/test_abi.py)
+SIGNATURES = {
+  'ngb_abi_version': ([], c_int),
+  'ngb_last_error': ([], c_char_p),
+  'ngb_init': ([c_int64], c_int),
+  'ngb_shutdown': ([], c_int),
+  'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
+  'ngb_launch_count': ([], c_int64),
+  'ngb_gemm': ([c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _S], c_int),
+  'ngb_conv_fprop': ([_P, _P, _P, _P] + [c_int64] * 9 + [_S], c_int),
+  'ngb_conv_dgrad': ([_P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
+  'ngb_conv_wgrad': ([_P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
+  'ngb_conv_bgrad': ([_P, _P, c_int64, c_int64, c_int64, c_int, _S], c_int),
+  'ngb_maxpool_fwd': ([_P, _P, _P] + [c_int64] * 7 + [_S], c_int),
+  'ngb_maxpool_bwd': ([_P, _P, _P] + [c_int64] * 7 + [c_int, _S], c_int),
+  'ngb_ew_binary_fwd': ([c_int, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, _S], c_int),
+  'ngb_ew_binary_bwd': ([c_int, c_int, _P, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, c_int, _S], c_int),
+  'ngb_ew_unary_fwd': ([c_int, c_float, _P, _P, c_int64, _S], c_int),
+  'ngb_ew_unary_bwd': ([c_int, c_float, _P, _P, _P, c_int64, c_int, _S], c_int),
+  'ngb_reduce_sum': ([_P, _i64p, c_int, c_uint32, _P, c_int, _S], c_int),
+  'ngb_fill': ([_P, c_float, c_int64, _S], c_int),
+  'ngb_axpy': ([_P, _P, c_float, c_int64, _S], c_int),
+  'ngb_transpose2d': ([_P, _P, c_int64, c_int64, _S], c_int),
+  'ngb_softmax_ce_fwd': ([_P, _P, c_int64, c_int64, c_int64, c_float, c_float, _P, _S], c_int),
+  'ngb_softmax_ce_bwd': ([_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P, c_int, _S], c_int),
+  'ngb_adam_step': ([_P, _P, _P, _P, c_int64] + [c_float] * 7 + [_S], c_int),
+  'ngb_sgd_step': ([_P, _P, c_int64, c_float, c_float, _S], c_int),
+  'ngb_momentum_step': ([_P, _P, _P, c_int64, c_float, c_float, c_float, _S], c_int),
+  'ngb_rmsprop_step': ([_P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _S], c_int),
+}
+
+for _name, (_args, _res) in SIGNATURES.items():
+  _fn = getattr(lib, _name)   # AttributeError here = the library does not export what the header declares
+  _fn.argtypes = _args
+  _fn.restype = _res
+
+if lib.ngb_abi_version() != 1:
+  raise ImportError(f"neograd_b200: ABI version mismatch ({lib.ngb_abi_version()} != 1); rebuild libngb200.so")
+
+_EXC = {ERR_INVALID: ValueError, ERR_UNSUPPORTED: NotImplementedError}
+
+
+def check(rc):
+  if rc != OK:
+    msg = lib.ngb_last_error().decode('utf-8', 'replace')
+    raise _EXC.get(rc, NgbError)(msg)
+
+
+def shape_arg(shape):
+  """tuple -> (int64*, rank)"""
+  n = len(shape)
+  return (c_int64 * max(n, 1))(*shape), n
+
+
+_runtime_ready = False
+
+
+def ensure_runtime():
+  """Allocates the library's scratch arena once (must happen before any CUDA-graph capture)."""
+  global _runtime_ready
+  if not _runtime_ready:
+    import torch
+    if not torch.cuda.is_available():
+      raise NgbError("neograd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    check(lib.ngb_init(0))
+    _runtime_ready = True
+
+
+def stream():
+  """cudaStream_t of torch's current stream (so torch.cuda.graph / stream contexts apply to our launches)."""
+  import torch
+  return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())

@@ -1,0 +1,388 @@
+// Direct (CUDA-core) convolution kernels: the general path for every geometry (any C, O, rectangular filters,
+// padding, stride) and the hot path for the small-channel layers of the LeNet / digits configs, where
+// K = C*KH*KW is far below what the tensor-core implicit GEMM needs.  The multi-channel, stride-1 layers of the
+// C5 sweep go to conv_igemm_tcgen05.cu instead (see the dispatcher at the bottom).
+// Reference: neograd/autograd/ops/conv.py:245-269 (fprop), 299-309 (dgrad), 311-321 (wgrad), 323-327 (bgrad);
+// single-channel Conv2D (conv.py:131-203) is the C = O = 1 case.
+//
+// Layout: x (N,C,H,W) natural; y / ug (N,O,Ho,Wo) in neograd order (position (p,q) at q*Ho+p), i.e. H is the
+// fastest output axis while W is the fastest input axis.  Every kernel stages its input patch in shared memory
+// transposed, so both the global reads (along W) and the global writes (along p) are coalesced.
+#include "common.cuh"
+
+namespace ngb {
+
+int conv_igemm_eligible(int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW, int64_t pad,
+                        int64_t stride);
+int conv_igemm_fprop(const float* x, const float* w, const float* b, float* y, int64_t N, int64_t C, int64_t H, int64_t W,
+                     int64_t O, int64_t KH, int64_t KW, int64_t pad, cudaStream_t st);
+int conv_igemm_dgrad(const float* ug, const float* w, float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O,
+                     int64_t KH, int64_t KW, int64_t pad, int accumulate, cudaStream_t st);
+
+constexpr int OT = 8;  // output channels per thread (register tile)
+
+struct ConvGeo {
+  int N, C, H, W, O, KH, KW, pad, stride, Ho, Wo;
+};
+
+// ---------------------------------------------------------------------------------------------- fprop
+// CTA = IMGS images x (TP x TQ) output positions x OT output channels; 256 threads, one position each.
+// smem: patchT[img][c][pw][ph+1] (input patch, transposed so that p is contiguous) and wts[c][kh][kw][OT].
+__global__ void __launch_bounds__(256) conv_fprop_direct_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                const float* __restrict__ b, float* __restrict__ y,
+                                                                ConvGeo g, int TP, int TQ, int IMGS, int CC) {
+  extern __shared__ float sm[];
+  const int PH = (TP - 1) * g.stride + g.KH, PW = (TQ - 1) * g.stride + g.KW;
+  const int PHp = PH | 1;
+  float* patch = sm;                                        // IMGS*CC*PW*PHp
+  float* wts = sm + (((size_t)IMGS * CC * PW * PHp + 3) & ~size_t(3));   // CC*KH*KW*OT, 16B aligned
+  const int tiles_p = ceil_div(g.Ho, TP), tiles_q = ceil_div(g.Wo, TQ);
+  const int o_tiles = ceil_div(g.O, OT);
+  int bid = blockIdx.x;
+  const int tq = bid % tiles_q; bid /= tiles_q;
+  const int tp = bid % tiles_p; bid /= tiles_p;
+  const int ot = bid % o_tiles; bid /= o_tiles;
+  const int n0 = bid * IMGS;
+  const int p0 = tp * TP, q0 = tq * TQ, o0 = ot * OT;
+
+  const int t = threadIdx.x;
+  const int per_img = TP * TQ;
+  const int img = t / per_img, rem = t - img * per_img;
+  const int lq = rem / TP, lp = rem - lq * TP;
+  const bool active = img < IMGS && (n0 + img) < g.N && (p0 + lp) < g.Ho && (q0 + lq) < g.Wo;
+
+  float acc[OT];
+#pragma unroll
+  for (int o = 0; o < OT; ++o) acc[o] = 0.f;
+
+  const int h_base = p0 * g.stride - g.pad, w_base = q0 * g.stride - g.pad;
+  const int kk = g.KH * g.KW;
+
+  for (int c0 = 0; c0 < g.C; c0 += CC) {
+    const int cc = min(CC, g.C - c0);
+    __syncthreads();
+    // input patch: coalesced along W, stored transposed
+    const int patch_elems = IMGS * cc * PH * PW;
+    for (int e = t; e < patch_elems; e += 256) {
+      int r = e;
+      const int pw = r % PW; r /= PW;
+      const int ph = r % PH; r /= PH;
+      const int c = r % cc; r /= cc;
+      const int im = r;
+      const int n = n0 + im, h = h_base + ph, ww = w_base + pw;
+      float v = 0.f;
+      if (n < g.N && h >= 0 && h < g.H && ww >= 0 && ww < g.W)
+        v = __ldg(x + (((int64_t)n * g.C + c0 + c) * g.H + h) * g.W + ww);
+      patch[((size_t)(im * CC + c) * PW + pw) * PHp + ph] = v;
+    }
+    // weights for this (o-tile, c-chunk): wts[c][kh*KW+kw][o]
+    const int w_elems = cc * kk * OT;
+    for (int e = t; e < w_elems; e += 256) {
+      const int o = e % OT;
+      const int r = e / OT;            // c*kk + tap
+      const int c = r / kk, tap = r - c * kk;
+      float v = 0.f;
+      if (o0 + o < g.O) v = __ldg(w + ((int64_t)(o0 + o) * g.C + c0 + c) * kk + tap);
+      wts[e] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int c = 0; c < cc; ++c) {
+        const float* pc = patch + (size_t)(img * CC + c) * PW * PHp;
+        const float* wc = wts + (size_t)c * kk * OT;
+        for (int kh = 0; kh < g.KH; ++kh) {
+          for (int kw = 0; kw < g.KW; ++kw) {
+            const float xv = pc[(size_t)(lq * g.stride + kw) * PHp + lp * g.stride + kh];
+            const float4 w0 = *reinterpret_cast<const float4*>(wc + (kh * g.KW + kw) * OT);
+            const float4 w1 = *reinterpret_cast<const float4*>(wc + (kh * g.KW + kw) * OT + 4);
+            acc[0] = fmaf(xv, w0.x, acc[0]); acc[1] = fmaf(xv, w0.y, acc[1]);
+            acc[2] = fmaf(xv, w0.z, acc[2]); acc[3] = fmaf(xv, w0.w, acc[3]);
+            acc[4] = fmaf(xv, w1.x, acc[4]); acc[5] = fmaf(xv, w1.y, acc[5]);
+            acc[6] = fmaf(xv, w1.z, acc[6]); acc[7] = fmaf(xv, w1.w, acc[7]);
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+    const int n = n0 + img, p = p0 + lp, q = q0 + lq;
+#pragma unroll
+    for (int o = 0; o < OT; ++o) {
+      if (o0 + o < g.O)
+        y[((int64_t)n * g.O + o0 + o) * g.Ho * g.Wo + (int64_t)q * g.Ho + p] = acc[o] + __ldg(b + o0 + o);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- dgrad
+// dx[n,c,h,w] = sum_{o,kh,kw} ug[n,o,p,q] * w[o,c,kh,kw] with p*s + kh - pad = h, q*s + kw - pad = w.
+// CTA = one image x (TH x TW) input cells x OT input channels ("c tile"); the ug patch that can reach the tile is
+// staged in smem as ugp[o][q][p] (p contiguous, as in global memory), weights as wts[o][kh][kw][ct].
+__global__ void __launch_bounds__(256) conv_dgrad_direct_kernel(const float* __restrict__ ug, const float* __restrict__ w,
+                                                                float* __restrict__ dx, ConvGeo g, int TH, int TW, int OC,
+                                                                int accumulate) {
+  extern __shared__ float sm[];
+  const int tiles_h = ceil_div(g.H, TH), tiles_w = ceil_div(g.W, TW), c_tiles = ceil_div(g.C, OT);
+  int bid = blockIdx.x;
+  const int tw = bid % tiles_w; bid /= tiles_w;
+  const int th = bid % tiles_h; bid /= tiles_h;
+  const int ct = bid % c_tiles; bid /= c_tiles;
+  const int n = bid;
+  const int h0 = th * TH, w0 = tw * TW, c0 = ct * OT;
+  // output positions that can touch rows [h0, h0+TH): p*s <= h+pad <= p*s+KH-1
+  const int s = g.stride;
+  int plo = (h0 + g.pad - (g.KH - 1) + s - 1) / s; if (h0 + g.pad - (g.KH - 1) < 0) plo = 0;
+  int phi = (h0 + TH - 1 + g.pad) / s; if (phi > g.Ho - 1) phi = g.Ho - 1;
+  int qlo = (w0 + g.pad - (g.KW - 1) + s - 1) / s; if (w0 + g.pad - (g.KW - 1) < 0) qlo = 0;
+  int qhi = (w0 + TW - 1 + g.pad) / s; if (qhi > g.Wo - 1) qhi = g.Wo - 1;
+  const int PP = max(phi - plo + 1, 0), PQ = max(qhi - qlo + 1, 0);
+  const int PPmax = (TH + g.KH - 2) / s + 2, PQmax = (TW + g.KW - 2) / s + 2;  // smem carve-up is geometry-independent
+  const int PPp = PPmax | 1;
+  float* ugp = sm;                                   // OC * PQmax * PPp
+  float* wts = sm + (((size_t)OC * PQmax * PPp + 3) & ~size_t(3));   // OC * KH*KW * OT, 16B aligned
+  const int kk = g.KH * g.KW;
+
+  const int t = threadIdx.x;
+  const int lh = t / TW, lw = t - lh * TW;
+  const int h = h0 + lh, ww = w0 + lw;
+  const bool active = lh < TH && h < g.H && ww < g.W;
+  float acc[OT];
+#pragma unroll
+  for (int c = 0; c < OT; ++c) acc[c] = 0.f;
+
+  for (int ob = 0; ob < g.O; ob += OC) {
+    const int oc = min(OC, g.O - ob);
+    __syncthreads();
+    const int pe = oc * PQ * PP;
+    for (int e = t; e < pe; e += 256) {
+      int r = e;
+      const int lp = r % PP; r /= PP;
+      const int lq = r % PQ; r /= PQ;
+      const int o = r;
+      ugp[((size_t)o * PQmax + lq) * PPp + lp] =
+          __ldg(ug + ((int64_t)n * g.O + ob + o) * g.Ho * g.Wo + (int64_t)(qlo + lq) * g.Ho + plo + lp);
+    }
+    const int we = oc * kk * OT;
+    for (int e = t; e < we; e += 256) {
+      const int c = e % OT;
+      const int r = e / OT;
+      const int o = r / kk, tap = r - o * kk;
+      float v = 0.f;
+      if (c0 + c < g.C) v = __ldg(w + ((int64_t)(ob + o) * g.C + c0 + c) * kk + tap);
+      wts[e] = v;
+    }
+    __syncthreads();
+    if (active) {
+      for (int kh = 0; kh < g.KH; ++kh) {
+        const int hn = h + g.pad - kh;
+        if (hn < 0 || hn % s) continue;
+        const int p = hn / s;
+        if (p < plo || p > phi) continue;
+        for (int kw = 0; kw < g.KW; ++kw) {
+          const int wn = ww + g.pad - kw;
+          if (wn < 0 || wn % s) continue;
+          const int q = wn / s;
+          if (q < qlo || q > qhi) continue;
+          const int tap = kh * g.KW + kw;
+          for (int o = 0; o < oc; ++o) {
+            const float gv = ugp[((size_t)o * PQmax + (q - qlo)) * PPp + (p - plo)];
+            const float4 wa = *reinterpret_cast<const float4*>(wts + ((size_t)o * kk + tap) * OT);
+            const float4 wb = *reinterpret_cast<const float4*>(wts + ((size_t)o * kk + tap) * OT + 4);
+            acc[0] = fmaf(gv, wa.x, acc[0]); acc[1] = fmaf(gv, wa.y, acc[1]);
+            acc[2] = fmaf(gv, wa.z, acc[2]); acc[3] = fmaf(gv, wa.w, acc[3]);
+            acc[4] = fmaf(gv, wb.x, acc[4]); acc[5] = fmaf(gv, wb.y, acc[5]);
+            acc[6] = fmaf(gv, wb.z, acc[6]); acc[7] = fmaf(gv, wb.w, acc[7]);
+          }
+        }
+      }
+    }
+  }
+  if (active) {
+#pragma unroll
+    for (int c = 0; c < OT; ++c) {
+      if (c0 + c < g.C) {
+        float* d = dx + (((int64_t)n * g.C + c0 + c) * g.H + h) * g.W + ww;
+        *d = accumulate ? *d + acc[c] : acc[c];
+      }
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- wgrad
+// dw[o,c,kh,kw] = sum_{n,p,q} ug[n,o,p,q] * xpad[n,c,p*s+kh,q*s+kw].  One thread per filter element, gridDim.y
+// splits the batch; per-split partials are summed by a deterministic second pass.
+__global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(const float* __restrict__ ug, const float* __restrict__ x,
+                                                                float* __restrict__ part, ConvGeo g, int imgs_per_split) {
+  const int kk = g.KH * g.KW;
+  const int64_t nw = (int64_t)g.O * g.C * kk;
+  const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nw) return;
+  const int tap = (int)(e % kk);
+  const int c = (int)((e / kk) % g.C);
+  const int o = (int)(e / ((int64_t)kk * g.C));
+  const int kh = tap / g.KW, kw = tap - kh * g.KW;
+  const int nb = blockIdx.y * imgs_per_split, ne = min(g.N, nb + imgs_per_split);
+  // valid output range for this tap (input index must fall inside the unpadded image)
+  const int s = g.stride;
+  int p_lo = 0, p_hi = g.Ho - 1, q_lo = 0, q_hi = g.Wo - 1;
+  while (p_lo <= p_hi && p_lo * s + kh - g.pad < 0) ++p_lo;
+  while (p_hi >= p_lo && p_hi * s + kh - g.pad >= g.H) --p_hi;
+  while (q_lo <= q_hi && q_lo * s + kw - g.pad < 0) ++q_lo;
+  while (q_hi >= q_lo && q_hi * s + kw - g.pad >= g.W) --q_hi;
+  float acc = 0.f;
+  for (int n = nb; n < ne; ++n) {
+    const float* gn = ug + ((int64_t)n * g.O + o) * g.Ho * g.Wo;
+    const float* xn = x + ((int64_t)n * g.C + c) * g.H * g.W;
+    for (int q = q_lo; q <= q_hi; ++q) {
+      const float* gq = gn + (int64_t)q * g.Ho;
+      const float* xq = xn + (q * s + kw - g.pad);
+      for (int p = p_lo; p <= p_hi; ++p) acc = fmaf(__ldg(gq + p), __ldg(xq + (int64_t)(p * s + kh - g.pad) * g.W), acc);
+    }
+  }
+  part[(int64_t)blockIdx.y * nw + e] = acc;
+}
+
+// ---------------------------------------------------------------------------------------------- bgrad
+// db[o] = sum_{n,f} ug[n,o,f].  grid = (O, splits over N); contiguous HoWo runs -> coalesced float loads.
+__global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict__ ug, float* __restrict__ part, int64_t N,
+                                                         int64_t O, int64_t HW, int64_t imgs_per_split) {
+  __shared__ float red[32];
+  const int64_t o = blockIdx.x;
+  const int64_t nb = (int64_t)blockIdx.y * imgs_per_split, ne = min(N, nb + imgs_per_split);
+  float acc = 0.f;
+  const int64_t span = (ne - nb) * HW;
+  for (int64_t i = threadIdx.x; i < span; i += blockDim.x) {
+    const int64_t n = nb + i / HW, f = i % HW;
+    acc += ug[(n * O + o) * HW + f];
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) part[(int64_t)blockIdx.y * O + o] = acc;
+}
+
+static int make_geo(ConvGeo* g, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW, int64_t pad,
+                    int64_t stride) {
+  NGB_CHECK_ARG(stride >= 1, "Stride must be greater than or equal to 1");
+  NGB_CHECK_ARG(pad >= 0, "Padding must be greater than or equal to zero");
+  NGB_CHECK_ARG(N >= 0 && C >= 1 && O >= 1 && KH >= 1 && KW >= 1 && H >= 1 && W >= 1, "conv: bad dimensions");
+  NGB_CHECK_ARG(H + 2 * pad >= KH && W + 2 * pad >= KW, "conv: filter larger than the padded input");
+  NGB_CHECK_ARG(N * C * H * W < (int64_t(1) << 40), "conv: tensor too large");
+  g->N = (int)N; g->C = (int)C; g->H = (int)H; g->W = (int)W; g->O = (int)O; g->KH = (int)KH; g->KW = (int)KW;
+  g->pad = (int)pad; g->stride = (int)stride;
+  g->Ho = (int)((H + 2 * pad - KH) / stride + 1);
+  g->Wo = (int)((W + 2 * pad - KW) / stride + 1);
+  return NGB_OK;
+}
+
+constexpr int kDirectSmem = 96 * 1024;
+
+}  // namespace ngb
+
+using namespace ngb;
+
+extern "C" int ngb_conv_fprop(const float* x, const float* w, const float* b, float* y, int64_t N, int64_t C, int64_t H,
+                              int64_t W, int64_t O, int64_t KH, int64_t KW, int64_t pad, int64_t stride, ngb_stream_t stream) {
+  ConvGeo g;
+  int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
+  if (rc) return rc;
+  if (N == 0) return NGB_OK;
+  cudaStream_t st = as_stream(stream);
+  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride)) return conv_igemm_fprop(x, w, b, y, N, C, H, W, O, KH, KW, pad, st);
+  // tile shape: p (fastest output axis) first
+  int TP = g.Ho < 16 ? g.Ho : 16;
+  int TQ = 256 / TP; if (TQ > g.Wo) TQ = g.Wo;
+  int IMGS = 256 / (TP * TQ); if (IMGS < 1) IMGS = 1; if (IMGS > g.N) IMGS = g.N;
+  const int PH = (TP - 1) * g.stride + g.KH, PW = (TQ - 1) * g.stride + g.KW, PHp = PH | 1;
+  const int64_t per_c = (int64_t)IMGS * PW * PHp + (int64_t)g.KH * g.KW * OT;
+  int CC = (int)((kDirectSmem / 4 - 4) / per_c);
+  if (CC < 1) return fail(NGB_ERR_UNSUPPORTED, "conv fprop: filter/stride too large for the direct kernel tile");
+  if (CC > g.C) CC = g.C;
+  if (CC > 16) CC = 16;
+  const size_t smem = (size_t)CC * per_c * 4 + 16;
+  static bool attr = false;
+  if (!attr) { NGB_CUDA(cudaFuncSetAttribute(conv_fprop_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDirectSmem)); attr = true; }
+  const int64_t blocks = (int64_t)ceil_div(g.N, IMGS) * ceil_div(g.O, OT) * ceil_div(g.Ho, TP) * ceil_div(g.Wo, TQ);
+  NGB_CHECK_ARG(blocks < (int64_t(1) << 31), "conv fprop: grid too large");
+  conv_fprop_direct_kernel<<<(unsigned)blocks, 256, smem, st>>>(x, w, b, y, g, TP, TQ, IMGS, CC);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+extern "C" int ngb_conv_dgrad(const float* ug, const float* w, float* dx, int64_t N, int64_t C, int64_t H, int64_t W,
+                              int64_t O, int64_t KH, int64_t KW, int64_t pad, int64_t stride, int accumulate,
+                              ngb_stream_t stream) {
+  ConvGeo g;
+  int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
+  if (rc) return rc;
+  if (N == 0) return NGB_OK;
+  cudaStream_t st = as_stream(stream);
+  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride))
+    return conv_igemm_dgrad(ug, w, dx, N, C, H, W, O, KH, KW, pad, accumulate, st);
+  int TW = g.W < 32 ? g.W : 32;
+  int TH = 256 / TW; if (TH > g.H) TH = g.H;
+  const int PPmax = (TH + g.KH - 2) / g.stride + 2, PQmax = (TW + g.KW - 2) / g.stride + 2, PPp = PPmax | 1;
+  const int64_t per_o = (int64_t)PQmax * PPp + (int64_t)g.KH * g.KW * OT;
+  int OC = (int)((kDirectSmem / 4 - 4) / per_o);
+  if (OC < 1) return fail(NGB_ERR_UNSUPPORTED, "conv dgrad: filter too large for the direct kernel tile");
+  if (OC > g.O) OC = g.O;
+  if (OC > 32) OC = 32;
+  const size_t smem = (size_t)OC * per_o * 4 + 16;
+  static bool attr = false;
+  if (!attr) { NGB_CUDA(cudaFuncSetAttribute(conv_dgrad_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kDirectSmem)); attr = true; }
+  const int64_t blocks = (int64_t)g.N * ceil_div(g.C, OT) * ceil_div(g.H, TH) * ceil_div(g.W, TW);
+  NGB_CHECK_ARG(blocks < (int64_t(1) << 31), "conv dgrad: grid too large");
+  conv_dgrad_direct_kernel<<<(unsigned)blocks, 256, smem, st>>>(ug, w, dx, g, TH, TW, OC, accumulate);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+extern "C" int ngb_conv_wgrad(const float* ug, const float* x, float* dw, int64_t N, int64_t C, int64_t H, int64_t W,
+                              int64_t O, int64_t KH, int64_t KW, int64_t pad, int64_t stride, int accumulate,
+                              ngb_stream_t stream) {
+  ConvGeo g;
+  int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
+  if (rc) return rc;
+  cudaStream_t st = as_stream(stream);
+  const int64_t nw = O * C * KH * KW;
+  if (N == 0) {
+    if (!accumulate) return ngb_fill(dw, 0.f, nw, stream);
+    return NGB_OK;
+  }
+  rc = ensure_init();
+  if (rc) return rc;
+  const int64_t xblocks = ceil_div<int64_t>(nw, 256);
+  int64_t splits = ceil_div<int64_t>(4 * kNumSMs, xblocks);
+  if (splits > N) splits = N;
+  const int64_t cap = scratch_bytes() / (nw * (int64_t)sizeof(float));
+  if (splits > cap) splits = cap;
+  if (splits < 1) return fail(NGB_ERR_SCRATCH, "conv wgrad: scratch arena too small for %lld filter elements", (long long)nw);
+  const int64_t ips = ceil_div<int64_t>(N, splits);
+  splits = ceil_div<int64_t>(N, ips);
+  dim3 grid((unsigned)xblocks, (unsigned)splits);
+  conv_wgrad_direct_kernel<<<grid, 256, 0, st>>>(ug, x, scratch_ptr(), g, (int)ips);
+  NGB_LAUNCH_CHECK();
+  return launch_sum_partials(scratch_ptr(), (int)splits, nw, dw, accumulate, st);
+}
+
+extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate,
+                              ngb_stream_t stream) {
+  NGB_CHECK_ARG(N >= 0 && O >= 1 && HoWo >= 0, "conv bgrad: bad dimensions");
+  cudaStream_t st = as_stream(stream);
+  if (N == 0 || HoWo == 0) {
+    if (!accumulate) return ngb_fill(db, 0.f, O, stream);
+    return NGB_OK;
+  }
+  int rc = ensure_init();
+  if (rc) return rc;
+  int64_t splits = ceil_div<int64_t>(4 * kNumSMs, O);
+  if (splits > N) splits = N;
+  // keep at least ~4K elements per CTA
+  const int64_t min_imgs = ceil_div<int64_t>(4096, HoWo);
+  if (splits > ceil_div<int64_t>(N, min_imgs)) splits = ceil_div<int64_t>(N, min_imgs);
+  if (splits < 1) splits = 1;
+  const int64_t ips = ceil_div<int64_t>(N, splits);
+  splits = ceil_div<int64_t>(N, ips);
+  dim3 grid((unsigned)O, (unsigned)splits);
+  conv_bgrad_kernel<<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips);
+  NGB_LAUNCH_CHECK();
+  return launch_sum_partials(scratch_ptr(), (int)splits, O, db, accumulate, st);
+}

@@ -1,0 +1,367 @@
+// TF32 GEMM on the 5th-generation tensor cores: TMA -> 128B-swizzled shared-memory ring -> tcgen05.mma (one issuing
+// thread) -> fp32 accumulators in TMEM (double buffered) -> tcgen05.ld epilogue.  Persistent, warp specialised:
+//   warp 0    TMA producer          (empty[] -> TMA loads -> full[])
+//   warp 1    MMA issuer + TMEM owner (full[] -> tcgen05.mma -> commit empty[] / tmem_full[])
+//   warps 2-5 epilogue              (tmem_full[] -> tcgen05.ld -> global stores -> tmem_empty[])
+// Both operand majors are supported so that Dot forward (A K-major, B MN-major), data-grad (both K-major) and
+// weight-grad (both MN-major) run on row-major neograd tensors without a transpose pass:
+//   basics.py:194  C = A.B     -> (A: K-major, B[K,N]: MN-major)
+//   basics.py:206  dA = ug.B^T -> (ug: K-major, B as [N_mma=K, K_mma=N] : K-major)
+//   basics.py:207  dB = A^T.ug -> (A^T: MN-major, ug: MN-major), reduction over the batch -> split-K
+// Work items are (output tile, K-split); split partials go to the scratch arena and are summed by a second,
+// deterministic pass (no atomics).
+#include "tc_common.cuh"
+
+#include <mutex>
+#include <stdlib.h>
+
+namespace ngb {
+
+int gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+              int64_t ldb, float* C, int64_t ldc, int accumulate, cudaStream_t st);
+int launch_splitk_reduce(const float* part, int splits, int64_t M, int64_t N, float* C, int64_t ldc, int accumulate,
+                         cudaStream_t st);
+
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+int make_tmap_f32(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                  const uint32_t* box, bool atom32b) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) return fail(NGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  static const bool plain_f32 = getenv("NGB_TMAP_FLOAT32") != nullptr;  // debug switch: no TF32 rounding in the TMA unit
+  cuuint64_t gdims[5], gstr[4];
+  cuuint32_t bdims[5], estr[5];
+  for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; bdims[i] = box[i]; estr[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
+  CUresult r = enc(out, plain_f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_TFLOAT32, (cuuint32_t)rank,
+                   const_cast<float*>(base), gdims, gstr, bdims, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   atom32b ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(NGB_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return NGB_OK;
+}
+
+// ---------------------------------------------------------------------------------------------- kernel
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;           // 32 fp32 = 128 bytes = one swizzle row
+constexpr int UMMA_K = 8;             // tf32: 32 bytes per instruction
+constexpr int kThreads = 192;
+constexpr uint32_t kSpinNone = 0;
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 2 accumulator stages (power of two >= 32)
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct GemmArgs {
+  int M, N;            // output extent
+  int k_blocks;        // ceil(K / BLOCK_K)
+  int tiles_m, tiles_n;
+  int splits;          // K splits per output tile
+  int kb_per_split;
+  float* C;            // final output (splits == 1) ...
+  int64_t ldc;
+  float* partial;      // ... or split partials [split][M*N] (ld = N)
+  int accumulate;
+};
+
+// A_MN / B_MN: operand is MN-major in global memory (1) or K-major (0).
+template <int BLOCK_N, int A_MN, int B_MN>
+__global__ void __launch_bounds__(kThreads, 1)
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+  using C_ = Cfg<BLOCK_N>;
+  constexpr int kStages = C_::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * C_::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_a);
+    prefetch_tmap(&tmap_b);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C_::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int num_work = g.tiles_m * g.tiles_n * g.splits;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+        const int split = w % g.splits, tile = w / g.splits;
+        const int m0 = (tile % g.tiles_m) * BLOCK_M, n0 = (tile / g.tiles_m) * BLOCK_N;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.k_blocks, kb0 + g.kb_per_split);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1);
+          mbar_arrive_expect_tx(&full[s], C_::kStageBytes);
+          uint8_t* sa = smem_a + s * C_::kABytes;
+          uint8_t* sb = smem_b + s * C_::kBBytes;
+          const int k0 = kb * BLOCK_K;
+          if (A_MN) {
+            // global dims {M, K}: one {32 x 32} box per 32-wide M chunk; chunk c lands at sa + c*4096
+#pragma unroll
+            for (int c = 0; c < BLOCK_M / 32; ++c) tma_load_2d(sa + c * 4096, &tmap_a, &full[s], m0 + c * 32, k0);
+          } else {
+            tma_load_2d(sa, &tmap_a, &full[s], k0, m0);  // global dims {K, M}: box {32, 128}
+          }
+          if (B_MN) {
+#pragma unroll
+            for (int c = 0; c < BLOCK_N / 32; ++c) tma_load_2d(sb + c * 4096, &tmap_b, &full[s], n0 + c * 32, k0);
+          } else {
+            tma_load_2d(sb, &tmap_b, &full[s], k0, n0);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+      // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major tf32 must use the 32-byte-atom variant of
+      // the 128B swizzle (tools/tc_probe.cu measured every other encoding to give zeros or garbage): 32-element MN
+      // chunks 4096 B apart (LBO), 4-row K groups 512 B apart (SBO); one UMMA_K = 8 K-rows = 1024 B.
+      constexpr uint64_t adesc_base = A_MN ? make_smem_desc_base(4096, 512, kLayoutSW128Base32B) : make_smem_desc_base(16, 1024);
+      constexpr uint64_t bdesc_base = B_MN ? make_smem_desc_base(4096, 512, kLayoutSW128Base32B) : make_smem_desc_base(16, 1024);
+      constexpr uint32_t a_kstep = A_MN ? 1024 : UMMA_K * 4;  // bytes to advance the start address per UMMA_K
+      constexpr uint32_t b_kstep = B_MN ? 1024 : UMMA_K * 4;
+      uint32_t it = 0, tile_it = 0;
+      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+        const int split = w % g.splits;
+        const int kb0 = split * g.kb_per_split;
+        const int kb1 = min(g.k_blocks, kb0 + g.kb_per_split);
+        const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * C_::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * C_::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_tf32(d_tmem, smem_desc(adesc_base, a_addr + k * a_kstep), smem_desc(bdesc_base, b_addr + k * b_kstep),
+                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+        }
+        umma_commit(&tmem_full[acc]);  // accumulator complete
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;  // TMEM lane quadrant this warp may access
+    uint32_t tile_it = 0;
+    const bool vec_ok = g.partial ? (g.N % 4 == 0) : ((g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0));
+    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+      const int split = w % g.splits, tile = w / g.splits;
+      const int m0 = (tile % g.tiles_m) * BLOCK_M, n0 = (tile / g.tiles_m) * BLOCK_N;
+      const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_ph);
+      tc_fence_after();
+      const int row = m0 + quad * 32 + lane;
+      float* out_row;
+      int64_t ld;
+      if (g.partial) { ld = g.N; out_row = g.partial + (int64_t)split * g.M * g.N + (int64_t)row * ld; }
+      else { ld = g.ldc; out_row = g.C + (int64_t)row * ld; }
+      const bool accum = !g.partial && g.accumulate;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BLOCK_N) {  // last chunk read: hand the accumulator back before the (slow) global stores
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (row < g.M) {
+          const int nbase = n0 + c0;
+          if (vec_ok && nbase + 32 <= g.N) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+              float4* p = reinterpret_cast<float4*>(out_row + nbase + j);
+              if (accum) { float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+              *p = o;
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (nbase + j < g.N) out_row[nbase + j] = accum ? out_row[nbase + j] + v[j] : v[j];
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C_::kTmemCols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- host launch
+template <int BLOCK_N, int A_MN, int B_MN>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int grid, cudaStream_t st) {
+  using C_ = Cfg<BLOCK_N>;
+  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(ta, tb, g);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+template <int BLOCK_N>
+static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int grid,
+                        cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BLOCK_N, 0, 0>(ta, tb, g, grid, st);
+  if (!a_mn && b_mn) return launch<BLOCK_N, 0, 1>(ta, tb, g, grid, st);
+  if (a_mn && !b_mn) return launch<BLOCK_N, 1, 0>(ta, tb, g, grid, st);
+  return launch<BLOCK_N, 1, 1>(ta, tb, g, grid, st);
+}
+
+bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc) {
+  (void)transA; (void)transB; (void)ldc;
+  if (M < 64 || N < 32 || K < 32) return false;
+  if (M * N * K < (int64_t(1) << 22)) return false;          // tiny problems: launch-bound, SIMT is as fast
+  if (lda % 4 || ldb % 4) return false;                        // TMA: global strides are multiples of 16 bytes
+  if (M > 0x7fffffff || N > 0x7fffffff || K > 0x7fffffff) return false;
+  return true;
+}
+
+int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
+            int64_t ldb, float* C, int64_t ldc, int accumulate, cudaStream_t st) {
+  if (!aligned16(A) || !aligned16(B)) return fail(NGB_ERR_UNSUPPORTED, "tcgen05 GEMM needs 16-byte aligned operands");
+  const int a_mn = transA ? 1 : 0;  // A stored [K,M] (M contiguous) -> MN-major
+  const int b_mn = transB ? 0 : 1;  // B stored [K,N] (N contiguous) -> MN-major; stored [N,K] -> K-major
+  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+
+  CUtensorMap ta, tb;
+  {
+    uint64_t dims[2], str[1];
+    uint32_t box[2];
+    if (a_mn) { dims[0] = M; dims[1] = K; box[0] = 32; box[1] = BLOCK_K; }
+    else { dims[0] = K; dims[1] = M; box[0] = BLOCK_K; box[1] = BLOCK_M; }
+    str[0] = (uint64_t)lda * 4;
+    int rc = make_tmap_f32(&ta, A, 2, dims, str, box, a_mn);
+    if (rc) return rc;
+    if (b_mn) { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = BLOCK_K; }
+    else { dims[0] = K; dims[1] = N; box[0] = BLOCK_K; box[1] = (uint32_t)BN; }
+    str[0] = (uint64_t)ldb * 4;
+    rc = make_tmap_f32(&tb, B, 2, dims, str, box, b_mn);
+    if (rc) return rc;
+  }
+
+  GemmArgs g;
+  g.M = (int)M; g.N = (int)N;
+  g.k_blocks = (int)ceil_div<int64_t>(K, BLOCK_K);
+  g.tiles_m = (int)ceil_div<int64_t>(M, BLOCK_M);
+  g.tiles_n = (int)ceil_div<int64_t>(N, BN);
+  const int tiles = g.tiles_m * g.tiles_n;
+  int splits = 1;
+  if (tiles < kNumSMs / 2 && g.k_blocks >= 16) {
+    splits = kNumSMs / tiles;
+    if (splits > g.k_blocks / 8) splits = g.k_blocks / 8;
+    if (splits > 1) {
+      if (ensure_init() != NGB_OK) return NGB_ERR_CUDA;
+      const int64_t cap = scratch_bytes() / (M * N * (int64_t)sizeof(float));
+      if (splits > cap) splits = (int)cap;
+    }
+    if (splits < 1) splits = 1;
+  }
+  g.kb_per_split = (int)ceil_div<int64_t>(g.k_blocks, splits);
+  g.splits = (int)ceil_div<int64_t>(g.k_blocks, g.kb_per_split);
+  g.C = C; g.ldc = ldc;
+  g.partial = g.splits > 1 ? scratch_ptr() : nullptr;
+  g.accumulate = accumulate;
+  const int work = tiles * g.splits;
+  const int grid = work < kNumSMs ? work : kNumSMs;
+
+  int rc;
+  if (BN == 64) rc = launch_major<64>(a_mn, b_mn, ta, tb, g, grid, st);
+  else if (BN == 128) rc = launch_major<128>(a_mn, b_mn, ta, tb, g, grid, st);
+  else rc = launch_major<256>(a_mn, b_mn, ta, tb, g, grid, st);
+  if (rc) return rc;
+  if (g.splits > 1) return launch_splitk_reduce(g.partial, g.splits, M, N, C, ldc, accumulate, st);
+  return NGB_OK;
+}
+
+}  // namespace tc
+}  // namespace ngb
+
+using namespace ngb;
+
+extern "C" int ngb_gemm_query(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
+                              int64_t ldc) {
+  return tc::gemm_tc_eligible(transA, transB, M, N, K, lda, ldb, ldc) ? NGB_GEMM_TCGEN05 : NGB_GEMM_SIMT;
+}
+
+extern "C" int ngb_gemm(int engine, int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda,
+                        const float* B, int64_t ldb, float* C, int64_t ldc, int accumulate, ngb_stream_t stream) {
+  NGB_CHECK_ARG(M >= 0 && N >= 0 && K >= 0, "ngb_gemm: negative dimension");
+  NGB_CHECK_ARG(lda >= (transA ? M : K) && ldb >= (transB ? K : N) && ldc >= N, "ngb_gemm: leading dimension too small");
+  cudaStream_t st = as_stream(stream);
+  if (M == 0 || N == 0) return NGB_OK;
+  if (K == 0) {
+    if (!accumulate) {
+      for (int64_t m = 0; m < M; ++m) NGB_CUDA(cudaMemsetAsync(C + m * ldc, 0, N * sizeof(float), st));
+    }
+    return NGB_OK;
+  }
+  bool use_tc = false;
+  if (engine == NGB_GEMM_TCGEN05) {
+    if (lda % 4 || ldb % 4 || K < 8) return fail(NGB_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 GEMM");
+    use_tc = true;
+  } else if (engine == NGB_GEMM_AUTO) {
+    use_tc = tc::gemm_tc_eligible(transA, transB, M, N, K, lda, ldb, ldc) && aligned16(A) && aligned16(B);
+  }
+  if (use_tc) return tc::gemm_tc(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, st);
+  return gemm_simt(transA, transB, M, N, K, A, lda, B, ldb, C, ldc, accumulate, st);
+}

@@ -1,0 +1,183 @@
+"""Helpers for the `-m gpu` parity tests: call libngb200.so through its C ABI (include/ngb200.h) on torch CUDA
+buffers and hand back NumPy arrays.  torch is used only for device memory and the stream."""
+import ctypes
+
+import numpy as np
+import torch
+
+from neograd_b200 import _backend as B
+
+lib = B.lib
+
+
+def dev(a, dtype=torch.float32):
+  """host array -> contiguous device tensor"""
+  return torch.as_tensor(np.ascontiguousarray(a)).to(device='cuda', dtype=dtype).contiguous()
+
+
+def host(t):
+  torch.cuda.synchronize()
+  return t.detach().cpu().numpy()
+
+
+def ptr(t):
+  return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def st():
+  return ctypes.c_void_p(B.stream())
+
+
+def call(name, *args):
+  B.ensure_runtime()
+  B.check(getattr(lib, name)(*args))
+
+
+def empty(*shape):
+  return torch.empty(shape, device='cuda', dtype=torch.float32)
+
+
+def f32(a):
+  """fp32-representable float64 copy: both sides of every parity test see the same values."""
+  return np.asarray(a, np.float32).astype(np.float64)
+
+
+def gemm(a, b, ta=False, tb=False, engine=B.GEMM_AUTO, accumulate=None):
+  """returns op(a) @ op(b) computed by ngb_gemm; a, b are host arrays as stored."""
+  A, Bm = dev(a), dev(b)
+  M = a.shape[1] if ta else a.shape[0]
+  K = a.shape[0] if ta else a.shape[1]
+  N = b.shape[0] if tb else b.shape[1]
+  if accumulate is not None:
+    C = dev(accumulate)
+    acc = 1
+  else:
+    C = torch.full((M, N), float('nan'), device='cuda', dtype=torch.float32)
+    acc = 0
+  call('ngb_gemm', engine, int(ta), int(tb), M, N, K, ptr(A), a.shape[1], ptr(Bm), b.shape[1], ptr(C), N, acc, st())
+  return host(C)
+
+
+def conv_fprop(x, w, b, pad, stride):
+  N, C, H, W = x.shape
+  O, _, KH, KW = w.shape
+  Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+  y = torch.full((N, O, Ho, Wo), float('nan'), device='cuda')
+  X, Wt, Bs = dev(x), dev(w), dev(b)
+  call('ngb_conv_fprop', ptr(X), ptr(Wt), ptr(Bs), ptr(y), N, C, H, W, O, KH, KW, pad, stride, st())
+  return host(y)
+
+
+def conv_dgrad(ug, w, xshape, pad, stride):
+  N, C, H, W = xshape
+  O, _, KH, KW = w.shape
+  dx = torch.full((N, C, H, W), float('nan'), device='cuda')
+  U, Wt = dev(ug), dev(w)
+  call('ngb_conv_dgrad', ptr(U), ptr(Wt), ptr(dx), N, C, H, W, O, KH, KW, pad, stride, 0, st())
+  return host(dx)
+
+
+def conv_wgrad(ug, x, wshape, pad, stride):
+  N, C, H, W = x.shape
+  O, _, KH, KW = wshape
+  dw = torch.full(tuple(wshape), float('nan'), device='cuda')
+  U, X = dev(ug), dev(x)
+  call('ngb_conv_wgrad', ptr(U), ptr(X), ptr(dw), N, C, H, W, O, KH, KW, pad, stride, 0, st())
+  return host(dw)
+
+
+def conv_bgrad(ug):
+  N, O = ug.shape[:2]
+  hw = int(np.prod(ug.shape[2:]))
+  db = torch.full((O,), float('nan'), device='cuda')
+  U = dev(ug)
+  call('ngb_conv_bgrad', ptr(U), ptr(db), N, O, hw, 0, st())
+  return host(db)
+
+
+def maxpool_fwd(x, k, pad, stride):
+  H, W = x.shape[-2:]
+  outer = int(np.prod(x.shape[:-2]))
+  Ho, Wo = (H + 2 * pad - k[0]) // stride + 1, (W + 2 * pad - k[1]) // stride + 1
+  X = dev(x)
+  y = torch.full(x.shape[:-2] + (Ho, Wo), float('nan'), device='cuda')
+  idx = torch.full(x.shape[:-2] + (Ho, Wo), 255, device='cuda', dtype=torch.uint8)
+  call('ngb_maxpool_fwd', ptr(X), ptr(y), ptr(idx), outer, H, W, k[0], k[1], pad, stride, st())
+  return host(y), host(idx)
+
+
+def maxpool_bwd(ug, idx, xshape, k, pad, stride):
+  H, W = xshape[-2:]
+  outer = int(np.prod(xshape[:-2]))
+  U, I = dev(ug), dev(idx, torch.uint8)
+  dx = torch.full(tuple(xshape), float('nan'), device='cuda')
+  call('ngb_maxpool_bwd', ptr(U), ptr(I), ptr(dx), outer, H, W, k[0], k[1], pad, stride, 0, st())
+  return host(dx)
+
+
+def binary_fwd(op, a, b):
+  a, b = np.asarray(a), np.asarray(b)
+  out_shape = np.broadcast_shapes(a.shape, b.shape)
+  A, Bm = dev(a), dev(b)
+  out = torch.full(out_shape, float('nan'), device='cuda')
+  ash, ar = B.shape_arg(a.shape)
+  bsh, br = B.shape_arg(b.shape)
+  call('ngb_ew_binary_fwd', op, ptr(A), 0.0, ash, ar, ptr(Bm), 0.0, bsh, br, ptr(out), st())
+  return host(out)
+
+
+def binary_bwd(op, side, a, b, ug, accumulate=None):
+  a, b = np.asarray(a), np.asarray(b)
+  A, Bm, U = dev(a), dev(b), dev(ug)
+  shape = (a.shape, b.shape)[side]
+  if accumulate is not None:
+    g = dev(accumulate)
+    acc = 1
+  else:
+    g = torch.full(shape, float('nan'), device='cuda')
+    acc = 0
+  ash, ar = B.shape_arg(a.shape)
+  bsh, br = B.shape_arg(b.shape)
+  call('ngb_ew_binary_bwd', op, side, ptr(U), ptr(A), 0.0, ash, ar, ptr(Bm), 0.0, bsh, br, ptr(g), acc, st())
+  return host(g)
+
+
+def unary_fwd(op, x, alpha=0.01):
+  X = dev(x)
+  out = torch.full(X.shape, float('nan'), device='cuda')
+  call('ngb_ew_unary_fwd', op, alpha, ptr(X), ptr(out), X.numel(), st())
+  return host(out)
+
+
+def unary_bwd(op, x, ug, alpha=0.01):
+  X, U = dev(x), dev(ug)
+  out = torch.full(X.shape, float('nan'), device='cuda')
+  call('ngb_ew_unary_bwd', op, alpha, ptr(X), ptr(U), ptr(out), X.numel(), 0, st())
+  return host(out)
+
+
+def reduce_sum(x, axes):
+  x = np.asarray(x)
+  mask = 0
+  for ax in axes:
+    mask |= 1 << (ax % x.ndim)
+  out_shape = tuple(s for i, s in enumerate(x.shape) if not (mask >> i) & 1)
+  X = dev(x)
+  out = torch.full(out_shape, float('nan'), device='cuda')
+  sh, r = B.shape_arg(x.shape)
+  call('ngb_reduce_sum', ptr(X), sh, r, mask, ptr(out), 0, st())
+  return host(out)
+
+
+def softmax_ce(logits, targets, axis):
+  sh = logits.shape
+  outer = int(np.prod(sh[:axis]))
+  L = sh[axis]
+  inner = int(np.prod(sh[axis + 1:]))
+  n = 1 if len(sh) in (0, 1) else sh[0]
+  Z, T = dev(logits), dev(targets)
+  loss = torch.full((1,), float('nan'), device='cuda')
+  dz = torch.full(sh, float('nan'), device='cuda')
+  call('ngb_softmax_ce_fwd', ptr(Z), ptr(T), outer, L, inner, 1.0 / n, 1e-9, ptr(loss), st())
+  call('ngb_softmax_ce_bwd', ptr(Z), ptr(T), None, outer, L, inner, 1.0 / n, ptr(dz), 0, st())
+  return float(host(loss)[0]), host(dz)

@@ -1,0 +1,357 @@
+"""GPU parity tests, op level: every entry point of include/ngb200.h against the CPU oracle (oracle/ops.py, pinned
+to the reference by tests/test_oracle_golden.py) and against the committed reference fixtures in tests/golden/.
+
+Tolerances (dist = ||a-b||/(||a||+||b||), the reference's own metric, neograd/autograd/utils.py:153):
+  * fp32 SIMT kernels (elementwise, unbroadcast, sums, SoftmaxCE, optimizers, direct conv, SIMT GEMM): 2e-6
+    (the reference is float64; inputs are fp32-representable, so only fp32 rounding of the arithmetic remains);
+  * tcgen05 TF32 kernels (Dot / conv implicit GEMM): 5e-4 (TF32 operand rounding, fp32 accumulate);
+  * MaxPool values, argmax indices and pool backward: bit-exact.
+"""
+import numpy as np
+import pytest
+
+from conftest import golden_names, load_golden
+from oracle import ops
+
+pytestmark = pytest.mark.gpu
+
+TOL32 = 2e-6
+TOLTF32 = 5e-4
+
+BOPS = {'add': 0, 'sub': 1, 'mul': 2, 'div': 3, 'pow': 4}
+UOPS = {'exp': 0, 'log': 1, 'relu': 2, 'leaky_relu': 3, 'sigmoid': 4, 'tanh': 5}
+
+
+@pytest.fixture(scope='module')
+def U():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  import abi_util
+  return abi_util
+
+
+def close(a, b, tol):
+  a, b = np.asarray(a, float), np.asarray(b, float)
+  assert a.shape == b.shape, (a.shape, b.shape)
+  assert np.all(np.isfinite(a)), 'non-finite values in the device result'
+  d = ops.dist(a, b)
+  assert d <= tol, d
+
+
+def f32(a):
+  return np.asarray(a, np.float32).astype(np.float64)
+
+
+# ------------------------------------------------------------------------------------------------- elementwise
+@pytest.mark.parametrize('name', golden_names('binary_'))
+def test_binary_golden(U, name):
+  g = load_golden(name)
+  op = str(g['op'])
+  a, b, ug = f32(g['a']), f32(g['b']), f32(g['ug'])
+  close(U.binary_fwd(BOPS[op], a, b), ops.binary_fwd(op, a, b), TOL32)
+  close(U.binary_bwd(BOPS[op], 0, a, b, ug), ops.binary_bwd(op, 0, a, b, ug), 4 * TOL32)
+  close(U.binary_bwd(BOPS[op], 1, a, b, ug), ops.binary_bwd(op, 1, a, b, ug), 4 * TOL32)
+  # and against the reference's own outputs (inputs differ from fp32 by rounding only)
+  close(U.binary_fwd(BOPS[op], a, b), g['out'], 1e-5)
+
+
+@pytest.mark.parametrize('shape_a,shape_b', [
+  ((4096, 784), (1, 784)),     # bias add / bias grad: column reduction
+  ((8192, 1), (1,)),           # (N,1) op scalar-like: full reduction
+  ((513, 77), (513, 1)),       # row reduction, odd sizes (no 128-bit path)
+  ((3, 5, 7, 9), (5, 1, 9)),   # general pattern
+  ((6, 1, 4), (1, 5, 1)),      # both sides broadcast
+  ((), (33, 3)),               # python-scalar operand
+  ((1000003,), (1000003,)),    # flat, odd length (vector body + scalar tail)
+])
+@pytest.mark.parametrize('op', ['add', 'sub', 'mul', 'div'])
+def test_binary_shapes(U, shape_a, shape_b, op):
+  rng = np.random.default_rng(sum(shape_a) * 31 + sum(shape_b) * 7 + BOPS[op])
+  a = f32(rng.standard_normal(shape_a))
+  b = f32(rng.standard_normal(shape_b) + (3.0 if op == 'div' else 0.0))
+  ug = f32(rng.standard_normal(np.broadcast_shapes(shape_a, shape_b)))
+  close(U.binary_fwd(BOPS[op], a, b), ops.binary_fwd(op, a, b), TOL32)
+  for side in (0, 1):
+    close(U.binary_bwd(BOPS[op], side, a, b, ug), ops.binary_bwd(op, side, a, b, ug), 4 * TOL32)
+
+
+def test_binary_bwd_accumulates(U):
+  rng = np.random.default_rng(5)
+  a, b = f32(rng.standard_normal((300, 40))), f32(rng.standard_normal((1, 40)))
+  ug, g0 = f32(rng.standard_normal((300, 40))), f32(rng.standard_normal((1, 40)))
+  close(U.binary_bwd(BOPS['mul'], 1, a, b, ug, accumulate=g0), g0 + ops.binary_bwd('mul', 1, a, b, ug), 4 * TOL32)
+
+
+def test_binary_incompatible_shapes_raise(U):
+  with pytest.raises(ValueError):
+    U.binary_fwd(0, np.zeros((2, 3)), np.zeros((4, 5)))
+
+
+@pytest.mark.parametrize('name', golden_names('unary_'))
+def test_unary_golden(U, name):
+  g = load_golden(name)
+  op = str(g['op'])
+  x, ug, alpha = f32(g['x']), f32(g['ug']), float(g['alpha'])
+  close(U.unary_fwd(UOPS[op], x, alpha), ops.unary_fwd(op, x, alpha), TOL32)
+  close(U.unary_bwd(UOPS[op], x, ug, alpha), ops.unary_bwd(op, x, ug, alpha), TOL32)
+  close(U.unary_fwd(UOPS[op], x, alpha), g['out'], 1e-5)
+
+
+@pytest.mark.parametrize('op', ['relu', 'leaky_relu', 'sigmoid', 'exp', 'tanh'])
+def test_unary_large_and_relu_at_zero(U, op):
+  rng = np.random.default_rng(3)
+  x = f32(rng.standard_normal((4096, 257)))
+  x[::7, ::3] = 0.0                      # activations.py:31 / 216: the gradient at exactly 0 is 1
+  ug = f32(rng.standard_normal(x.shape))
+  close(U.unary_fwd(UOPS[op], x), ops.unary_fwd(op, x), TOL32)
+  got = U.unary_bwd(UOPS[op], x, ug)
+  close(got, ops.unary_bwd(op, x, ug), TOL32)
+  if op in ('relu', 'leaky_relu'):
+    assert np.array_equal(got[::7, ::3], ug[::7, ::3].astype(np.float32))
+
+
+@pytest.mark.parametrize('name', golden_names('sum_'))
+def test_sum_golden(U, name):
+  g = load_golden(name)
+  axis = None if int(g['axis']) == -99 else int(g['axis'])
+  x = f32(g['x'])
+  axes = tuple(range(x.ndim)) if axis is None else (axis,)
+  close(U.reduce_sum(x, axes), ops.sum_fwd(x, axis), TOL32)
+
+
+@pytest.mark.parametrize('shape,axes', [((8192, 10), (0,)), ((8192, 10), (1,)), ((1 << 20,), (0,)), ((33, 65, 17), (0, 2)),
+                                        ((256, 16, 8, 8), (0, 2, 3))])
+def test_reduce_sum_shapes(U, shape, axes):
+  x = f32(np.random.default_rng(9).standard_normal(shape) + 1.0)   # mean 1: no catastrophic cancellation in the reference sum
+  close(U.reduce_sum(x, axes), x.sum(axis=axes), 4 * TOL32)
+
+
+# ------------------------------------------------------------------------------------------------- Dot
+@pytest.mark.parametrize('name', golden_names('dot_'))
+def test_dot_golden(U, name):
+  g = load_golden(name)
+  a, b, ug = f32(g['a']), f32(g['b']), f32(g['ug'])
+  for eng, tol in ((1, TOL32), (0, TOLTF32)):
+    close(U.gemm(a, b, engine=eng), ops.dot_fwd(a, b), tol)
+    close(U.gemm(ug, b, tb=True, engine=eng), ops.dot_dgrad(ug, b), tol)
+    close(U.gemm(a, ug, ta=True, engine=eng), ops.dot_wgrad(a, ug), tol)
+
+
+GEMM_SHAPES = [   # (M, K, N): the Linear layers of configs C1-C4 + tile-edge cases
+  (750, 2, 100), (750, 100, 1), (200, 36, 10), (4096, 16, 120), (4096, 120, 84), (4096, 84, 10), (4096, 256, 120),
+  (8192, 784, 512), (8192, 512, 256), (8192, 256, 784), (8192, 256, 1),
+  (128, 32, 64), (129, 33, 65), (1000, 200, 300), (257, 1024, 96),
+]
+
+
+@pytest.mark.parametrize('M,K,N', GEMM_SHAPES)
+def test_gemm_simt(U, M, K, N):
+  rng = np.random.default_rng(M * 7 + K * 3 + N)
+  a, b, ug = f32(rng.standard_normal((M, K))), f32(rng.standard_normal((K, N)) / np.sqrt(K)), f32(rng.standard_normal((M, N)))
+  close(U.gemm(a, b, engine=1), a @ b, TOL32)
+  close(U.gemm(ug, b, tb=True, engine=1), ug @ b.T, TOL32)
+  close(U.gemm(a, ug, ta=True, engine=1), a.T @ ug, TOL32)
+
+
+@pytest.mark.parametrize('M,K,N', [s for s in GEMM_SHAPES if s[1] % 4 == 0 and s[2] % 4 == 0 and s[1] >= 8])
+def test_gemm_tcgen05(U, M, K, N):
+  """The three Dot passes on the tensor cores (forced engine), incl. split-K wgrad and ragged tiles."""
+  rng = np.random.default_rng(M + K * 5 + N * 11)
+  a, b, ug = f32(rng.standard_normal((M, K))), f32(rng.standard_normal((K, N)) / np.sqrt(K)), f32(rng.standard_normal((M, N)))
+  close(U.gemm(a, b, engine=2), a @ b, TOLTF32)                 # basics.py:194
+  if N % 4 == 0:
+    close(U.gemm(ug, b, tb=True, engine=2), ug @ b.T, TOLTF32)  # basics.py:206
+  close(U.gemm(a, ug, ta=True, engine=2), a.T @ ug, TOLTF32)    # basics.py:207
+
+
+def test_gemm_tcgen05_exact_on_tf32_inputs(U):
+  """With operands already representable in TF32 and small integer-ish values the tensor-core result is exact."""
+  rng = np.random.default_rng(1)
+  a = rng.integers(-4, 5, (256, 64)).astype(np.float64)
+  b = rng.integers(-4, 5, (64, 128)).astype(np.float64)
+  assert np.array_equal(U.gemm(a, b, engine=2), (a @ b).astype(np.float32))
+  assert np.array_equal(U.gemm(a, a, ta=True, engine=2), (a.T @ a).astype(np.float32))
+  assert np.array_equal(U.gemm(b, b, tb=True, engine=2), (b @ b.T).astype(np.float32))
+
+
+def test_gemm_accumulate(U):
+  rng = np.random.default_rng(2)
+  a, b, c = f32(rng.standard_normal((300, 64))), f32(rng.standard_normal((64, 128))), f32(rng.standard_normal((300, 128)))
+  close(U.gemm(a, b, engine=1, accumulate=c), c + a @ b, TOL32)
+  close(U.gemm(a, b, engine=2, accumulate=c), c + a @ b, TOLTF32)
+
+
+def test_gemm_linearity_large(U):
+  """Size-independent property at a C5-sweep size: (A1+A2).B == A1.B + A2.B within TF32 tolerance."""
+  rng = np.random.default_rng(4)
+  M, K, N = 65536, 256, 256
+  a1, a2 = f32(rng.standard_normal((M, K))), f32(rng.standard_normal((M, K)))
+  b = f32(rng.standard_normal((K, N)) / 16)
+  close(U.gemm(a1 + a2, b), U.gemm(a1, b).astype(float) + U.gemm(a2, b), 2 * TOLTF32)
+
+
+# ------------------------------------------------------------------------------------------------- Conv
+@pytest.mark.parametrize('name', golden_names('conv3d_'))
+def test_conv3d_golden(U, name):
+  g = load_golden(name)
+  p, s = int(g['pad']), int(g['stride'])
+  x, w, b, ug = f32(g['x']), f32(g['w']), f32(g['b']), f32(g['ug'])
+  close(U.conv_fprop(x, w, b, p, s), ops.conv3d_fwd(x, w, b, p, s), TOL32)
+  close(U.conv_dgrad(ug, w, x.shape, p, s), ops.conv3d_dgrad(ug, w, x.shape, p, s), TOL32)
+  close(U.conv_wgrad(ug, x, w.shape, p, s), ops.conv3d_wgrad(ug, x, w.shape, p, s), TOL32)
+  close(U.conv_bgrad(ug), ops.conv3d_bgrad(ug), TOL32)
+  close(U.conv_fprop(x, w, b, p, s), g['out'], 1e-5)
+  close(U.conv_wgrad(ug, x, w.shape, p, s), g['gw'], 1e-5)
+
+
+@pytest.mark.parametrize('name', golden_names('conv2d_'))
+def test_conv2d_golden(U, name):
+  """neograd's single-channel Conv2D (conv.py:121-215) = the C = O = 1 case of the same entry points."""
+  g = load_golden(name)
+  p, s = int(g['pad']), int(g['stride'])
+  x, w, b, ug = f32(g['x']), f32(g['w']), f32(g['b']), f32(g['ug'])
+  x4, w4, b1, ug4 = x[:, None], w[None, None], b.reshape(1), ug[:, None]
+  close(U.conv_fprop(x4, w4, b1, p, s)[:, 0], ops.conv2d_fwd(x, w, b, p, s), TOL32)
+  close(U.conv_dgrad(ug4, w4, x4.shape, p, s)[:, 0], ops.conv2d_dgrad(ug, w, x.shape, p, s), TOL32)
+  close(U.conv_wgrad(ug4, x4, w4.shape, p, s)[0, 0], ops.conv2d_wgrad(ug, x, w.shape, p, s), TOL32)
+  close(U.conv_bgrad(ug4)[0], ops.conv2d_bgrad(ug), TOL32)
+  close(U.conv_fprop(x4, w4, b1, p, s)[:, 0], g['out'], 1e-5)
+
+
+CONV_CASES = [   # N, C, H, W, O, KH, KW, pad, stride
+  (64, 1, 28, 28, 6, 5, 5, 0, 1),      # LeNet-B conv1
+  (64, 6, 12, 12, 16, 5, 5, 0, 1),     # LeNet-B conv2
+  (32, 1, 28, 28, 1, 5, 5, 0, 1),      # LeNet-A conv1 (neograd Conv2D)
+  (200, 1, 8, 8, 1, 3, 3, 0, 1),       # digits
+  (3, 2, 11, 14, 3, 2, 3, 2, 2),       # rectangular filter, pad 2, stride 2
+  (2, 3, 9, 9, 4, 3, 3, 1, 1),
+  (2, 5, 17, 13, 9, 4, 4, 0, 3),       # stride leftovers: unvisited cells get zero gradient (conv.py:40-42, 300)
+  (4, 16, 16, 16, 32, 3, 3, 1, 1),     # multi-channel 3x3 p1 (C5 family, small)
+]
+
+
+@pytest.mark.parametrize('N,C,H,W,O,KH,KW,pad,stride', CONV_CASES)
+def test_conv_direct(U, N, C, H, W, O, KH, KW, pad, stride):
+  rng = np.random.default_rng(N + C * 3 + H * 5 + O * 7 + KH)
+  x = f32(rng.standard_normal((N, C, H, W)))
+  w = f32(rng.standard_normal((O, C, KH, KW)) / np.sqrt(C * KH * KW))
+  b = f32(rng.standard_normal(O))
+  y = ops.conv3d_fwd(x, w, b, pad, stride)
+  ug = f32(rng.standard_normal(y.shape))
+  close(U.conv_fprop(x, w, b, pad, stride), y, TOL32)
+  close(U.conv_dgrad(ug, w, x.shape, pad, stride), ops.conv3d_dgrad(ug, w, x.shape, pad, stride), TOL32)
+  close(U.conv_wgrad(ug, x, w.shape, pad, stride), ops.conv3d_wgrad(ug, x, w.shape, pad, stride), 2 * TOL32)
+  close(U.conv_bgrad(ug), ops.conv3d_bgrad(ug), 2 * TOL32)
+
+
+def test_conv_errors(U):
+  x, w, b = np.zeros((1, 1, 5, 5)), np.zeros((1, 1, 3, 3)), np.zeros(1)
+  with pytest.raises(ValueError):
+    U.conv_fprop(x, w, b, 0, 0)        # conv.py:33 (stride >= 1)
+  with pytest.raises(ValueError):
+    U.conv_fprop(x, w, b, -1, 1)       # conv.py:34 (padding >= 0)
+
+
+# ------------------------------------------------------------------------------------------------- MaxPool
+@pytest.mark.parametrize('name', golden_names('maxpool'))
+def test_maxpool_golden_bit_exact(U, name):
+  g = load_golden(name)
+  ks, p, s = (int(g['kh']), int(g['kw'])), int(g['pad']), int(g['stride'])
+  x, ug = f32(g['x']), f32(g['ug'])
+  y, idx = U.maxpool_fwd(x, ks, p, s)
+  y_ref, idx_ref = ops.maxpool_fwd(x, ks, p, s)
+  assert np.array_equal(y, y_ref.astype(np.float32))
+  assert np.array_equal(idx, idx_ref)                   # bit-exact argmax, first maximum, zero padding participates
+  gx = U.maxpool_bwd(ug, idx, x.shape, ks, p, s)
+  assert np.array_equal(gx, ops.maxpool_bwd(ug, x, ks, p, s).astype(np.float32))
+  if np.array_equal(x, g['x']):                         # fixture inputs representable in fp32 -> reference outputs too
+    assert np.array_equal(y, g['out'].astype(np.float32))
+    assert np.array_equal(np.where(g['covered'], gx, 0.0), g['gx'].astype(np.float32))
+
+
+@pytest.mark.parametrize('shape,k,pad,stride', [
+  ((512, 24, 24), (2, 2), 0, 2), ((512, 8, 8), (2, 2), 0, 2), ((64, 6, 24, 24), (2, 2), 0, 2), ((64, 16, 8, 8), (2, 2), 0, 2),
+  ((2, 3, 12, 15), (3, 3), 0, 3), ((3, 9, 10), (3, 2), 1, 2), ((2, 7, 7), (3, 3), 0, 1), ((5, 13, 11), (2, 2), 0, 2),
+])
+def test_maxpool_bit_exact_with_ties(U, shape, k, pad, stride):
+  rng = np.random.default_rng(sum(shape) + k[0])
+  x = f32(rng.standard_normal(shape))
+  x = np.maximum(x, 0.0)                 # post-ReLU zeros: many exact ties, incl. all-zero windows
+  x[0] = 1.0                             # an all-equal image
+  x[-1] = -np.abs(x[-1]) - 1.0           # all negative: with padding the zero pad wins (conv.py:399,416)
+  y_ref, idx_ref = ops.maxpool_fwd(x, k, pad, stride)
+  y, idx = U.maxpool_fwd(x, k, pad, stride)
+  assert np.array_equal(y, y_ref.astype(np.float32))
+  assert np.array_equal(idx, idx_ref)
+  ug = f32(rng.standard_normal(y.shape))
+  assert np.array_equal(U.maxpool_bwd(ug, idx, shape, k, pad, stride), ops.maxpool_bwd(ug, x, k, pad, stride).astype(np.float32))
+
+
+# ------------------------------------------------------------------------------------------------- SoftmaxCE
+@pytest.mark.parametrize('name', golden_names('sce_'))
+def test_softmax_ce_golden(U, name):
+  g = load_golden(name)
+  axis = int(g['axis'])
+  z, t = f32(g['logits']), f32(g['targets'])
+  loss, dz = U.softmax_ce(z, t, axis)
+  close(loss, ops.softmax_ce_fwd(z, t, axis), TOL32)
+  close(dz, ops.softmax_ce_bwd(z, t, axis), TOL32)
+  close(loss, g['out'], 1e-5)
+
+
+def test_softmax_ce_batch(U):
+  rng = np.random.default_rng(6)
+  z = f32(rng.standard_normal((4096, 10)) * 3)
+  t = np.eye(10)[rng.integers(0, 10, 4096)]
+  loss, dz = U.softmax_ce(z, t, 1)
+  close(loss, ops.softmax_ce_fwd(z, t, 1), TOL32)
+  close(dz, ops.softmax_ce_bwd(z, t, 1), TOL32)
+
+
+# ------------------------------------------------------------------------------------------------- optimizers
+@pytest.mark.parametrize('name', ['adam', 'gd', 'momentum', 'rmsprop'])
+def test_optimizers_golden(U, name):
+  """4 steps on the reference's own trajectories (fixtures from the unmodified nn/optim.py)."""
+  import torch
+  g = load_golden('optim_' + name)
+  for i in range(3):
+    p = U.dev(np.atleast_1d(f32(g[f'p0_{i}'])).ravel())
+    s1, s2 = torch.zeros_like(p), torch.zeros_like(p)
+    ref = f32(g[f'p0_{i}'])
+    r1 = r2 = 0.0
+    for step in range(4):
+      gr = f32(g[f'g{step}_{i}'])
+      G = U.dev(np.atleast_1d(gr).ravel())
+      n = p.numel()
+      if name == 'adam':
+        t = step + 1
+        U.call('ngb_adam_step', U.ptr(p), U.ptr(G), U.ptr(s1), U.ptr(s2), n, 0.05, 0.9, 0.999, 1e-8,
+               1.0 / (1 - 0.9 ** t), 1.0 / (1 - 0.999 ** t), 1.0, U.st())
+        ref, r1, r2 = ops.adam_step(ref, gr, r1, r2, t, 0.05)
+      elif name == 'gd':
+        U.call('ngb_sgd_step', U.ptr(p), U.ptr(G), n, 0.1, 1.0, U.st())
+        ref = ops.sgd_step(ref, gr, 0.1)
+      elif name == 'momentum':
+        U.call('ngb_momentum_step', U.ptr(p), U.ptr(G), U.ptr(s1), n, 0.1, 0.9, 1.0, U.st())
+        ref, r1 = ops.momentum_step(ref, gr, r1, 0.1)
+      else:
+        U.call('ngb_rmsprop_step', U.ptr(p), U.ptr(G), U.ptr(s1), n, 0.01, 0.9, 1e-8, 1.0, U.st())
+        ref, r1 = ops.rmsprop_step(ref, gr, r1, 0.01)
+      close(U.host(p).reshape(np.shape(ref)), ref, 1e-5)
+      close(U.host(p).reshape(np.shape(ref)), g[f'p{step + 1}_{i}'], 1e-5)
+
+
+def test_adam_large_flat_arena(U):
+  import torch
+  rng = np.random.default_rng(8)
+  n = 1268241                               # C4 GAN parameter count (odd -> scalar tail)
+  p0, g0 = f32(rng.standard_normal(n)), f32(rng.standard_normal(n) * 0.1)
+  p, G = U.dev(p0), U.dev(g0)
+  m, v = torch.zeros_like(p), torch.zeros_like(p)
+  U.call('ngb_adam_step', U.ptr(p), U.ptr(G), U.ptr(m), U.ptr(v), n, 5e-3, 0.9, 0.999, 1e-8, 1 / (1 - 0.9), 1 / (1 - 0.999), 1.0,
+         U.st())
+  ref, rm, rv = ops.adam_step(p0, g0, 0.0, 0.0, 1, 5e-3)
+  close(U.host(p), ref, TOL32)
+  close(U.host(m), rm, TOL32)
+  close(U.host(v), rv, TOL32)
