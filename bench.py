@@ -1,0 +1,365 @@
+#!/usr/bin/env python
+"""bench.py -- CNN training throughput of the neograd hot path on B200 (BASELINE.json: "CNN train samples/s").
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (one rank per GPU under torchrun)
+  python bench.py --impl reference --steps K --warmup W     # the reference's CPU algorithm (oracle port) on host cores
+
+A "step" is one full training iteration of the hot path over one synthetic batch: zero_grad, forward, SoftmaxCE,
+backward, (gradient allreduce,) fused Adam -- README.md:109-115 of the reference.  Workload (config.workload):
+LeNet-B = Conv3D(1,6,5x5) ReLU MaxPool3D(2,2) Conv3D(6,16,5x5) ReLU MaxPool3D(2,2) Linear 256-120-84-10 on synthetic
+28x28x1 images, batch 4096 PER GPU (weak scaling), fp32 / TF32.
+
+Reported on one JSON line:
+  value        whole-job samples/s with the batch resident in HBM; every step is the CUDA-graph replay of the captured
+               step (all kernels run every step; nothing is cached), timed with CUDA events per step, L2 flushed
+               between timed steps, max over ranks
+  e2e          same metric through the public API with HOST inputs: per step a pinned H2D copy of the batch, the step,
+               and a D2H read of the loss; wall clock between synchronised barriers
+  eager        same step dispatched op by op from Python (no graph capture), for comparison
+  roofline     the kernel with the largest share of the step: algorithmic bytes / its mean CUDA-event time
+  cpu_baseline the oracle port (float64 NumPy restatement of the reference algorithm) on a bounded sample, rank 0, N=1
+"""
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+
+BATCH = 4096
+WORKLOADS = ('lenet_b', 'lenet_a')
+
+
+def peaks():
+  p = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'source': 'fallback'}
+  try:
+    with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as f:
+      m = json.load(f)
+    p.update(hbm_gbs=float(m['hbm_gbs']), bf16_tflops=float(m['bf16_tflops']), source='measured')
+  except Exception:
+    pass
+  p['tf32_tflops'] = p['bf16_tflops'] / 2   # B200 TF32 dense rate is half the BF16 rate (no direct measurement yet)
+  return p
+
+
+# --------------------------------------------------------------------------------------------- reference arm (CPU)
+def oracle_samples_per_s(workload, batch, steps, warmup):
+  from oracle import models
+  kind = workload[-1]
+  rng = np.random.default_rng(0)
+  x = rng.standard_normal((batch, 28, 28) if kind == 'a' else (batch, 1, 28, 28))
+  y = np.eye(10)[rng.integers(0, 10, batch)]
+  net = (models.lenet_a if kind == 'a' else models.lenet_b)(np.random.default_rng(1))
+  opt = models.Adam(net, 1e-3)
+  for _ in range(warmup):
+    models.train_step(net, opt, 'softmax_ce', x, y)
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    models.train_step(net, opt, 'softmax_ce', x, y)
+  dt = time.perf_counter() - t0
+  return batch * steps / dt, dt / steps
+
+
+def run_reference(args):
+  rank = int(os.environ.get('RANK', '0'))
+  if rank != 0:
+    return
+  batch = 1024
+  cores = len(os.sched_getaffinity(0))
+  v, per = oracle_samples_per_s(args.workload, batch, args.steps, max(args.warmup, 1))
+  sample = f'{args.steps} steps of batch {batch} (of {BATCH}) of {args.workload}, float64 NumPy/OpenBLAS default threads'
+  print(json.dumps({
+    'impl': 'reference', 'metric': 'cnn_train_samples_per_s', 'value': v, 'unit': 'samples/s', 'n_gpus': args.gpus,
+    'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': per * 1e3, 'higher_is_better': True, 'scaling': 'weak',
+    'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+    'config': {'workload': args.workload, 'batch_per_step': batch, 'note': 'oracle port of the reference CPU path (the reference is pure Python/NumPy and is not present on the GPU box)'},
+    'cpu_baseline': {'value': v, 'unit': 'samples/s', 'cores': cores, 'kind': 'port', 'sample': sample},
+    'e2e': {'value': v, 'unit': 'samples/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+  }))
+
+
+# --------------------------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+  def __init__(self, index):
+    super().__init__(daemon=True)
+    self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      self.nv = pynvml
+      self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+      self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+    except Exception:
+      self.nv = None
+
+  def run(self):
+    if self.nv is None:
+      return
+    nv = self.nv
+    names = {'hw_slowdown': getattr(nv, 'nvmlClocksEventReasonHwSlowdown', 0x8),
+             'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
+             'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
+             'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+    while not self.stop_flag:
+      try:
+        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+        try:
+          r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+        except Exception:
+          r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+        for k, bit in names.items():
+          if r & bit:
+            self.reasons.add(k)
+      except Exception:
+        pass
+      time.sleep(0.05)
+
+  def result(self):
+    self.stop_flag = True
+    if not self.samples:
+      return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': []}
+    return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+
+
+# --------------------------------------------------------------------------------------------- algorithmic work per call
+def _numel(shape_arr, rank):
+  n = 1
+  for i in range(rank):
+    n *= shape_arr[i]
+  return n
+
+
+def call_work(name, a):
+  """(algorithmic bytes, flops) of one C-ABI call, from its arguments (formulas: SURVEY section 8d / DESIGN.md)."""
+  if name == 'ngb_gemm':
+    M, N, K = a[3], a[4], a[5]
+    return 4 * (M * K + K * N + M * N), 2 * M * N * K
+  if name in ('ngb_conv_fprop', 'ngb_conv_dgrad', 'ngb_conv_wgrad'):
+    o = 4 if name == 'ngb_conv_fprop' else 3
+    N, C, H, W, O, KH, KW, pad, stride = a[o:o + 9]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    return 4 * (N * C * H * W + O * C * KH * KW + N * O * Ho * Wo), 2 * N * O * C * KH * KW * Ho * Wo
+  if name == 'ngb_conv_bgrad':
+    return 4 * (a[2] * a[3] * a[4] + a[3]), a[2] * a[3] * a[4]
+  if name in ('ngb_maxpool_fwd', 'ngb_maxpool_bwd'):
+    outer, H, W, KH, KW, pad, stride = a[3:10]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    return 4 * outer * H * W + 5 * outer * Ho * Wo, outer * Ho * Wo * KH * KW
+  if name == 'ngb_ew_unary_fwd':
+    return 8 * a[4], a[4]
+  if name == 'ngb_ew_unary_bwd':
+    return 12 * a[5], a[5]
+  if name == 'ngb_ew_binary_fwd':
+    na, nb = (_numel(a[3], a[4]) if a[1] else 0), (_numel(a[7], a[8]) if a[5] else 0)
+    sa = [a[3][i] for i in range(a[4])]
+    sb = [a[7][i] for i in range(a[8])]
+    no = int(np.prod(np.broadcast_shapes(tuple(sa), tuple(sb)))) if (sa or sb) else 1
+    return 4 * (na + nb + no), no
+  if name == 'ngb_ew_binary_bwd':
+    sa = [a[5][i] for i in range(a[6])]
+    sb = [a[9][i] for i in range(a[10])]
+    nu = int(np.prod(np.broadcast_shapes(tuple(sa), tuple(sb)))) if (sa or sb) else 1
+    ng_ = int(np.prod((sa, sb)[a[1]])) if (sa, sb)[a[1]] else 1
+    other = 0
+    if a[0] in (2, 3, 4):   # mul / div / pow read the operands
+      other = (int(np.prod(sa)) if a[3] else 0) + (int(np.prod(sb)) if a[7] else 0)
+    return 4 * (nu + other + ng_), nu
+  if name in ('ngb_adam_step', 'ngb_adam_step_dev'):
+    return 28 * a[4], 12 * a[4]
+  if name == 'ngb_sgd_step':
+    return 12 * a[2], 2 * a[2]
+  if name in ('ngb_softmax_ce_fwd', 'ngb_softmax_ce_bwd'):
+    o = 2 if name == 'ngb_softmax_ce_fwd' else 3
+    n = a[o] * a[o + 1] * a[o + 2]
+    return (8 if name == 'ngb_softmax_ce_fwd' else 12) * n, 10 * n
+  if name in ('ngb_fill',):
+    return 4 * a[2], 0
+  if name in ('ngb_axpy',):
+    return 12 * a[3], 2 * a[3]
+  if name == 'ngb_copy':
+    return 8 * a[2], 0
+  if name == 'ngb_reduce_sum':
+    return 4 * _numel(a[1], a[2]), _numel(a[1], a[2])
+  return 0, 0
+
+
+# --------------------------------------------------------------------------------------------- device arm
+def run_device(args):
+  import torch
+  import neograd_b200 as ng
+  from neograd_b200 import _backend as B
+  from neograd_b200 import distributed as dist
+  from neograd_b200.capture import CapturedStep, copy_from_host
+  from neograd_b200.configs import lenet_synthetic, train_step
+
+  world = int(os.environ.get('WORLD_SIZE', '1'))
+  rank = int(os.environ.get('RANK', '0'))
+  local = int(os.environ.get('LOCAL_RANK', '0'))
+  torch.cuda.set_device(local)
+  if world > 1:
+    dist.init('nccl')
+  pk = peaks()
+  kind = args.workload[-1]
+
+  # every rank: its own shard of the global batch (weak scaling: BATCH per GPU), identical initial parameters
+  model, x, y = lenet_synthetic(kind, BATCH, seed=100 + rank)
+  if world > 1:
+    dist.broadcast_params(model.parameters())
+  X, Y = ng.tensor(x), ng.tensor(y)
+  optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
+  loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+
+  def step():
+    return train_step(model, optim, loss_fn, X, Y)
+
+  def barrier():
+    torch.cuda.synchronize()
+    if world > 1:
+      torch.distributed.barrier()
+    torch.cuda.synchronize()
+
+  def max_over_ranks(v):
+    if world == 1:
+      return v
+    t = torch.tensor([v], device='cuda', dtype=torch.float64)
+    torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    return float(t.item())
+
+  flush_buf = torch.empty(256 << 20, device='cuda', dtype=torch.uint8)   # 256 MiB > 126 MB L2
+
+  def timed(fn, steps):
+    """sum of per-step CUDA-event times (ms), L2 flushed before every step"""
+    evs = []
+    barrier()
+    for _ in range(steps):
+      flush_buf.zero_()
+      e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+      e0.record()
+      fn()
+      e1.record()
+      evs.append((e0, e1))
+    barrier()
+    return sum(a.elapsed_time(b) for a, b in evs)
+
+  # ---- eager warm-up, then capture the whole step in a CUDA graph
+  for _ in range(max(args.warmup, 3)):
+    step()
+  torch.cuda.synchronize()
+  n0 = B.lib.ngb_launch_count()
+  step()
+  launches_per_step = int(B.lib.ngb_launch_count() - n0)
+  captured = CapturedStep(step, warmup=2)
+  for _ in range(max(args.warmup, 3)):
+    captured()
+
+  clocks = ClockSampler(local)
+  clocks.start()
+  graph_ms = max_over_ranks(timed(captured, args.steps))
+  eager_ms = max_over_ranks(timed(step, args.steps))
+  clk = clocks.result()
+
+  # ---- e2e: host inputs -> pinned H2D copy -> step -> D2H loss, wall clock
+  xh, yh = torch.from_numpy(x).pin_memory(), torch.from_numpy(y).pin_memory()
+  loss_host = torch.empty((), dtype=torch.float32).pin_memory()
+
+  def e2e_step():
+    copy_from_host(X, xh)
+    copy_from_host(Y, yh)
+    loss = captured()
+    loss_host.copy_(loss.data.t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return float(loss_host)
+
+  for _ in range(3):
+    e2e_step()
+  barrier()
+  t0 = time.perf_counter()
+  for _ in range(args.steps):
+    last_loss = e2e_step()
+  barrier()
+  e2e_s = max_over_ranks(time.perf_counter() - t0)
+
+  # ---- per-kernel breakdown of one eager step (CUDA events around every C-ABI call), rank 0
+  roofline, breakdown = None, None
+  if rank == 0:
+    reps = 5
+    with B.profile_calls() as prof:
+      for _ in range(reps):
+        step()
+    summ = prof.summary()
+    total_ms = sum(d['ms'] for d in summ.values())
+    breakdown = {k: {'calls_per_step': d['calls'] // reps, 'ms_per_step': d['ms'] / reps, 'share': d['ms'] / total_ms}
+                 for k, d in summ.items()}
+    # dominant single launch site: group the top entry point's calls by identical shape arguments
+    top = next(iter(summ))
+    groups = {}
+    for a, ms in summ[top]['items']:
+      key = tuple(v for v in a if isinstance(v, int))
+      g = groups.setdefault(key, {'ms': 0.0, 'n': 0, 'args': a})
+      g['ms'] += ms
+      g['n'] += 1
+    gkey, g = max(groups.items(), key=lambda kv: kv[1]['ms'])
+    by, fl = call_work(top, g['args'])
+    mean_s = g['ms'] / g['n'] * 1e-3
+    ridge = pk['tf32_tflops'] * 1e12 / (pk['hbm_gbs'] * 1e9)
+    if fl / max(by, 1) > ridge:
+      roofline = {'kernel': top, 'bound': 'tensor', 'achieved': fl / mean_s / 1e12, 'peak': pk['tf32_tflops'], 'unit': 'TFLOP/s'}
+    else:
+      roofline = {'kernel': top, 'bound': 'hbm', 'achieved': by / mean_s / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
+    roofline.update(frac=roofline['achieved'] / roofline['peak'], traffic=None, peak_source=pk['source'],
+                    algorithmic_bytes=by, algorithmic_flops=fl, mean_launch_us=mean_s * 1e6, shape_args=list(gkey),
+                    share_of_eager_step=g['ms'] / total_ms)
+
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    b = 256
+    v, per = oracle_samples_per_s(args.workload, b, 5, 1)
+    cpu = {'value': v, 'unit': 'samples/s', 'cores': len(os.sched_getaffinity(0)), 'kind': 'port',
+           'sample': f'5 steps of batch {b} (of {BATCH}) of {args.workload}: oracle port, float64 NumPy/OpenBLAS default threads'}
+
+  if rank == 0:
+    total_samples = BATCH * world * args.steps
+    out = {
+      'metric': 'cnn_train_samples_per_s', 'value': total_samples / (graph_ms * 1e-3), 'unit': 'samples/s', 'n_gpus': world,
+      'steps': args.steps, 'warmup': max(args.warmup, 3), 'ms_per_step': graph_ms / args.steps, 'higher_is_better': True,
+      'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32 (TF32 tensor-core operands where a Dot qualifies)',
+      'data': 'synthetic',
+      'config': {'workload': f'{args.workload}: LeNet-style CNN, synthetic 28x28x1, fwd+bwd+Adam(1e-3), SoftmaxCE',
+                 'batch_per_gpu': BATCH, 'global_batch': BATCH * world, 'parallelism': f'dp{world}',
+                 'l2': 'flushed (256 MiB memset) between timed steps', 'step_dispatch': 'CUDA-graph replay of the captured step'},
+      'clocks': clk,
+      'e2e': {'value': total_samples / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(x.nbytes + y.nbytes),
+              'd2h_bytes_per_step': 4, 'ms_per_step': e2e_s / args.steps * 1e3, 'last_loss': last_loss},
+      'gpu_launches': captured.launches * args.steps,
+      'launches_per_step': {'graph': captured.launches, 'eager': launches_per_step},
+      'eager': {'value': total_samples / (eager_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': eager_ms / args.steps},
+      'roofline': roofline, 'cpu_baseline': cpu, 'kernel_breakdown_eager': breakdown,
+    }
+    print(json.dumps(out))
+  if world > 1:
+    dist.destroy()
+
+
+def main():
+  ap = argparse.ArgumentParser()
+  ap.add_argument('--gpus', type=int, default=1)
+  ap.add_argument('--steps', type=int, default=20)
+  ap.add_argument('--warmup', type=int, default=3)
+  ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+  ap.add_argument('--workload', default='lenet_b', choices=WORKLOADS)
+  ap.add_argument('--no-cpu-baseline', action='store_true')
+  args = ap.parse_args()
+  if args.impl == 'reference':
+    run_reference(args)
+  else:
+    run_device(args)
+
+
+if __name__ == '__main__':
+  main()

@@ -53,6 +53,10 @@ const char* ngb_last_error(void);
 /* Allocates the per-device scratch arena (bytes; 0 = default 64 MiB). Idempotent; must run before graph capture. */
 int ngb_init(int64_t scratch_bytes);
 int ngb_shutdown(void);
+/* Process-wide precision mode: what NGB_GEMM_AUTO (and the conv dispatcher) resolve to.  NGB_GEMM_AUTO (default) = TF32
+ * tensor cores whenever the shape qualifies; NGB_GEMM_SIMT = exact-fp32 CUDA-core kernels everywhere (parity runs,
+ * grad_check); NGB_GEMM_TCGEN05 is not a valid default.  Returns the previous value. */
+int ngb_set_default_engine(int engine);
 /* Which engine ngb_gemm(NGB_GEMM_AUTO) would pick: returns NGB_GEMM_SIMT or NGB_GEMM_TCGEN05. */
 int ngb_gemm_query(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc);
 /* Number of kernels this library has launched in this process (for bench.py's gpu_launches). */
@@ -115,6 +119,9 @@ int ngb_reduce_sum(const float* x, const int64_t* shape, int rank, uint32_t axis
 int ngb_fill(float* dst, float value, int64_t n, ngb_stream_t stream);
 int ngb_axpy(float* dst, const float* src, float alpha, int64_t n, ngb_stream_t stream);  /* dst += alpha*src; tensor.py:301 */
 int ngb_transpose2d(const float* src, float* dst, int64_t rows, int64_t cols, ngb_stream_t stream); /* basics.py:417 */
+int ngb_copy(float* dst, const float* src, int64_t n, ngb_stream_t stream);                /* device-to-device, async */
+/* dst = np.transpose(src, perm) materialised C-contiguous; shape is src's shape, rank <= 6. */
+int ngb_permute(const float* src, float* dst, const int64_t* shape, const int* perm, int rank, ngb_stream_t stream);
 
 /* ---- SoftmaxCE: neograd/nn/loss.py:124-172 ----------------------------------------------------------------- */
 /* logits/targets viewed as (outer, L, inner); softmax along L.  loss (1 float) = -(1/num_examples) * sum t*log(p+eps). */
@@ -125,16 +132,29 @@ int ngb_softmax_ce_bwd(const float* logits, const float* targets, const float* u
                        int64_t inner, float inv_num_examples, float* dlogits, int accumulate,
                        ngb_stream_t stream);                                                /* loss.py:167-170 */
 
+/* ---- Softmax layer: neograd/nn/activations.py:105-180 ------------------------------------------------------- */
+/* x viewed as (outer, L, inner); y = exp(x - max) / sum along L (activations.py:161-174). */
+int ngb_softmax_fwd(const float* x, int64_t outer, int64_t L, int64_t inner, float* y, ngb_stream_t stream);
+/* dx = Jacobian(softmax(x)) . ug per slice (activations.py:131-158) = s * (ug - sum_L(ug * s)). */
+int ngb_softmax_bwd(const float* x, const float* ug, int64_t outer, int64_t L, int64_t inner, float* dx,
+                    int accumulate, ngb_stream_t stream);
+
 /* ---- optimizers: neograd/nn/optim.py ------------------------------------------------------------------------ */
-/* One fused pass over a flat parameter arena.  g is multiplied by grad_scale first (1/world for data parallel). */
-int ngb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                  float epsilon, float inv_bias_corr1, float inv_bias_corr2, float grad_scale,
-                  ngb_stream_t stream);                                                     /* optim.py:168-179, 191-197 */
-int ngb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, ngb_stream_t stream);  /* optim.py:42-47 */
-int ngb_momentum_step(float* p, const float* g, float* m, int64_t n, float lr, float beta, float grad_scale,
+/* One fused pass over a flat parameter arena.  g is multiplied by grad_scale first (1/world for data parallel).
+ * Hyper-parameters are doubles (the reference computes in float64): 1-beta and the bias corrections are formed in
+ * double on the host and only then rounded to fp32.  `t` is the iteration count AFTER the increment of optim.py:169. */
+int ngb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                  double epsilon, int64_t t, double grad_scale, ngb_stream_t stream);       /* optim.py:168-179, 191-197 */
+/* CUDA-graph friendly variant: the iteration count lives in device memory.  With tick != 0, *t_dev is incremented (by a
+ * one-thread launch ahead of the update) before use, so a captured training step replays with the right bias
+ * correction; an optimizer that updates several ranges of one arena ticks on the first range only. */
+int ngb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                      double epsilon, int32_t* t_dev, int tick, double grad_scale, ngb_stream_t stream);
+int ngb_sgd_step(float* p, const float* g, int64_t n, double lr, double grad_scale, ngb_stream_t stream);  /* optim.py:42-47 */
+int ngb_momentum_step(float* p, const float* g, float* m, int64_t n, double lr, double beta, double grad_scale,
                       ngb_stream_t stream);                                                 /* optim.py:63-70, 86-92 */
-int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, float lr, float beta, float epsilon,
-                     float grad_scale, ngb_stream_t stream);                                /* optim.py:112-118, 134-140 */
+int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, double lr, double beta, double epsilon,
+                     double grad_scale, ngb_stream_t stream);                               /* optim.py:112-118, 134-140 */
 
 #ifdef __cplusplus
 }

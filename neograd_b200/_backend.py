@@ -6,7 +6,7 @@ torch.distributed (plumbing); every arithmetic kernel on the hot path lives in t
 """
 import ctypes
 import os
-from ctypes import c_float, c_int, c_int64, c_uint32, c_void_p, c_char_p, POINTER
+from ctypes import c_double, c_float, c_int, c_int64, c_uint32, c_void_p, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libngb200.so')
@@ -30,7 +30,15 @@ def _load():
   return ctypes.CDLL(LIB_PATH)
 
 
-lib = _load()
+_cdll = _load()
+
+
+class _Lib:
+  """Namespace holding one callable per exported function (plain ctypes functions; swapped for timing wrappers by
+  `profile_calls`)."""
+
+
+lib = _Lib()
 
 _i64p = POINTER(c_int64)
 _P = c_void_p
@@ -42,6 +50,7 @@ SIGNATURES = {
   'ngb_last_error': ([], c_char_p),
   'ngb_init': ([c_int64], c_int),
   'ngb_shutdown': ([], c_int),
+  'ngb_set_default_engine': ([c_int], c_int),
   'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
   'ngb_launch_count': ([], c_int64),
   'ngb_gemm': ([c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _S], c_int),
@@ -59,18 +68,24 @@ SIGNATURES = {
   'ngb_fill': ([_P, c_float, c_int64, _S], c_int),
   'ngb_axpy': ([_P, _P, c_float, c_int64, _S], c_int),
   'ngb_transpose2d': ([_P, _P, c_int64, c_int64, _S], c_int),
+  'ngb_copy': ([_P, _P, c_int64, _S], c_int),
+  'ngb_permute': ([_P, _P, _i64p, POINTER(c_int), c_int, _S], c_int),
+  'ngb_softmax_fwd': ([_P, c_int64, c_int64, c_int64, _P, _S], c_int),
+  'ngb_softmax_bwd': ([_P, _P, c_int64, c_int64, c_int64, _P, c_int, _S], c_int),
   'ngb_softmax_ce_fwd': ([_P, _P, c_int64, c_int64, c_int64, c_float, c_float, _P, _S], c_int),
   'ngb_softmax_ce_bwd': ([_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P, c_int, _S], c_int),
-  'ngb_adam_step': ([_P, _P, _P, _P, c_int64] + [c_float] * 7 + [_S], c_int),
-  'ngb_sgd_step': ([_P, _P, c_int64, c_float, c_float, _S], c_int),
-  'ngb_momentum_step': ([_P, _P, _P, c_int64, c_float, c_float, c_float, _S], c_int),
-  'ngb_rmsprop_step': ([_P, _P, _P, c_int64, c_float, c_float, c_float, c_float, _S], c_int),
+  'ngb_adam_step': ([_P, _P, _P, _P, c_int64] + [c_double] * 4 + [c_int64, c_double, _S], c_int),
+  'ngb_adam_step_dev': ([_P, _P, _P, _P, c_int64] + [c_double] * 4 + [_P, c_int, c_double, _S], c_int),
+  'ngb_sgd_step': ([_P, _P, c_int64, c_double, c_double, _S], c_int),
+  'ngb_momentum_step': ([_P, _P, _P, c_int64, c_double, c_double, c_double, _S], c_int),
+  'ngb_rmsprop_step': ([_P, _P, _P, c_int64, c_double, c_double, c_double, c_double, _S], c_int),
 }
 
 for _name, (_args, _res) in SIGNATURES.items():
-  _fn = getattr(lib, _name)   # AttributeError here = the library does not export what the header declares
+  _fn = getattr(_cdll, _name)   # AttributeError here = the library does not export what the header declares
   _fn.argtypes = _args
   _fn.restype = _res
+  setattr(lib, _name, _fn)
 
 if lib.ngb_abi_version() != 1:
   raise ImportError(f"neograd_b200: ABI version mismatch ({lib.ngb_abi_version()} != 1); rebuild libngb200.so")
@@ -108,3 +123,55 @@ def stream():
   """cudaStream_t of torch's current stream (so torch.cuda.graph / stream contexts apply to our launches)."""
   import torch
   return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+
+
+def set_precision(mode):
+  """'tf32' (default): Dot / multi-channel conv run on the tcgen05 tensor cores when the shape qualifies;
+  'fp32': exact-fp32 CUDA-core kernels everywhere (parity runs, grad_check).  Returns the previous mode."""
+  prev = lib.ngb_set_default_engine({'tf32': GEMM_AUTO, 'fp32': GEMM_SIMT}[mode])
+  return 'fp32' if prev == GEMM_SIMT else 'tf32'
+
+
+class profile_calls:
+  """Context manager: brackets every kernel-launching C-ABI call with CUDA events on the launching stream.
+  `records` is a list of (name, args, start_event, end_event); call `summary()` after the block (it synchronises).
+  Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
+  SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
+          'ngb_set_default_engine')
+
+  def __enter__(self):
+    import torch
+    self.records = []
+    self._saved = {}
+    for name in SIGNATURES:
+      if name in self.SKIP:
+        continue
+      fn = getattr(lib, name)
+      self._saved[name] = fn
+
+      def wrapped(*args, _fn=fn, _name=name):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = _fn(*args)
+        e1.record()
+        self.records.append((_name, args, e0, e1))
+        return rc
+      setattr(lib, name, wrapped)
+    return self
+
+  def __exit__(self, *exc):
+    for name, fn in self._saved.items():
+      setattr(lib, name, fn)
+
+  def summary(self):
+    """{name: {'calls': n, 'ms': total, 'items': [(args, ms), ...]}} sorted by total time."""
+    import torch
+    torch.cuda.synchronize()
+    out = {}
+    for name, args, e0, e1 in self.records:
+      ms = e0.elapsed_time(e1)
+      d = out.setdefault(name, {'calls': 0, 'ms': 0.0, 'items': []})
+      d['calls'] += 1
+      d['ms'] += ms
+      d['items'].append((args, ms))
+    return dict(sorted(out.items(), key=lambda kv: -kv[1]['ms']))

@@ -1,0 +1,191 @@
+"""Conv2D / Conv3D / MaxPool2D / MaxPool3D (reference: neograd/autograd/ops/conv.py).
+
+One kernel launch per forward and per operand gradient (the reference runs a Python loop over output positions).
+Results and upstream gradients use the reference's output order -- position (p,q) of the textbook (Ho,Wo) map is
+stored at flat index q*Ho+p (conv.py:39-47 vs 149-151) -- which the kernels produce / consume directly.
+neograd's single-channel Conv2D (conv.py:121-215) runs through the same entry points with C = O = 1."""
+import ctypes
+
+import numpy as np
+
+from ... import _backend as B
+from ... import device as D
+from ..tensor import GradFn
+from .operation import Operation
+
+
+class Conv:
+  """Geometry shared by the four ops (conv.py:6-117)."""
+
+  def check_geometry(self):
+    assert self.stride >= 1, 'Stride must be greater than or equal to 1'          # conv.py:33
+    assert self.padding >= 0, 'Padding must be greater than or equal to zero'     # conv.py:34
+
+  def get_result_shape(self, inputs_shape, kernel_shape):
+    """conv.py:49-68: floor((dim + 2p - k)/s + 1) on the last two dims."""
+    self.check_geometry()
+    ho = int((inputs_shape[-2] + 2 * self.padding - kernel_shape[-2]) / self.stride + 1)
+    wo = int((inputs_shape[-1] + 2 * self.padding - kernel_shape[-1]) / self.stride + 1)
+    return ho, wo
+
+
+def _conv_forward(op, x4, w4, b1, out_shape):
+  N, C, H, W = x4.shape
+  O, _, KH, KW = w4.shape
+  y = D.DeviceArray.empty(out_shape)
+  B.check(B.lib.ngb_conv_fprop(x4.ptr, w4.ptr, b1.ptr, y.ptr, N, C, H, W, O, KH, KW, op.padding, op.stride, D._st()))
+  return y
+
+
+def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
+  """dgrad / wgrad / bgrad closures (conv.py:299-327, 179-199); each can accumulate into the gradient buffer."""
+  N, C, H, W = x4shape
+  O, _, KH, KW = w4shape
+  pad, stride = op.padding, op.stride
+  x, w = inputs.data, kernel.data
+
+  def dgrad(ug, dst, acc):
+    if dst is None:
+      dst, acc = D.DeviceArray.empty(inputs.shape), False
+    B.check(B.lib.ngb_conv_dgrad(ug.ptr, w.ptr, dst.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st()))
+    return dst
+
+  def wgrad(ug, dst, acc):
+    if dst is None:
+      dst, acc = D.DeviceArray.empty(kernel.shape), False
+    B.check(B.lib.ngb_conv_wgrad(ug.ptr, x.ptr, dst.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st()))
+    return dst
+
+  def bgrad(ug, dst, acc):
+    if dst is None:
+      dst, acc = D.DeviceArray.empty(bias.shape), False
+    B.check(B.lib.ngb_conv_bgrad(ug.ptr, dst.ptr, N, O, ug.size // max(N * O, 1), int(acc), D._st()))
+    return dst
+
+  inputs.set_grad_fn(GradFn(dgrad))
+  kernel.set_grad_fn(GradFn(wgrad))
+  bias.set_grad_fn(GradFn(bgrad))
+
+
+class Conv2D(Operation, Conv):
+  """conv.py:121-215: (N,H,W) (*) (KH,KW) + scalar bias -> (N,Ho,Wo)."""
+
+  def __init__(self, padding=0, stride=1):
+    self.padding = padding
+    self.stride = stride
+
+  def forward(self, inputs, kernel, bias):
+    inputs, kernel, bias = self.get_tensors(inputs, kernel, bias)
+    self.validate_inputs(inputs)
+    ho, wo = self.get_result_shape(inputs.shape, kernel.shape)
+    N, H, W = inputs.shape
+    y = _conv_forward(self, inputs.data.reshape((N, 1, H, W)), kernel.data.reshape((1, 1) + kernel.shape),
+                      bias.data.reshape((1,)), (N, ho, wo))
+    return self.get_result_tensor(y, inputs, kernel, bias)
+
+  def backward(self, inputs, kernel, bias):
+    N, H, W = inputs.shape
+    _conv_grad_fns(self, inputs, kernel, bias, (N, 1, H, W), (1, 1) + kernel.shape)
+
+  def validate_inputs(self, inputs):
+    if len(inputs.shape) != 3:
+      raise ValueError("Only 3D inputs, with 0th dim as number of examples are supported!")
+
+
+def conv2d(inputs, kernel, bias, padding, stride):
+  return Conv2D(padding, stride).forward(inputs, kernel, bias)
+
+
+class Conv3D(Operation, Conv):
+  """conv.py:234-343: (N,C,H,W) (*) (O,C,KH,KW) + bias (O,) -> (N,O,Ho,Wo)."""
+
+  def __init__(self, padding=0, stride=1):
+    self.padding = padding
+    self.stride = stride
+
+  def forward(self, inputs, kernel, bias):
+    inputs, kernel, bias = self.get_tensors(inputs, kernel, bias)
+    self.validate_inputs(inputs)
+    if len(kernel.shape) != 4 or kernel.shape[1] != inputs.shape[1]:
+      raise ValueError(f"operands could not be broadcast together with shapes {inputs.shape} {kernel.shape}")
+    ho, wo = self.get_result_shape(inputs.shape, kernel.shape)
+    y = _conv_forward(self, inputs.data, kernel.data, bias.data.reshape((kernel.shape[0],)),
+                      (inputs.shape[0], kernel.shape[0], ho, wo))
+    return self.get_result_tensor(y, inputs, kernel, bias)
+
+  def backward(self, inputs, kernel, bias):
+    _conv_grad_fns(self, inputs, kernel, bias, inputs.shape, kernel.shape)
+
+  def validate_inputs(self, inputs):
+    if len(inputs.shape) != 4:
+      raise ValueError("Only 4D inputs, with 0th dim as number of examples, 1st dim as number of channels are supported!")
+
+
+def conv3d(inputs, kernel, bias, padding, stride):
+  return Conv3D(padding, stride).forward(inputs, kernel, bias)
+
+
+class _MaxPool(Operation, Conv):
+  """conv.py:362-542.  Forward also stores the uint8 argmax of every window (first maximum, row-major in the
+  zero-padded window: np.argmax at conv.py:424/523); backward routes ug through those indices instead of re-running
+  argmax over the input."""
+  NDIM = None
+  ERR = None
+
+  def __init__(self, kernel_shape, padding=0, stride=1):
+    self.kernel_shape = kernel_shape
+    self.padding = padding
+    self.stride = stride
+    self._idx = None
+
+  def forward(self, inputs):
+    inputs = self.get_tensors(inputs)
+    self.validate_inputs(inputs)
+    if len(self.kernel_shape) != 2:
+      raise ValueError("Only 2D kernels are allowed!")                    # conv.py:377-380, 476-479
+    ho, wo = self.get_result_shape(inputs.shape, self.kernel_shape)
+    lead = inputs.shape[:-2]
+    H, W = inputs.shape[-2:]
+    outer = int(np.prod(lead))
+    y = D.DeviceArray.empty(lead + (ho, wo))
+    idx = D.torch().empty(lead + (ho, wo), device='cuda', dtype=D.torch().uint8)
+    B.check(B.lib.ngb_maxpool_fwd(inputs.data.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), outer, H, W,
+                                  self.kernel_shape[0], self.kernel_shape[1], self.padding, self.stride, D._st()))
+    self._idx = idx
+    return self.get_result_tensor(y, inputs)
+
+  def backward(self, inputs):
+    idx, (KH, KW), pad, stride = self._idx, self.kernel_shape, self.padding, self.stride
+    lead = inputs.shape[:-2]
+    H, W = inputs.shape[-2:]
+    outer = int(np.prod(lead))
+
+    def into(ug, dst, acc):
+      if dst is None:
+        dst, acc = D.DeviceArray.empty(inputs.shape), False
+      B.check(B.lib.ngb_maxpool_bwd(ug.ptr, ctypes.c_void_p(idx.data_ptr()), dst.ptr, outer, H, W, KH, KW, pad, stride,
+                                    int(acc), D._st()))
+      return dst
+    inputs.set_grad_fn(GradFn(into))
+
+  def validate_inputs(self, inputs):
+    if len(inputs.shape) != self.NDIM:
+      raise ValueError(self.ERR)
+
+
+class MaxPool2D(_MaxPool):
+  NDIM = 3
+  ERR = "Only 3D inputs, with 0th dim as number of examples are supported!"
+
+
+class MaxPool3D(_MaxPool):
+  NDIM = 4
+  ERR = "Only 4D inputs, with 0th dim as number of examples, 1st dim as number of channels are supported!"
+
+
+def maxpool2d(inputs, kernel_shape, padding, stride):
+  return MaxPool2D(kernel_shape, padding, stride).forward(inputs)
+
+
+def maxpool3d(inputs, kernel_shape, padding, stride):
+  return MaxPool3D(kernel_shape, padding, stride).forward(inputs)

@@ -1,0 +1,253 @@
+"""Tensor: neograd's user-facing array-with-gradient, with `data` and `grad` resident in B200 HBM
+(reference: neograd/autograd/tensor.py).  The public surface is the reference's; the differences are internal:
+
+  * `data` / `grad` are `DeviceArray`s (fp32, device) instead of float64 ndarrays;
+  * Python-scalar operands stay scalars (kernel immediates) until something asks for their `.data`;
+  * gradients of the built-in ops are written by ONE kernel that fuses local-gradient x upstream-gradient, the
+    `unbroadcast` reduction (utils.py:34-78), the reshape (tensor.py:99) and the `+=` accumulation (tensor.py:301)
+    straight into the gradient buffer (see `GradFn.into`); user-defined Operations that return a plain array from
+    their grad_fn take the reference's generic path;
+  * a parameter's `data` / `grad` may be pinned views into an optimizer's flat arena (nn/optim.py here): assigning to
+    them copies into place so the arena (one allreduce, one fused optimizer launch) stays valid.
+"""
+import numpy as np
+
+from ..device import DeviceArray
+from .utils import process_data, unbroadcast_data
+
+
+class GradFn:
+  """A grad_fn the engine can fuse.  `into(ug, dst, accumulate)` must write (accumulate=False) or add
+  (accumulate=True) the operand-shaped gradient into `dst`; `dst=None` means allocate.  Calling the object like the
+  reference's lambdas (`grad_fn(ug) -> array`) still works."""
+  __slots__ = ('into',)
+
+  def __init__(self, into):
+    self.into = into
+
+  def __call__(self, ug):
+    return self.into(ug, None, False)
+
+
+class Tensor:
+  def __init__(self, data, requires_grad=False, requires_broadcasting=True):
+    self._data = None
+    self._scalar = None
+    self._pinned = False        # data buffer is a view into an optimizer arena: assignments copy into place
+    self._grad = None           # gradient buffer (may be a pinned arena view)
+    self._grad_live = False     # whether _grad currently holds the gradient (False <=> reference's `0.`)
+    self._grad_pinned = False
+    self.data = data
+    self.requires_grad = requires_grad
+    self.requires_broadcasting = requires_broadcasting
+    self.grad_fn = None
+
+  # ------------------------------------------------------------------ data
+  @property
+  def data(self):
+    if self._data is None:                       # lazy upload of a Python-scalar operand
+      self._data = DeviceArray.full((), self._scalar)
+    return self._data
+
+  @data.setter
+  def data(self, data):
+    """tensor.py:312-322: every assignment is coerced by process_data (TypeError on unsupported types)."""
+    if type(data) in (int, float) and self._data is None and not self._pinned:
+      self._scalar = float(data)
+      return
+    new = process_data(data)
+    self._scalar = None
+    if self._pinned and self._data is not None:
+      if new is not self._data:
+        if new.shape != self._data.shape:
+          raise ValueError(f'cannot assign data of shape {new.shape} to a parameter of shape {self._data.shape} '
+                           'that is registered with an optimizer')
+        self._data.assign(new)
+    else:
+      self._data = new
+
+  @property
+  def shape(self):
+    return () if self._data is None else self._data.shape
+
+  # ------------------------------------------------------------------ grad
+  @property
+  def grad(self):
+    if self._grad_live:
+      return self._grad
+    return 0. if self.requires_grad else None     # tensor.py:36, 42
+
+  @grad.setter
+  def grad(self, value):
+    if value is None or (isinstance(value, (int, float)) and value == 0):
+      self._grad_live = False
+      if not self._grad_pinned:
+        self._grad = None
+      return
+    if isinstance(value, (int, float)):
+      value = DeviceArray.full(self.shape, value)
+    value = process_data(value)
+    if self._grad_pinned:
+      self._grad.assign(value)
+    else:
+      self._grad = value
+    self._grad_live = True
+
+  def zero_grad(self):
+    """tensor.py:39-42."""
+    self._grad_live = False
+    if not self._grad_pinned:
+      self._grad = None
+
+  def accumulate_grad(self, grad):
+    """tensor.py:291-301: `self.grad += grad` (the first accumulation replaces the Python 0.)."""
+    if self._grad_live:
+      self._grad.add_(grad)
+    elif self._grad_pinned:
+      self._grad.assign(grad)
+      self._grad_live = True
+    else:
+      self._grad = grad.copy()   # the producer may hand back the upstream buffer itself (Add): never alias it
+      self._grad_live = True
+
+  def set_grad_fn(self, grad_fn):
+    """tensor.py:106-114."""
+    self.grad_fn = grad_fn if self.requires_grad else None
+
+  # ------------------------------------------------------------------ backward
+  def backward(self, upper_grad=1., retain_graph=False):
+    """tensor.py:44-73."""
+    if not self.requires_grad:
+      raise ValueError("Only tensors who requires_grad can call backward")
+    from .utils import get_graph
+    graph = get_graph()
+    if type(upper_grad) in (int, float):
+      if self.shape != ():
+        raise ValueError("Shapes of grad and Tensor data must match!")
+      upper_grad = DeviceArray.full((), upper_grad)
+    else:
+      upper_grad = process_data(upper_grad)
+      if self.shape != upper_grad.shape:
+        raise ValueError("Shapes of grad and Tensor data must match!")
+    self.accumulate_grad(upper_grad)
+    node = graph.get_node(self)
+    node.backward(retain_graph)
+    if not retain_graph:
+      graph.reset_graph()
+
+  def _backward(self, node, retain_graph, calculate_grads=True):
+    """tensor.py:75-104.  For every child (an op that consumed this tensor): install the grad_fns, run this operand's
+    grad_fn on the child's gradient, unbroadcast, reshape, accumulate."""
+    from .utils import get_graph
+    graph = get_graph()
+    for child in node.children:
+      if self.requires_grad and calculate_grads:
+        child.backward_fn(*[n.tens for n in child.parents])
+        ct = child.tens
+        upper_grad = ct._grad if ct._grad_live else DeviceArray.zeros(ct.shape)
+        gf = self.grad_fn
+        if isinstance(gf, GradFn):
+          self._ensure_grad_buffer()
+          gf.into(upper_grad, self._grad, self._grad_live)
+          self._grad_live = True
+        else:
+          grad = gf(upper_grad)
+          grad = unbroadcast_data(grad, self.shape, child.parent_broadcast_shape)
+          grad = process_data(grad) if not isinstance(grad, DeviceArray) else grad
+          self.accumulate_grad(grad.reshape(self.shape))
+      if not retain_graph and child.are_parents_visited():
+        graph.remove_tensor(child.tens)
+    if not retain_graph and node.are_parents_visited():
+      graph.remove_tensor(node.tens)
+
+  def _ensure_grad_buffer(self):
+    if self._grad is None:
+      self._grad = DeviceArray.empty(self.shape)
+      self._grad_live = False
+
+  # ------------------------------------------------------------------ operators (tensor.py:116-289)
+  def __add__(self, other):
+    from .ops import add
+    return add(self, other)
+
+  def __radd__(self, other):
+    from .ops import add
+    return add(other, self)
+
+  def __sub__(self, other):
+    from .ops import sub
+    return sub(self, other)
+
+  def __rsub__(self, other):
+    from .ops import sub
+    return sub(other, self)
+
+  def __mul__(self, other):
+    from .ops import mul
+    return mul(self, other)
+
+  def __rmul__(self, other):
+    from .ops import mul
+    return mul(other, self)
+
+  def __truediv__(self, other):
+    from .ops import div
+    return div(self, other)
+
+  def __rtruediv__(self, other):
+    from .ops import div
+    return div(other, self)
+
+  def __pow__(self, other):
+    from .ops import pow as _pow
+    return _pow(self, other)
+
+  def __rpow__(self, other):
+    from .ops import pow as _pow
+    return _pow(other, self)
+
+  def __pos__(self):
+    from .ops import mul
+    return mul(1, self)          # tensor.py:226-232
+
+  def __neg__(self):
+    from .ops import mul
+    return mul(-1, self)         # tensor.py:234-240
+
+  def dot(self, other):
+    from .ops import dot
+    return dot(self, other)
+
+  def sum(self, axis=None):
+    from .ops import sum as _sum
+    return _sum(self, axis)
+
+  def exp(self):
+    from .ops import exp
+    return exp(self)
+
+  def flatten(self):
+    from .ops import flatten
+    return flatten(self)
+
+  def reshape(self, new_shape):
+    from .ops import reshape
+    return reshape(self, new_shape)
+
+  @property
+  def T(self):
+    from .ops import transpose
+    return transpose(self)
+
+  def __getitem__(self, *indices):
+    """tensor.py:342-355: one int or slice on the leading axis -> an UNTRACKED tensor (a view of the same HBM)."""
+    index = indices[0]
+    if isinstance(index, (int, slice)):
+      return Tensor(self.data[index], requires_grad=self.requires_grad)
+    raise TypeError(f"Expected index of int or slice instead got {type(index)}")
+
+  def __repr__(self):
+    return f'Tensor({self.data.numpy()},\n requires_grad={self.requires_grad},\n requires_broadcasting={self.requires_broadcasting})'
+
+  def __str__(self):
+    return f'Tensor( {self.data.numpy()},\n requires_grad={self.requires_grad},\n grad_fn={self.grad_fn},\n shape={self.shape},\n requires_broadcasting={self.requires_broadcasting} )\n'

@@ -21,6 +21,7 @@ int64_t scratch_bytes();
 int ensure_init();
 
 extern std::atomic<int64_t> g_launches;
+extern std::atomic<int> g_default_engine;   // NGB_GEMM_AUTO or NGB_GEMM_SIMT (ngb_set_default_engine)
 inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 #define NGB_CHECK_ARG(cond, ...)                                   \

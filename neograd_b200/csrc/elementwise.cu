@@ -380,6 +380,24 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
   }
 }
 
+// General axis permutation: one thread per output element; consecutive threads write consecutive addresses.
+struct PermDims { int rank; int64_t out_size[MAXD]; int64_t src_stride[MAXD]; };
+__global__ void __launch_bounds__(256) permute_kernel(const float* __restrict__ src, float* __restrict__ dst, PermDims d,
+                                                      int64_t total) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t rem = i, off = 0;
+#pragma unroll
+    for (int k = MAXD - 1; k >= 0; --k) {
+      if (k < d.rank) {
+        const int64_t c = rem % d.out_size[k];
+        rem /= d.out_size[k];
+        off += c * d.src_stride[k];
+      }
+    }
+    dst[i] = __ldg(src + off);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 // Builds the (collapsed) broadcast description.  Returns false on incompatible shapes.
 static bool build_dims(const int64_t* a_shape, int a_rank, const int64_t* b_shape, int b_rank, int side /* -1: fwd */,
@@ -615,6 +633,33 @@ extern "C" int ngb_axpy(float* dst, const float* src, float alpha, int64_t n, ng
   if (n == 0) return NGB_OK;
   axpy_kernel<<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, as_stream(stream)>>>(dst, src, alpha, n,
                                                                                     aligned16(dst) && aligned16(src));
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+extern "C" int ngb_copy(float* dst, const float* src, int64_t n, ngb_stream_t stream) {
+  NGB_CHECK_ARG(n >= 0, "ngb_copy: negative length");
+  if (n == 0 || dst == src) return NGB_OK;
+  NGB_CUDA(cudaMemcpyAsync(dst, src, (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, as_stream(stream)));
+  return NGB_OK;
+}
+
+extern "C" int ngb_permute(const float* src, float* dst, const int64_t* shape, const int* perm, int rank, ngb_stream_t stream) {
+  NGB_CHECK_ARG(rank >= 1 && rank <= MAXD, "ngb_permute: rank must be 1..%d", MAXD);
+  int64_t stride[MAXD], total = 1;
+  for (int k = rank - 1; k >= 0; --k) { stride[k] = total; total *= shape[k]; }
+  PermDims d;
+  d.rank = rank;
+  bool seen[MAXD] = {};
+  for (int k = 0; k < MAXD; ++k) { d.out_size[k] = 1; d.src_stride[k] = 0; }
+  for (int k = 0; k < rank; ++k) {
+    NGB_CHECK_ARG(perm[k] >= 0 && perm[k] < rank && !seen[perm[k]], "ngb_permute: perm is not a permutation");
+    seen[perm[k]] = true;
+    d.out_size[k] = shape[perm[k]];
+    d.src_stride[k] = stride[perm[k]];
+  }
+  if (total == 0) return NGB_OK;
+  permute_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(src, dst, d, total);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }

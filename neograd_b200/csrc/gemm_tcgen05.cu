@@ -338,8 +338,16 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
 
 using namespace ngb;
 
+namespace ngb { std::atomic<int> g_default_engine{NGB_GEMM_AUTO}; }
+
+extern "C" int ngb_set_default_engine(int engine) {
+  if (engine != NGB_GEMM_AUTO && engine != NGB_GEMM_SIMT) return g_default_engine.load();
+  return g_default_engine.exchange(engine);
+}
+
 extern "C" int ngb_gemm_query(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb,
                               int64_t ldc) {
+  if (g_default_engine.load() == NGB_GEMM_SIMT) return NGB_GEMM_SIMT;
   return tc::gemm_tc_eligible(transA, transB, M, N, K, lda, ldb, ldc) ? NGB_GEMM_TCGEN05 : NGB_GEMM_SIMT;
 }
 
@@ -356,6 +364,7 @@ extern "C" int ngb_gemm(int engine, int transA, int transB, int64_t M, int64_t N
     return NGB_OK;
   }
   bool use_tc = false;
+  if (engine == NGB_GEMM_AUTO) engine = g_default_engine.load();
   if (engine == NGB_GEMM_TCGEN05) {
     if (lda % 4 || ldb % 4 || K < 8) return fail(NGB_ERR_UNSUPPORTED, "shape not eligible for the tcgen05 GEMM");
     use_tc = true;

@@ -60,9 +60,65 @@ __global__ void __launch_bounds__(256) softmax_ce_bwd_kernel(const float* __rest
   }
 }
 
+// Softmax layer (activations.py:105-180): one thread per (outer, inner) slice.
+__global__ void __launch_bounds__(256) softmax_fwd_kernel(const float* __restrict__ x, int64_t outer, int64_t L, int64_t inner,
+                                                          float* __restrict__ y) {
+  const int64_t rows = outer * inner;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = r / inner, in = r - o * inner;
+    const int64_t base = o * L * inner + in;
+    float mx = -INFINITY;
+    for (int64_t l = 0; l < L; ++l) mx = fmaxf(mx, x[base + l * inner]);
+    float sum = 0.f;
+    for (int64_t l = 0; l < L; ++l) sum += expf(x[base + l * inner] - mx);
+    const float inv = 1.f / sum;
+    for (int64_t l = 0; l < L; ++l) y[base + l * inner] = expf(x[base + l * inner] - mx) * inv;
+  }
+}
+
+// dx_i = s_i * (ug_i - sum_j ug_j s_j): the product of the softmax Jacobian with ug (activations.py:131-158).
+__global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restrict__ x, const float* __restrict__ ug,
+                                                          int64_t outer, int64_t L, int64_t inner, float* __restrict__ dx,
+                                                          int accumulate) {
+  const int64_t rows = outer * inner;
+  for (int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; r < rows; r += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t o = r / inner, in = r - o * inner;
+    const int64_t base = o * L * inner + in;
+    float mx = -INFINITY;
+    for (int64_t l = 0; l < L; ++l) mx = fmaxf(mx, x[base + l * inner]);
+    float sum = 0.f;
+    for (int64_t l = 0; l < L; ++l) sum += expf(x[base + l * inner] - mx);
+    const float inv = 1.f / sum;
+    float dotp = 0.f;
+    for (int64_t l = 0; l < L; ++l) dotp += ug[base + l * inner] * (expf(x[base + l * inner] - mx) * inv);
+    for (int64_t l = 0; l < L; ++l) {
+      const int64_t a = base + l * inner;
+      const float g = (expf(x[a] - mx) * inv) * (ug[a] - dotp);
+      dx[a] = accumulate ? dx[a] + g : g;
+    }
+  }
+}
+
 }  // namespace ngb
 
 using namespace ngb;
+
+extern "C" int ngb_softmax_fwd(const float* x, int64_t outer, int64_t L, int64_t inner, float* y, ngb_stream_t stream) {
+  NGB_CHECK_ARG(outer >= 0 && L >= 1 && inner >= 0, "ngb_softmax_fwd: bad shape");
+  if (outer * inner == 0) return NGB_OK;
+  softmax_fwd_kernel<<<grid_for(outer * inner, 256), 256, 0, as_stream(stream)>>>(x, outer, L, inner, y);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+extern "C" int ngb_softmax_bwd(const float* x, const float* ug, int64_t outer, int64_t L, int64_t inner, float* dx,
+                               int accumulate, ngb_stream_t stream) {
+  NGB_CHECK_ARG(outer >= 0 && L >= 1 && inner >= 0, "ngb_softmax_bwd: bad shape");
+  if (outer * inner == 0) return NGB_OK;
+  softmax_bwd_kernel<<<grid_for(outer * inner, 256), 256, 0, as_stream(stream)>>>(x, ug, outer, L, inner, dx, accumulate);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
 
 extern "C" int ngb_softmax_ce_fwd(const float* logits, const float* targets, int64_t outer, int64_t L, int64_t inner,
                                   float inv_num_examples, float epsilon, float* loss, ngb_stream_t stream) {

@@ -2,23 +2,32 @@
 // Reference: neograd/nn/optim.py -- GD 42-47, Momentum 63-92, RMSProp 112-140, Adam 168-197.
 // HBM-bound: Adam moves 28 B/element (read p,g,m,v; write p,m,v), SGD 12 B/element; 128-bit accesses, grid-stride,
 // grid a multiple of 148 SMs.  `grad_scale` folds the data-parallel 1/world averaging into the same pass.
+// Hyper-parameters arrive as doubles; 1-beta and the bias corrections are formed in double and rounded once.
 #include "common.cuh"
 
 namespace ngb {
 
-struct AdamP { float lr, b1, b2, eps, ibc1, ibc2, gs; };
+struct AdamP { float lr, b1, omb1, b2, omb2, eps, ibc1, ibc2, gs; };
 
 __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, const AdamP& a) {
   g *= a.gs;
-  m = a.b1 * m + (1.f - a.b1) * g;          // optim.py:196
-  v = a.b2 * v + (1.f - a.b2) * g * g;      // optim.py:197
+  m = a.b1 * m + a.omb1 * g;                // optim.py:196
+  v = a.b2 * v + a.omb2 * (g * g);          // optim.py:197
   const float mh = m * a.ibc1;              // optim.py:177
   const float vh = v * a.ibc2;              // optim.py:178
   p -= a.lr * (mh / (sqrtf(vh) + a.eps));   // optim.py:179
 }
 
+// T_DEV: the iteration count is read from device memory (already incremented by adam_tick_kernel).
+template <bool T_DEV>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, int64_t n, AdamP a, int vec_ok) {
+                                                   float* __restrict__ v, int64_t n, AdamP a, const int32_t* __restrict__ t_dev,
+                                                   double b1d, double b2d, int vec_ok) {
+  if (T_DEV) {
+    const double t = (double)*t_dev;
+    a.ibc1 = (float)(1.0 / (1.0 - pow(b1d, t)));
+    a.ibc2 = (float)(1.0 / (1.0 - pow(b2d, t)));
+  }
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
   int64_t done = 0;
   if (vec_ok) {
@@ -37,6 +46,8 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
   for (int64_t i = done + tid; i < n; i += nt) adam1(p[i], g[i], m[i], v[i], a);
 }
 
+__global__ void adam_tick_kernel(int32_t* t_dev) { *t_dev += 1; }   // optim.py:169
+
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr,
                                                   float gs, int vec_ok) {
   const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x, nt = (int64_t)gridDim.x * blockDim.x;
@@ -54,60 +65,89 @@ __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const f
 }
 
 __global__ void __launch_bounds__(256) momentum_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                       float* __restrict__ m, int64_t n, float lr, float beta, float gs) {
+                                                       float* __restrict__ m, int64_t n, float lr, float beta, float omb,
+                                                       float gs) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
-    const float mm = beta * m[i] + (1.f - beta) * (g[i] * gs);   // optim.py:92
+    const float mm = beta * m[i] + omb * (g[i] * gs);            // optim.py:92
     m[i] = mm;
     p[i] -= lr * mm;                                             // optim.py:70
   }
 }
 
 __global__ void __launch_bounds__(256) rmsprop_kernel(float* __restrict__ p, const float* __restrict__ g,
-                                                      float* __restrict__ r, int64_t n, float lr, float beta, float eps,
-                                                      float gs) {
+                                                      float* __restrict__ r, int64_t n, float lr, float beta, float omb,
+                                                      float eps, float gs) {
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
     const float gg = g[i] * gs;
-    const float rr = beta * r[i] + (1.f - beta) * gg * gg;       // optim.py:140
+    const float rr = beta * r[i] + omb * (gg * gg);              // optim.py:140
     r[i] = rr;
     p[i] -= lr * (gg / (sqrtf(rr) + eps));                       // optim.py:118
   }
+}
+
+static AdamP make_adam(double lr, double b1, double b2, double eps, double t, double gs) {
+  AdamP a;
+  a.lr = (float)lr; a.b1 = (float)b1; a.omb1 = (float)(1.0 - b1); a.b2 = (float)b2; a.omb2 = (float)(1.0 - b2);
+  a.eps = (float)eps; a.gs = (float)gs;
+  a.ibc1 = t > 0 ? (float)(1.0 / (1.0 - pow(b1, t))) : 1.f;
+  a.ibc2 = t > 0 ? (float)(1.0 / (1.0 - pow(b2, t))) : 1.f;
+  return a;
 }
 
 }  // namespace ngb
 
 using namespace ngb;
 
-extern "C" int ngb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2,
-                             float epsilon, float inv_bias_corr1, float inv_bias_corr2, float grad_scale,
-                             ngb_stream_t stream) {
+extern "C" int ngb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
+                             double epsilon, int64_t t, double grad_scale, ngb_stream_t stream) {
+  NGB_CHECK_ARG(t >= 1, "ngb_adam_step: t is the 1-based iteration count");
   if (n == 0) return NGB_OK;
-  AdamP a{lr, beta1, beta2, epsilon, inv_bias_corr1, inv_bias_corr2, grad_scale};
+  const AdamP a = make_adam(lr, beta1, beta2, epsilon, (double)t, grad_scale);
   const int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
-  adam_kernel<<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, vec);
+  adam_kernel<false><<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, nullptr, 0, 0, vec);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
 
-extern "C" int ngb_sgd_step(float* p, const float* g, int64_t n, float lr, float grad_scale, ngb_stream_t stream) {
+extern "C" int ngb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1,
+                                 double beta2, double epsilon, int32_t* t_dev, int tick, double grad_scale,
+                                 ngb_stream_t stream) {
+  NGB_CHECK_ARG(t_dev != nullptr, "ngb_adam_step_dev: t_dev is NULL");
+  cudaStream_t st = as_stream(stream);
+  if (tick) {
+    adam_tick_kernel<<<1, 1, 0, st>>>(t_dev);
+    NGB_LAUNCH_CHECK();
+  }
   if (n == 0) return NGB_OK;
-  sgd_kernel<<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, as_stream(stream)>>>(p, g, n, lr, grad_scale,
+  const AdamP a = make_adam(lr, beta1, beta2, epsilon, 0, grad_scale);
+  const int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
+  adam_kernel<true><<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, st>>>(p, g, m, v, n, a, t_dev, beta1, beta2, vec);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+extern "C" int ngb_sgd_step(float* p, const float* g, int64_t n, double lr, double grad_scale, ngb_stream_t stream) {
+  if (n == 0) return NGB_OK;
+  sgd_kernel<<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, as_stream(stream)>>>(p, g, n, (float)lr, (float)grad_scale,
                                                                                    aligned16(p) && aligned16(g));
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
 
-extern "C" int ngb_momentum_step(float* p, const float* g, float* m, int64_t n, float lr, float beta, float grad_scale,
+extern "C" int ngb_momentum_step(float* p, const float* g, float* m, int64_t n, double lr, double beta, double grad_scale,
                                  ngb_stream_t stream) {
   if (n == 0) return NGB_OK;
-  momentum_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, n, lr, beta, grad_scale);
+  momentum_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, m, n, (float)lr, (float)beta, (float)(1.0 - beta),
+                                                                  (float)grad_scale);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
 
-extern "C" int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, float lr, float beta, float epsilon,
-                                float grad_scale, ngb_stream_t stream) {
+extern "C" int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, double lr, double beta, double epsilon,
+                                double grad_scale, ngb_stream_t stream) {
   if (n == 0) return NGB_OK;
-  rmsprop_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, r, n, lr, beta, epsilon, grad_scale);
+  rmsprop_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(p, g, r, n, (float)lr, (float)beta, (float)(1.0 - beta),
+                                                                 (float)epsilon, (float)grad_scale);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }

@@ -1,0 +1,85 @@
+"""Losses (reference: neograd/nn/loss.py).  MSE / BCE / CE are composites of the elementwise ops exactly as in the
+reference (so BCE keeps its swapped arguments, loss.py:83 / SURVEY A.7); SoftmaxCE is one fused Operation."""
+from ..autograd import sum as _sum, log
+from ..autograd.ops.operation import Operation
+from ..autograd.tensor import GradFn
+from .. import _backend as B
+from .. import device as D
+from .activations import _split_axis
+
+
+class Loss:
+  def __call__(self, outputs, targets):
+    return self.forward(outputs, targets)
+
+  def get_num_examples(self, outputs_shape):
+    """loss.py:22-37."""
+    return 1 if len(outputs_shape) in (0, 1) else outputs_shape[0]
+
+
+class MSE(Loss):
+  """loss.py:41-62."""
+
+  def forward(self, outputs, targets):
+    num_examples = self.get_num_examples(outputs.shape)
+    return (1 / (2 * num_examples)) * _sum((outputs - targets) ** 2)
+
+  def __repr__(self): return 'MSE()'
+  def __str__(self): return 'MeanSquaredError'
+
+
+class BCE(Loss):
+  """loss.py:66-91."""
+
+  def forward(self, outputs, targets, epsilon=1e-9):
+    num_examples = self.get_num_examples(outputs.shape)
+    entropy = _sum((outputs * log(targets + epsilon)) + ((1 - outputs) * (log(1 - targets + epsilon))))
+    return (-1 / num_examples) * entropy
+
+  def __repr__(self): return 'BCE()'
+  def __str__(self): return 'BinaryCrossEntropy'
+
+
+class CE(Loss):
+  """loss.py:95-120."""
+
+  def forward(self, outputs, targets, epsilon=1e-9):
+    num_examples = self.get_num_examples(outputs.shape)
+    entropy = _sum(targets * log(outputs + epsilon))
+    return (-1 / num_examples) * entropy
+
+  def __repr__(self): return 'CE()'
+  def __str__(self): return 'CrossEntropy'
+
+
+class SoftmaxCE(Operation, Loss):
+  """loss.py:124-172: loss = -(1/N) sum t*log(softmax(z)+eps); dz = (ug/N)(softmax(z) - t)."""
+
+  def __init__(self, axis):
+    self.axis = axis
+
+  def forward(self, outputs, targets, epsilon=1e-9):
+    outputs, targets = self.get_tensors(outputs, targets)
+    if outputs.shape != targets.shape:
+      raise ValueError(f"operands could not be broadcast together with shapes {outputs.shape} {targets.shape}")
+    n = self.get_num_examples(outputs.shape)
+    outer, L, inner = _split_axis(outputs.shape, self.axis)
+    loss = D.DeviceArray.empty(())
+    B.check(B.lib.ngb_softmax_ce_fwd(outputs.data.ptr, targets.data.ptr, outer, L, inner, 1.0 / n, epsilon, loss.ptr, D._st()))
+    return self.get_result_tensor(loss, outputs, targets)
+
+  def backward(self, outputs, targets):
+    z, t = outputs.data, targets.data
+    n = self.get_num_examples(outputs.shape)
+    outer, L, inner = _split_axis(outputs.shape, self.axis)
+
+    def into(ug, dst, acc):
+      if dst is None:
+        dst, acc = D.DeviceArray.empty(z.shape), False
+      B.check(B.lib.ngb_softmax_ce_bwd(z.ptr, t.ptr, ug.ptr, outer, L, inner, 1.0 / n, dst.ptr, int(acc), D._st()))
+      return dst
+    outputs.set_grad_fn(GradFn(into))
+    assert targets.requires_grad is False, 'Targets Tensor should have requires_grad=False'
+
+  def __repr__(self): return f'SoftmaxCE(axis={self.axis})'
+  def __str__(self): return 'SoftmaxCrossEntropy'

@@ -247,10 +247,12 @@ def test_conv_direct(U, N, C, H, W, O, KH, KW, pad, stride):
 
 def test_conv_errors(U):
   x, w, b = np.zeros((1, 1, 5, 5)), np.zeros((1, 1, 3, 3)), np.zeros(1)
-  with pytest.raises(ValueError):
-    U.conv_fprop(x, w, b, 0, 0)        # conv.py:33 (stride >= 1)
-  with pytest.raises(ValueError):
-    U.conv_fprop(x, w, b, -1, 1)       # conv.py:34 (padding >= 0)
+  import torch
+  X, W, Bs, y = U.dev(x), U.dev(w), U.dev(b), torch.zeros(1, 1, 3, 3, device='cuda')
+  with pytest.raises(ValueError, match='Stride'):       # conv.py:33 (stride >= 1)
+    U.call('ngb_conv_fprop', U.ptr(X), U.ptr(W), U.ptr(Bs), U.ptr(y), 1, 1, 5, 5, 1, 3, 3, 0, 0, U.st())
+  with pytest.raises(ValueError, match='Padding'):      # conv.py:34 (padding >= 0)
+    U.call('ngb_conv_fprop', U.ptr(X), U.ptr(W), U.ptr(Bs), U.ptr(y), 1, 1, 5, 5, 1, 3, 3, -1, 1, U.st())
 
 
 # ------------------------------------------------------------------------------------------------- MaxPool
@@ -326,8 +328,7 @@ def test_optimizers_golden(U, name):
       n = p.numel()
       if name == 'adam':
         t = step + 1
-        U.call('ngb_adam_step', U.ptr(p), U.ptr(G), U.ptr(s1), U.ptr(s2), n, 0.05, 0.9, 0.999, 1e-8,
-               1.0 / (1 - 0.9 ** t), 1.0 / (1 - 0.999 ** t), 1.0, U.st())
+        U.call('ngb_adam_step', U.ptr(p), U.ptr(G), U.ptr(s1), U.ptr(s2), n, 0.05, 0.9, 0.999, 1e-8, t, 1.0, U.st())
         ref, r1, r2 = ops.adam_step(ref, gr, r1, r2, t, 0.05)
       elif name == 'gd':
         U.call('ngb_sgd_step', U.ptr(p), U.ptr(G), n, 0.1, 1.0, U.st())
@@ -349,9 +350,18 @@ def test_adam_large_flat_arena(U):
   p0, g0 = f32(rng.standard_normal(n)), f32(rng.standard_normal(n) * 0.1)
   p, G = U.dev(p0), U.dev(g0)
   m, v = torch.zeros_like(p), torch.zeros_like(p)
-  U.call('ngb_adam_step', U.ptr(p), U.ptr(G), U.ptr(m), U.ptr(v), n, 5e-3, 0.9, 0.999, 1e-8, 1 / (1 - 0.9), 1 / (1 - 0.999), 1.0,
-         U.st())
+  U.call('ngb_adam_step', U.ptr(p), U.ptr(G), U.ptr(m), U.ptr(v), n, 5e-3, 0.9, 0.999, 1e-8, 1, 1.0, U.st())
   ref, rm, rv = ops.adam_step(p0, g0, 0.0, 0.0, 1, 5e-3)
   close(U.host(p), ref, TOL32)
   close(U.host(m), rm, TOL32)
   close(U.host(v), rv, TOL32)
+  # graph-friendly variant: iteration count in device memory, incremented by the launch itself
+  p2, m2, v2 = U.dev(p0), torch.zeros_like(p), torch.zeros_like(p)
+  t_dev = torch.zeros(1, device='cuda', dtype=torch.int32)
+  for _ in range(3):
+    U.call('ngb_adam_step_dev', U.ptr(p2), U.ptr(G), U.ptr(m2), U.ptr(v2), n, 5e-3, 0.9, 0.999, 1e-8, U.ptr(t_dev), 1, 1.0, U.st())
+  ref, rm, rv = p0, 0.0, 0.0
+  for t in (1, 2, 3):
+    ref, rm, rv = ops.adam_step(ref, g0, rm, rv, t, 5e-3)
+  assert int(t_dev.item()) == 3
+  close(U.host(p2), ref, TOL32)

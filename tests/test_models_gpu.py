@@ -1,0 +1,213 @@
+"""GPU parity tests, step level: the BASELINE configs run through the public neograd API on the device and are
+compared with (a) trajectories recorded from the unmodified reference (tests/golden/step_*.npz, made by
+oracle/gen_golden.py) and (b) the CPU oracle on the same seeded inputs.
+
+Tolerances (dist = ||a-b||/(||a||+||b||)): first-step gradients 1e-5 on the fp32 SIMT path, 1e-3 where a Dot is large
+enough to go to the TF32 tensor cores (LeNet-B's 4096x256x120 Linear); loss trajectories 1e-4 / 2e-3; parameters after
+N Adam steps 1e-3 / 1e-2 (Adam's m/sqrt(v) normalisation amplifies the relative error of near-zero gradient entries)."""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import ops, models
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope='module')
+def ng():
+  import torch
+  if not torch.cuda.is_available():
+    pytest.skip('needs a CUDA device')
+  import neograd_b200
+  return neograd_b200
+
+
+def dist(a, b):
+  return ops.dist(np.asarray(a, float).ravel(), np.asarray(b, float).ravel())
+
+
+def _init(model, g):
+  from neograd_b200.configs import set_params
+  n = len(model.parameters())
+  set_params(model, [g[f'init_{i}'] for i in range(n)])
+  return n
+
+
+def test_c1_mlp_50_adam_steps(ng):
+  from neograd_b200.configs import MLPCircles, train_step
+  g = load_golden('step_c1_mlp')
+  np.random.seed(0)
+  model = MLPCircles()
+  n = _init(model, g)
+  X, y = ng.tensor(g['X']), ng.tensor(g['y'])
+  optim = ng.nn.optim.Adam(model.parameters(), 0.05)
+  loss_fn = ng.nn.loss.BCE()
+  losses = [float(train_step(model, optim, loss_fn, X, y).data) for _ in range(50)]
+  assert dist(losses, g['losses']) < 1e-4, dist(losses, g['losses'])
+  for i, p in enumerate(model.parameters()):
+    assert dist(p.data.numpy(), g[f'final_{i}']) < 2e-3, (i, dist(p.data.numpy(), g[f'final_{i}']))
+  # README.md:117-121 style evaluation works on device data
+  with model.eval():
+    out = model(X)
+  preds = np.where(out.data >= 0.5, 1, 0)
+  assert preds.shape == (750, 1)
+
+
+def test_c2_digits_batches(ng):
+  from neograd_b200.configs import DigitsCNN, train_step
+  g = load_golden('step_c2_digits')
+  np.random.seed(0)
+  model = DigitsCNN()
+  n = _init(model, g)
+  X, Y = ng.tensor(g['X']), ng.tensor(g['Y'])
+  optim = ng.nn.optim.Adam(model.parameters(), 5e-3)
+  loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+  losses = []
+  for _ in range(5):
+    for xb, yb in ng.nn.get_batches(X, Y, 200):
+      losses.append(float(train_step(model, optim, loss_fn, xb, yb).data))
+  assert dist(losses, g['losses']) < 1e-4, dist(losses, g['losses'])
+  for i, p in enumerate(model.parameters()):
+    assert dist(p.data.numpy(), g[f'final_{i}']) < 2e-3, (i, dist(p.data.numpy(), g[f'final_{i}']))
+
+
+@pytest.mark.parametrize('kind', ['a', 'b'])
+def test_c3_lenet_grads_and_steps(ng, kind):
+  from neograd_b200.configs import LeNetA, LeNetB, train_step
+  g = load_golden(f'step_c3{kind}_lenet')
+  np.random.seed(0)
+  model = (LeNetA if kind == 'a' else LeNetB)()
+  n = _init(model, g)
+  X, Y = ng.tensor(g['X']), ng.tensor(g['Y'])
+  loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+  loss = loss_fn(model(X), Y)
+  loss.backward()
+  for i, p in enumerate(model.parameters()):
+    d = dist(p.grad.numpy(), g[f'grad0_{i}'])
+    assert d < 1e-3, (i, d)
+  optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
+  losses = [float(train_step(model, optim, loss_fn, X, Y).data) for _ in range(4)]
+  assert dist(losses, g['losses']) < 2e-3, dist(losses, g['losses'])
+  for i, p in enumerate(model.parameters()):
+    d = dist(p.data.numpy(), g[f'final_{i}'])
+    assert d < 1e-2, (i, d)
+
+
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])
+@pytest.mark.parametrize('kind,batch', [('a', 4096), ('b', 512)])
+def test_c3_lenet_vs_oracle_at_size(ng, kind, batch, precision):
+  """Same seeded inputs through the device path and the float64 oracle at (close to) the BASELINE batch size, in both
+  precision modes.  Zero-initialised biases move by exactly lr*sign(g) in the first Adam steps, so entries whose
+  gradient is at rounding-noise level may flip: they are bounded in absolute terms (a fraction of lr * steps)."""
+  from neograd_b200.configs import lenet_synthetic, train_step
+  prev = ng.set_precision(precision)
+  try:
+    model, x, y = lenet_synthetic(kind, batch)
+    net = (models.lenet_a if kind == 'a' else models.lenet_b)(np.random.default_rng(0))
+    net.set_params([p.data.numpy() for p in model.parameters()])
+    X, Y = ng.tensor(x), ng.tensor(y)
+    lr, steps = 1e-3, 3
+    optim = ng.nn.optim.Adam(model.parameters(), lr)
+    oopt = models.Adam(net, lr)
+    loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+    dev_losses = [float(train_step(model, optim, loss_fn, X, Y).data) for _ in range(steps)]
+    ref_losses = [models.train_step(net, oopt, 'softmax_ce', x.astype(np.float64), y.astype(np.float64)) for _ in range(steps)]
+    tol_loss, tol_w, frac_b = (1e-5, 1e-4, 0.02) if precision == 'fp32' else (2e-3, 2e-3, 0.1)
+    assert dist(dev_losses, ref_losses) < tol_loss, (dev_losses, ref_losses)
+    for i, (p, r) in enumerate(zip(model.parameters(), net.params())):
+      got = p.data.numpy()
+      if i % 2 == 0:
+        assert dist(got, r) < tol_w, (i, dist(got, r))
+      else:   # bias: mean absolute deviation as a fraction of the distance travelled
+        assert np.mean(np.abs(got - r)) < frac_b * lr * steps, (i, np.mean(np.abs(got - r)) / (lr * steps))
+  finally:
+    ng.set_precision(prev)
+
+
+def test_gan_choreography_small(ng):
+  """examples/gans/basic.ipynb cells 9-10 at notebook scale: freeze/unfreeze, retain_graph, zero_grad(all_members),
+  two Adam instances over model.parameters() sharing the moments stored on the Params."""
+  from neograd_b200.configs import GAN, set_params
+  nn = ng.nn
+  np.random.seed(0)
+  model = GAN(64, 50, 25)
+  rng = np.random.default_rng(0)
+  set_params(model, [0.05 * rng.standard_normal(p.shape) for p in model.parameters()])   # plain randn saturates the sigmoid
+  real = ng.tensor(rng.standard_normal((200, 64)))
+  optim_g, optim_d = nn.optim.Adam(model.parameters(), 5e-3), nn.optim.Adam(model.parameters(), 5e-3)
+  loss_fn = nn.loss.BCE()
+  ones, zeros = ng.tensor(np.ones((200, 1))), ng.tensor(np.zeros((200, 1)))
+  before = [p.data.numpy().copy() for p in model.parameters()]
+  for _ in range(2):
+    # generator step
+    model.discriminator.freeze()
+    optim_g.zero_grad(all_members=True)
+    noise = ng.tensor(rng.standard_normal((200, 64)))
+    loss_g = loss_fn(model(noise), ones)
+    loss_g.backward()
+    optim_g.step()
+    model.discriminator.unfreeze()
+    # discriminator step
+    model.generator.freeze()
+    optim_d.zero_grad(all_members=True)
+    fake = model.generator(ng.tensor(rng.standard_normal((200, 64))))
+    loss_d = loss_fn(model.discriminator(real), ones) + loss_fn(model.discriminator(fake), zeros)
+    loss_d.backward()
+    optim_d.step()
+    model.generator.unfreeze()
+  assert np.isfinite(float(loss_g.data)) and np.isfinite(float(loss_d.data))
+  after = [p.data.numpy() for p in model.parameters()]
+  assert all(np.any(a != b) for a, b in zip(after, before))
+  assert optim_g.iter == 2 and optim_d.iter == 2
+  assert model.parameters()[0].momentum_grad.shape == model.parameters()[0].shape
+
+
+def test_grad_check_passes_on_device(ng):
+  """neograd's acceptance tool (autograd/utils.py:195-234) with device-appropriate epsilon."""
+  from neograd_b200.configs import MLPCircles
+  np.random.seed(3)
+  model = MLPCircles()
+  rng = np.random.default_rng(0)
+  X, y = ng.tensor(rng.standard_normal((64, 2))), ng.tensor(rng.integers(0, 2, (64, 1)).astype(float))
+  d = ng.grad_check(model, X, y, ng.nn.loss.MSE(), print_vals=False)
+  assert d < 1e-2, d
+
+
+def test_engine_semantics(ng):
+  t = ng.tensor
+  a = t(np.arange(6.).reshape(2, 3), requires_grad=True)
+  b = t([[1., 2., 3.]], requires_grad=True)
+  c = ((a * b) + 2).sum()
+  assert a.grad == 0. and t([1.]).grad is None                    # tensor.py:36
+  c.backward()
+  assert np.allclose(a.grad.numpy(), [[1, 2, 3], [1, 2, 3]])
+  assert np.allclose(b.grad.numpy(), [[3, 5, 7]])                  # unbroadcast over axis 0 (utils.py:34-78)
+  assert len(ng._NG_GRAPH.nodes_dict) == 0                         # graph reset after backward (tensor.py:72-73)
+  with pytest.raises(ValueError):
+    t([1., 2.]).backward()                                         # tensor.py:62-63
+  with pytest.raises(ValueError):
+    (a * 2).backward([1., 2.])                                     # tensor.py:67-68 shape mismatch
+  ng._NG_GRAPH.reset_graph()
+  with pytest.raises(TypeError):
+    t('abc')                                                       # utils.py:28-31
+  with pytest.raises(TypeError):
+    t(np.float64(3.0))                                             # exact-type check, SURVEY A.4
+  with pytest.raises(TypeError):
+    a[np.array([0])]                                               # tensor.py:351-354
+  with ng.no_track():
+    d = a * 3
+  assert ng._NG_GRAPH.get_node(d) is None
+  with ng.new_graph():
+    e = (a + 1).sum()
+    e.backward()
+  assert np.allclose(a.grad.numpy(), [[2, 3, 4], [2, 3, 4]])       # accumulated on top of the first backward
+  with pytest.raises(AssertionError):
+    ng.nn.Conv2D((3, 3), stride=0)(t(np.zeros((1, 5, 5))))         # conv.py:33
+  with pytest.raises(ValueError):
+    ng.nn.Conv2D((3, 3))(t(np.zeros((1, 1, 5, 5))))                # conv.py:214-215
+  with pytest.raises(ValueError):
+    ng.nn.MaxPool2D((2, 2, 2))                                     # layers/conv.py:108-109
+  lin = ng.nn.Linear(3, 2)
+  with pytest.raises(AttributeError):
+    lin.weights = ng.nn.layers.Param(np.zeros((3, 2)))             # layers/__init__.py:187-188
