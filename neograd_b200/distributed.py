@@ -54,7 +54,8 @@ def rank():
 def all_reduce_sum(arr):
   """In-place sum over ranks of a flat DeviceArray (or any object with a torch tensor in `.t`, or a torch tensor)."""
   import torch.distributed as td
-  td.all_reduce(getattr(arr, 't', arr), op=td.ReduceOp.SUM)
+  import torch
+  td.all_reduce(arr if isinstance(arr, torch.Tensor) else arr.t, op=td.ReduceOp.SUM)
 
 
 def shard(n, r=None, w=None):

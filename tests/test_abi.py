@@ -1,0 +1,56 @@
+"""CPU checks of the drop-in boundary: the library loads, exports every symbol include/ngb200.h declares, the ctypes
+table matches the header, and the product package never reaches into the oracle (no CPU fallback)."""
+import os
+import re
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def header_functions():
+  text = open(os.path.join(ROOT, 'include', 'ngb200.h')).read()
+  text = re.sub(r'/\*.*?\*/', '', text, flags=re.S)
+  decls = re.findall(r'\b(?:int|int64_t|const char\*)\s+(ngb_\w+)\s*\(([^;]*?)\)\s*;', text, flags=re.S)
+  return {name: [a.strip() for a in args.split(',')] if args.strip() != 'void' else [] for name, args in decls}
+
+
+def test_library_exports_every_declared_symbol():
+  import ctypes
+  from neograd_b200 import _backend as B
+  fns = header_functions()
+  assert len(fns) >= 30
+  cdll = ctypes.CDLL(B.LIB_PATH)
+  for name in fns:
+    assert hasattr(cdll, name), f'{name} is declared in include/ngb200.h but not exported by libngb200.so'
+  assert cdll.ngb_abi_version() == 1
+
+
+def test_ctypes_table_matches_header():
+  from neograd_b200 import _backend as B
+  fns = header_functions()
+  assert set(fns) == set(B.SIGNATURES), set(fns) ^ set(B.SIGNATURES)
+  for name, args in fns.items():
+    assert len(args) == len(B.SIGNATURES[name][0]), (name, args, B.SIGNATURES[name][0])
+
+
+def test_no_compute_without_gpu_and_error_reporting():
+  import torch
+  from neograd_b200 import _backend as B
+  if torch.cuda.is_available():
+    return
+  try:
+    B.ensure_runtime()
+  except B.NgbError as e:
+    assert 'no CPU fallback' in str(e)
+  else:
+    raise AssertionError('ensure_runtime() must fail loudly without a CUDA device')
+
+
+def test_product_never_imports_oracle():
+  bad = []
+  for dp, _, files in os.walk(os.path.join(ROOT, 'neograd_b200')):
+    for f in files:
+      if f.endswith(('.py', '.cu', '.cuh', '.h')):
+        src = open(os.path.join(dp, f)).read()
+        if re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M) or 'oracle/' in src and f.endswith('.py') and 'import' in src and re.search(r'import.*oracle', src):
+          bad.append(os.path.join(dp, f))
+  assert not bad, bad
