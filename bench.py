@@ -285,13 +285,15 @@ def run_device(args):
   barrier()
   e2e_s = max_over_ranks(time.perf_counter() - t0)
 
-  # ---- per-kernel breakdown of one eager step (CUDA events around every C-ABI call), rank 0
+  # ---- per-kernel breakdown of one eager step (CUDA events around every C-ABI call).  Every rank runs the steps (they
+  # contain the gradient allreduce); rank 0 keeps the numbers.
   roofline, breakdown = None, None
+  reps = 5
+  with B.profile_calls() as prof:
+    for _ in range(reps):
+      step()
+  barrier()
   if rank == 0:
-    reps = 5
-    with B.profile_calls() as prof:
-      for _ in range(reps):
-        step()
     summ = prof.summary()
     total_ms = sum(d['ms'] for d in summ.values())
     breakdown = {k: {'calls_per_step': d['calls'] // reps, 'ms_per_step': d['ms'] / reps, 'share': d['ms'] / total_ms}
@@ -341,9 +343,14 @@ def run_device(args):
       'eager': {'value': total_samples / (eager_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': eager_ms / args.steps},
       'roofline': roofline, 'cpu_baseline': cpu, 'kernel_breakdown_eager': breakdown,
     }
-    print(json.dumps(out))
+    print(json.dumps(out), flush=True)
   if world > 1:
-    dist.destroy()
+    # NCCL teardown after a graph-captured collective was seen to hang on exit: synchronise, then leave without running
+    # the communicator destructors (the process is ending anyway).
+    barrier()
+    sys.stdout.flush()
+    sys.stderr.flush()
+    os._exit(0)
 
 
 def main():

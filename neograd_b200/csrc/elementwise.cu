@@ -202,6 +202,43 @@ __global__ void __launch_bounds__(256) ew_bwd_colreduce_kernel(int op, int side,
   }
 }
 
+// Column sum of ug itself (the local gradient of add / sub / identity is +-1): the bias-gradient hot case.  128-bit loads,
+// 4 independent loads in flight per thread, CTA = 128 columns x 8 row lanes.
+__global__ void __launch_bounds__(256) colsum4_kernel(const float* __restrict__ ug, float* __restrict__ dst, int accumulate,
+                                                      int64_t R, int64_t K4, int64_t rows_per_split, float scale) {
+  __shared__ float4 tile[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int64_t c4 = (int64_t)blockIdx.x * 32 + tx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_split;
+  const int64_t r1 = min(R, r0 + rows_per_split);
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (c4 < K4) {
+    const float* base = ug + 4 * c4;
+    int64_t r = r0 + ty;
+    for (; r + 24 < r1; r += 32) {
+      const float4 a = ld_stream4(base + r * K4 * 4), b = ld_stream4(base + (r + 8) * K4 * 4);
+      const float4 c = ld_stream4(base + (r + 16) * K4 * 4), d = ld_stream4(base + (r + 24) * K4 * 4);
+      acc.x += (a.x + b.x) + (c.x + d.x); acc.y += (a.y + b.y) + (c.y + d.y);
+      acc.z += (a.z + b.z) + (c.z + d.z); acc.w += (a.w + b.w) + (c.w + d.w);
+    }
+    for (; r < r1; r += 8) {
+      const float4 a = ld_stream4(base + r * K4 * 4);
+      acc.x += a.x; acc.y += a.y; acc.z += a.z; acc.w += a.w;
+    }
+  }
+  tile[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && c4 < K4) {
+    float4 s4 = tile[0][tx];
+#pragma unroll
+    for (int j = 1; j < 8; ++j) { const float4 t = tile[j][tx]; s4.x += t.x; s4.y += t.y; s4.z += t.z; s4.w += t.w; }
+    s4.x *= scale; s4.y *= scale; s4.z *= scale; s4.w *= scale;
+    float4* o = reinterpret_cast<float4*>(dst + ((int64_t)blockIdx.y * K4 + c4) * 4);
+    if (accumulate && gridDim.y == 1) { const float4 old = *o; s4.x += old.x; s4.y += old.y; s4.z += old.z; s4.w += old.w; }
+    *o = s4;
+  }
+}
+
 // Full reduction, pattern [R]: every CTA grid-strides the whole range and leaves one partial.
 __global__ void __launch_bounds__(256) ew_bwd_fullreduce_kernel(int op, int side, const float* __restrict__ ug,
                                                                 const float* __restrict__ a, float as, int64_t sa0,
@@ -493,6 +530,31 @@ static int reduce_dispatch(int op, int side, const BDims& d, int64_t total, cons
   if (col_pat) {
     const int64_t Kc = d.size[1], Rc = d.size[0];
     const int64_t sa0 = d.sa[0], sa1 = d.sa[1], sb0 = d.sb[0], sb1 = d.sb[1];
+    // local gradient == +-ug (add, sub, identity): vectorised column sum
+    const bool plain = op == NGB_ADD || op == NGB_SUB || op == OP_IDENT || (op == NGB_SECOND && side == 1);
+    if (plain && Kc % 4 == 0 && aligned16(ug) && aligned16(grad)) {
+      const float scale = (op == NGB_SUB && side == 1) ? -1.f : 1.f;
+      const int64_t K4 = Kc / 4, cb = ceil_div<int64_t>(K4, 32);
+      int64_t splits = ceil_div<int64_t>(4 * kNumSMs, cb);
+      const int64_t max_splits = ceil_div<int64_t>(Rc, 128);
+      if (splits > max_splits) splits = max_splits;
+      if (splits < 1) splits = 1;
+      if (splits > 1) {
+        NGB_CHECK_ARG(ensure_init() == NGB_OK, "scratch init failed");
+        if (splits * Kc * (int64_t)sizeof(float) > scratch_bytes()) splits = scratch_bytes() / (Kc * sizeof(float));
+        if (splits < 1) splits = 1;
+      }
+      const int64_t rps = ceil_div<int64_t>(Rc, splits);
+      splits = ceil_div<int64_t>(Rc, rps);
+      dim3 grid((unsigned)cb, (unsigned)splits);
+      colsum4_kernel<<<grid, 256, 0, st>>>(ug, splits > 1 ? scratch_ptr() : grad, accumulate, Rc, K4, rps, scale);
+      NGB_LAUNCH_CHECK();
+      if (splits > 1) {
+        sum_partials_kernel<<<grid_for(Kc, 256), 256, 0, st>>>(scratch_ptr(), (int)splits, Kc, grad, accumulate);
+        NGB_LAUNCH_CHECK();
+      }
+      return NGB_OK;
+    }
     const int64_t colblocks = ceil_div<int64_t>(Kc, 32);
     int64_t splits = ceil_div<int64_t>(2 * kNumSMs, colblocks);
     const int64_t max_splits = ceil_div<int64_t>(Rc, 64);
