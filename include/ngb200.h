@@ -53,6 +53,9 @@ const char* ngb_last_error(void);
 /* Allocates the per-device scratch arena (bytes; 0 = default 64 MiB). Idempotent; must run before graph capture. */
 int ngb_init(int64_t scratch_bytes);
 int ngb_shutdown(void);
+/* Pre-sizes the grow-on-demand workspace the tensor-core convolutions stage their channels-last operand copies in
+ * (N*C*H*W*4 bytes of the largest staged tensor).  Only needed before CUDA-graph capture, where growing is not allowed. */
+int ngb_workspace_reserve(int64_t bytes);
 /* Process-wide precision mode: what NGB_GEMM_AUTO (and the conv dispatcher) resolve to.  NGB_GEMM_AUTO (default) = TF32
  * tensor cores whenever the shape qualifies; NGB_GEMM_SIMT = exact-fp32 CUDA-core kernels everywhere (parity runs,
  * grad_check); NGB_GEMM_TCGEN05 is not a valid default.  Returns the previous value. */

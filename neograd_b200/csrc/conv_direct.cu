@@ -286,7 +286,8 @@ extern "C" int ngb_conv_fprop(const float* x, const float* w, const float* b, fl
   if (rc) return rc;
   if (N == 0) return NGB_OK;
   cudaStream_t st = as_stream(stream);
-  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride)) return conv_igemm_fprop(x, w, b, y, N, C, H, W, O, KH, KW, pad, st);
+  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(x) && aligned16(y) && aligned16(w))
+    return conv_igemm_fprop(x, w, b, y, N, C, H, W, O, KH, KW, pad, st);
   // tile shape: p (fastest output axis) first
   int TP = g.Ho < 16 ? g.Ho : 16;
   int TQ = 256 / TP; if (TQ > g.Wo) TQ = g.Wo;
@@ -315,7 +316,7 @@ extern "C" int ngb_conv_dgrad(const float* ug, const float* w, float* dx, int64_
   if (rc) return rc;
   if (N == 0) return NGB_OK;
   cudaStream_t st = as_stream(stream);
-  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride))
+  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(ug) && aligned16(dx) && aligned16(w))
     return conv_igemm_dgrad(ug, w, dx, N, C, H, W, O, KH, KW, pad, accumulate, st);
   int TW = g.W < 32 ? g.W : 32;
   int TH = 256 / TW; if (TH > g.H) TH = g.H;

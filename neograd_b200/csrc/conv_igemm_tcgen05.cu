@@ -1,9 +1,416 @@
-// Implicit-GEMM convolution on tcgen05 (placeholder dispatcher: filled in by the TMA-fed kernel).
+// Implicit-GEMM convolution on the 5th-generation tensor cores (tcgen05 / TMEM), operands fed by TMA.
+// Covers the multi-channel, stride-1 layers of the C5 sweep (Conv3D, neograd/autograd/ops/conv.py:245-269 forward,
+// 299-309 data gradient, 311-321 weight gradient); everything else stays on the direct kernels (conv_direct.cu).
+//
+// Forward and data-gradient are the same "transposing" convolution in neograd's layouts:
+//     out[n, co, j1, j0] = bias[co] + sum_{t1,t0,ci} in[n, ci, i1 = j0 + t1 - pad1, i0 = j1 + t0 - pad0] * Wp[t1*T0+t0][co][ci]
+// where i0 / j0 are the CONTIGUOUS axes of in / out; the output's fast axis runs along the input's slow spatial axis:
+//   forward : in = x  (i0 = w, i1 = h),  out = y  in neograd order (j0 = p along h, j1 = q along w; conv.py:39-47 vs 149-151)
+//   dgrad   : in = ug (i0 = p, i1 = q),  out = dx natural layout   (j0 = w, j1 = h), filter flipped, pad' = K-1-pad
+//
+// Why a staging pass: a filter tap shifts the input by one ELEMENT along its contiguous axis, and a TMA box must start
+// on a 16-byte boundary in global memory (tools/tma_probe.cu: a swizzled box at inner coordinate -1 faults).  So the
+// input is first re-laid out channels-innermost, S[n][i0][i1][c] (one read + one write of the input, rounding to TF32
+// on the way), after which every tap is a shift on OUTER tensor-map dimensions and padding is TMA's zero fill.
+//
+// GEMM view per work item: D[128 positions, BN channels] += A[128, K] * B[K, BN],  K = taps x Cin.
+//   * A (K-major, 128B swizzle): ONE 4-D box {32 c, 32 along i1, 4 along i0, 1 image} per K-block = (tap, 32 channels):
+//     row r = di0*32 + di1, so TMEM lane (r mod 32) walks the output's contiguous axis j0 and the epilogue stores are
+//     128-byte coalesced with no shuffle.
+//   * B (K-major): weights pre-packed once per call into Wp[tap][co][ci] (scratch arena), boxes {32 ci, BN co}.
+//   * accumulators in TMEM (2 x BN columns, double buffered); epilogue warps tcgen05.ld -> (+bias / +=) -> global.
+// Weight gradient: dw[o,c,tap] = sum_positions ug[pos, o] * x[pos + tap, c] with BOTH operands read from their staged
+// (channels-innermost = MN-major) form, K = positions, split over CTAs with a deterministic second pass.
+// Warp roles are those of gemm_tcgen05.cu: warp 0 TMA producer, warp 1 MMA issuer + TMEM owner, warps 2-5 epilogue.
 #include "tc_common.cuh"
+
+#include <mutex>
+
 namespace ngb {
-int conv_igemm_eligible(int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t) { return 0; }
-int conv_igemm_fprop(const float*, const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                     int64_t, int64_t, cudaStream_t) { return fail(NGB_ERR_UNSUPPORTED, "conv igemm not built"); }
-int conv_igemm_dgrad(const float*, const float*, float*, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t, int64_t,
-                     int64_t, int, cudaStream_t) { return fail(NGB_ERR_UNSUPPORTED, "conv igemm not built"); }
+
+using namespace tc;
+
+int launch_splitk_reduce(const float* part, int splits, int64_t M, int64_t N, float* C, int64_t ldc, int accumulate,
+                         cudaStream_t st);
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int BLOCK_M = 128;
+constexpr int BLOCK_K = 32;       // channels per K-block
+constexpr int UMMA_K = 8;
+constexpr int TILE_J0 = 32;       // output extent along its contiguous axis (= i1 direction): one 128-byte line per warp store
+constexpr int TILE_J1 = 4;        // output extent along j1 (= i0 direction): one TMEM lane quadrant each
+
+template <int BLOCK_N>
+struct Cfg {
+  static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;   // 16 KB
+  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+};
+
+struct IgemmArgs {
+  int N, Cin, Cout;
+  int I0, I1, J0, J1;        // input / output spatial extents (contiguous axis first)
+  int T0, T1, pad0, pad1;    // taps along i0 / i1 and the padding on those axes
+  int tiles_j0, tiles_j1, tiles_co;
+  int cblocks;               // Cin / 32
+  float* out;
+  const float* bias;         // may be null
+  int accumulate;
+};
+
+// ---------------------------------------------------------------------------------------------- staging
+// in[n][c][i1][i0] -> S[n][i0][i1][c] (TF32-rounded).  32 x 32 (c, i0) tiles through padded smem: reads coalesced
+// along i0, writes coalesced along c.
+__device__ __forceinline__ float to_tf32(float v) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(v));
+  return __uint_as_float(r);
+}
+
+__global__ void __launch_bounds__(256) stage_channels_last_kernel(const float* __restrict__ in, float* __restrict__ S, int N, int C,
+                                                                  int I1, int I0, FastDiv d_t0, FastDiv d_tc, FastDiv d_i1) {
+  __shared__ float tile[32][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int t0n = (I0 + 31) >> 5, tcn = (C + 31) >> 5;
+  const int64_t items = (int64_t)N * I1 * tcn * t0n;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    uint32_t r, b0, bc, n, i1;
+    d_t0.divmod((uint32_t)it, r, b0);   // items < 2^32 is checked by the caller
+    d_tc.divmod(r, r, bc);
+    d_i1.divmod(r, n, i1);
+    const int c0 = bc * 32, i00 = b0 * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int c = c0 + ty + j, i0 = i00 + tx;
+      tile[ty + j][tx] = (c < C && i0 < I0) ? __ldg(in + (((int64_t)n * C + c) * I1 + i1) * I0 + i0) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) {
+      const int i0 = i00 + ty + j, c = c0 + tx;
+      if (i0 < I0 && c < C) S[(((int64_t)n * I0 + i0) * I1 + i1) * C + c] = to_tf32(tile[tx][ty + j]);
+    }
+    __syncthreads();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- fprop / dgrad kernel
+template <int BLOCK_N>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w, const IgemmArgs g) {
+  using C_ = Cfg<BLOCK_N>;
+  constexpr int kStages = C_::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * C_::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_in);
+    prefetch_tmap(&tmap_w);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C_::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = g.T0 * g.T1;
+  const int kblocks = taps * g.cblocks;
+  const int tiles_sp = g.tiles_j0 * g.tiles_j1;
+  const int64_t num_work = (int64_t)g.N * tiles_sp * g.tiles_co;
+
+  // work item -> (n, tile_j1, tile_j0, co tile); co fastest so CTAs that run together share the A tile in L2
+  auto decode = [&](int64_t w, int& n, int& j0b, int& j1b, int& co0) {
+    const int ct = (int)(w % g.tiles_co);
+    int64_t r = w / g.tiles_co;
+    const int sp = (int)(r % tiles_sp);
+    n = (int)(r / tiles_sp);
+    j0b = (sp % g.tiles_j0) * TILE_J0;
+    j1b = (sp / g.tiles_j0) * TILE_J1;
+    co0 = ct * BLOCK_N;
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int n, j0b, j1b, co0;
+        decode(w, n, j0b, j1b, co0);
+        for (int t1 = 0; t1 < g.T1; ++t1) {
+          for (int t0 = 0; t0 < g.T0; ++t0) {
+            const int tap = t1 * g.T0 + t0;
+            for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
+              const int s = it % kStages;
+              const uint32_t ph = (it / kStages) & 1;
+              mbar_wait(&empty[s], ph ^ 1, 1);
+              mbar_arrive_expect_tx(&full[s], C_::kStageBytes);
+              // staged input dims {c, i1, i0, n}: the tap is a shift of the two spatial (outer) coordinates
+              tma_load_4d(smem_a + s * C_::kABytes, &tmap_in, &full[s], cb * BLOCK_K, j0b + t1 - g.pad1, j1b + t0 - g.pad0, n);
+              tma_load_2d(smem_b + s * C_::kBBytes, &tmap_w, &full[s], cb * BLOCK_K, tap * g.Cout + co0);
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
+      constexpr uint64_t desc_base = make_smem_desc_base(16, 1024);   // K-major, 128B swizzle (both operands)
+      uint32_t it = 0, tile_it = 0;
+      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+        const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < kblocks; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph, 3);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * C_::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * C_::kBBytes);
+#pragma unroll
+          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+            umma_tf32(d_tmem, smem_desc(desc_base, a_addr + k * UMMA_K * 4), smem_desc(desc_base, b_addr + k * UMMA_K * 4), idesc,
+                      (kb > 0 || k > 0) ? 1u : 0u);
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(&tmem_full[acc]);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int quad = warp & 3;                // TMEM lane quadrant == offset along j1; lane == offset along j0
+    uint32_t tile_it = 0;
+    const int64_t plane = (int64_t)g.J0 * g.J1;
+    for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+      int n, j0b, j1b, co0;
+      decode(w, n, j0b, j1b, co0);
+      const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
+      mbar_wait(&tmem_full[acc], acc_ph, 4);
+      tc_fence_after();
+      const int j0 = j0b + lane, j1 = j1b + quad;
+      const bool ok = j0 < g.J0 && j1 < g.J1;
+      float* obase = g.out + ((int64_t)n * g.Cout + co0) * plane + (int64_t)j1 * g.J0 + j0;
+#pragma unroll 1
+      for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
+        float v[32];
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + c0, v);
+        tmem_ld_wait();
+        if (c0 + 32 >= BLOCK_N) {
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+        }
+        if (ok) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int co = co0 + c0 + j;
+            if (co < g.Cout) {
+              float r = v[j];
+              if (g.bias) r += __ldg(g.bias + co);
+              float* o = obase + (int64_t)(c0 + j) * plane;
+              *o = g.accumulate ? *o + r : r;
+            }
+          }
+        }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C_::kTmemCols);
+  }
+}
+
+// Wp[tap][co][ci]: forward  tap = kh*KW + kw,                         co = o, ci = c
+//                  dgrad    tap = t1*T0 + t0 with kh = KH-1-t0, kw = KW-1-t1 (T0 = KH, T1 = KW), co = c, ci = o
+__global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int O, int C,
+                                                           int KH, int KW, int dgrad) {
+  const int64_t total = (int64_t)O * C * KH * KW;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    // i enumerates the destination so writes are coalesced
+    if (!dgrad) {
+      const int c = (int)(i % C);
+      const int o = (int)((i / C) % O);
+      const int tap = (int)(i / ((int64_t)C * O));
+      const int kh = tap / KW, kw = tap % KW;
+      wp[i] = to_tf32(__ldg(w + (((int64_t)o * C + c) * KH + kh) * KW + kw));
+    } else {
+      const int o = (int)(i % O);
+      const int c = (int)((i / O) % C);
+      const int tap = (int)(i / ((int64_t)C * O));
+      const int t1 = tap / KH, t0 = tap % KH;
+      const int kh = KH - 1 - t0, kw = KW - 1 - t1;
+      wp[i] = to_tf32(__ldg(w + (((int64_t)o * C + c) * KH + kh) * KW + kw));
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- workspace
+// Staged copies of activations can be GBs (C5: 4.3 GB), so they live in a grow-on-demand buffer of their own rather
+// than in the fixed scratch arena.  Growing allocates, so it must not happen inside a CUDA-graph capture: callers that
+// capture call ngb_workspace_reserve() first.
+std::mutex g_ws_mu;
+float* g_ws = nullptr;
+int64_t g_ws_bytes = 0;
+
+int workspace(int64_t bytes, float** out, cudaStream_t st) {
+  std::lock_guard<std::mutex> lk(g_ws_mu);
+  if (bytes > g_ws_bytes) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cs);
+    if (cs != cudaStreamCaptureStatusNone)
+      return fail(NGB_ERR_SCRATCH, "conv workspace (%lld bytes) must be reserved with ngb_workspace_reserve() before graph capture",
+                  (long long)bytes);
+    if (g_ws) {
+      NGB_CUDA(cudaDeviceSynchronize());
+      NGB_CUDA(cudaFree(g_ws));
+      g_ws = nullptr;
+      g_ws_bytes = 0;
+    }
+    const int64_t want = bytes + (bytes >> 3);
+    NGB_CUDA(cudaMalloc(&g_ws, want));
+    g_ws_bytes = want;
+  }
+  *out = g_ws;
+  return NGB_OK;
+}
+
+int stage(const float* in, float* S, int64_t N, int64_t C, int64_t I1, int64_t I0, cudaStream_t st) {
+  const int64_t t0n = ceil_div<int64_t>(I0, 32), tcn = ceil_div<int64_t>(C, 32);
+  const int64_t items = N * I1 * tcn * t0n;
+  if (items >= (int64_t(1) << 32)) return fail(NGB_ERR_UNSUPPORTED, "conv igemm: tensor too large to stage");
+  const int grid = (int)(items < (int64_t)kNumSMs * 16 ? items : (int64_t)kNumSMs * 16);
+  stage_channels_last_kernel<<<grid, 256, 0, st>>>(in, S, (int)N, (int)C, (int)I1, (int)I0, FastDiv((uint32_t)t0n),
+                                                  FastDiv((uint32_t)tcn), FastDiv((uint32_t)I1));
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+template <int BN>
+int launch_igemm(const CUtensorMap& tin, const CUtensorMap& tw, const IgemmArgs& g, int grid, cudaStream_t st) {
+  using C_ = Cfg<BN>;
+  auto kern = conv_igemm_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(tin, tw, g);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+// The shared host path.  `in` is [N][Cin][I1][I0]; out is [N][Cout][J1][J0].
+int run_igemm(const float* in, const float* w, const float* bias, float* out, int64_t N, int64_t Cin, int64_t Cout, int64_t I0,
+              int64_t I1, int64_t T0, int64_t T1, int64_t pad0, int64_t pad1, int64_t O, int64_t C, int64_t KH, int64_t KW,
+              int dgrad, int accumulate, cudaStream_t st) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  const int64_t wp_elems = O * C * KH * KW;
+  if (wp_elems * 4 > scratch_bytes()) return fail(NGB_ERR_SCRATCH, "conv igemm: packed weights do not fit the scratch arena");
+  float* wp = scratch_ptr();
+  pack_weights_kernel<<<grid_for(wp_elems, 256), 256, 0, st>>>(w, wp, (int)O, (int)C, (int)KH, (int)KW, dgrad);
+  NGB_LAUNCH_CHECK();
+
+  float* S = nullptr;
+  rc = workspace(N * Cin * I0 * I1 * 4, &S, st);
+  if (rc) return rc;
+  rc = stage(in, S, N, Cin, I1, I0, st);
+  if (rc) return rc;
+
+  IgemmArgs g;
+  g.N = (int)N; g.Cin = (int)Cin; g.Cout = (int)Cout;
+  g.I0 = (int)I0; g.I1 = (int)I1;
+  g.J0 = (int)(I1 + 2 * pad1 - T1 + 1);
+  g.J1 = (int)(I0 + 2 * pad0 - T0 + 1);
+  g.T0 = (int)T0; g.T1 = (int)T1; g.pad0 = (int)pad0; g.pad1 = (int)pad1;
+  g.tiles_j0 = ceil_div(g.J0, TILE_J0);
+  g.tiles_j1 = ceil_div(g.J1, TILE_J1);
+  const int BN = Cout <= 64 ? 64 : (Cout <= 128 ? 128 : 256);
+  g.tiles_co = (int)ceil_div<int64_t>(Cout, BN);
+  g.cblocks = (int)(Cin / BLOCK_K);
+  g.out = out; g.bias = bias; g.accumulate = accumulate;
+
+  CUtensorMap tin, tw;
+  {
+    const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)I1, (uint64_t)I0, (uint64_t)N};
+    const uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)Cin * I1 * 4, (uint64_t)Cin * I1 * I0 * 4};
+    const uint32_t box[4] = {BLOCK_K, TILE_J0, TILE_J1, 1};
+    rc = make_tmap_f32(&tin, S, 4, dims, str, box, false);
+    if (rc) return rc;
+    const uint64_t wdims[2] = {(uint64_t)Cin, (uint64_t)(T0 * T1 * Cout)};
+    const uint64_t wstr[1] = {(uint64_t)Cin * 4};
+    const uint32_t wbox[2] = {BLOCK_K, (uint32_t)BN};
+    rc = make_tmap_f32(&tw, wp, 2, wdims, wstr, wbox, false);
+    if (rc) return rc;
+  }
+  const int64_t work = (int64_t)N * g.tiles_j0 * g.tiles_j1 * g.tiles_co;
+  const int grid = (int)(work < kNumSMs ? work : kNumSMs);
+  if (BN == 64) rc = launch_igemm<64>(tin, tw, g, grid, st);
+  else if (BN == 128) rc = launch_igemm<128>(tin, tw, g, grid, st);
+  else rc = launch_igemm<256>(tin, tw, g, grid, st);
+  return rc;
+}
+
+}  // namespace
+
+int conv_igemm_eligible(int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW, int64_t pad,
+                        int64_t stride) {
+  if (g_default_engine.load() == NGB_GEMM_SIMT) return 0;
+  if (stride != 1) return 0;
+  if (C % 32 || O % 32) return 0;                       // K-blocks of 32 channels for both passes
+  if (pad > KH - 1 || pad > KW - 1) return 0;            // dgrad's pad' = K-1-pad must stay >= 0
+  const int64_t Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+  if (Ho < 1 || Wo < 1) return 0;
+  if (N * Ho * Wo < 4096) return 0;                      // tiny problems: the direct kernel is launch-bound anyway
+  if (N > 0x7fffffff || (int64_t)C * H * W > 0x7fffffff) return 0;
+  return 1;
+}
+
+int conv_igemm_fprop(const float* x, const float* w, const float* b, float* y, int64_t N, int64_t C, int64_t H, int64_t W,
+                     int64_t O, int64_t KH, int64_t KW, int64_t pad, cudaStream_t st) {
+  // in = x: i0 = w (taps kw), i1 = h (taps kh)
+  return run_igemm(x, w, b, y, N, C, O, /*I0=*/W, /*I1=*/H, /*T0=*/KW, /*T1=*/KH, pad, pad, O, C, KH, KW, 0, 0, st);
+}
+
+int conv_igemm_dgrad(const float* ug, const float* w, float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O,
+                     int64_t KH, int64_t KW, int64_t pad, int accumulate, cudaStream_t st) {
+  const int64_t Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+  // in = ug (neograd order): i0 = p (taps along kh, flipped), i1 = q (taps along kw, flipped)
+  return run_igemm(ug, w, nullptr, dx, N, O, C, /*I0=*/Ho, /*I1=*/Wo, /*T0=*/KH, /*T1=*/KW, KH - 1 - pad, KW - 1 - pad, O, C, KH,
+                   KW, 1, accumulate, st);
+}
+
 }  // namespace ngb
+
+using namespace ngb;
+
+extern "C" int ngb_workspace_reserve(int64_t bytes) {
+  float* p = nullptr;
+  return workspace(bytes, &p, nullptr);
+}

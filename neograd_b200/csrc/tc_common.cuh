@@ -64,16 +64,27 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+// On timeout the waiter records (tag, block, thread) in a per-translation-unit device word and leaves the kernel with
+// `exit` (its peers time out the same way), so a pipeline bug ends as a reported error, not a wedged or poisoned context.
+static __device__ unsigned long long g_mbar_timeout = 0;
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 2000000000ull) {
-      printf("ngb200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
-      __trap();
+    if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 1000000000ull) {
+      atomicCAS(&g_mbar_timeout, 0ull,
+                (1ull << 63) | ((unsigned long long)tag << 48) | ((unsigned long long)blockIdx.x << 16) | threadIdx.x);
+      asm volatile("exit;");
     }
   }
+}
+// Host side: reads and clears this translation unit's timeout word (0 = no timeout).
+inline unsigned long long take_mbar_timeout() {
+  unsigned long long v = 0, z = 0;
+  cudaMemcpyFromSymbol(&v, g_mbar_timeout, sizeof(v));
+  if (v) cudaMemcpyToSymbol(g_mbar_timeout, &z, sizeof(z));
+  return v;
 }
 
 // ---------------------------------------------------------------------------------------------- TMA

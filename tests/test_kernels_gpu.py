@@ -245,6 +245,43 @@ def test_conv_direct(U, N, C, H, W, O, KH, KW, pad, stride):
   close(U.conv_bgrad(ug), ops.conv3d_bgrad(ug), 2 * TOL32)
 
 
+IGEMM_CASES = [   # N, C, H, W, O, KH, KW, pad  (stride 1, C % 32 == O % 32 == 0: tcgen05 implicit-GEMM path)
+  (16, 32, 16, 16, 64, 3, 3, 1),       # smallest eligible
+  (4, 64, 20, 24, 32, 3, 3, 1),        # non-square, partial tiles in both directions
+  (4, 32, 18, 18, 32, 3, 3, 0),        # no padding
+  (2, 32, 28, 32, 96, 5, 5, 2),        # 5x5, O not a power of two (ragged channel tile)
+  (2, 128, 32, 32, 128, 3, 3, 1),      # C5 family
+  (1, 64, 64, 64, 256, 3, 3, 1),       # BN = 256
+  (3, 32, 16, 20, 32, 3, 2, 1),        # rectangular filter
+]
+
+
+@pytest.mark.parametrize('N,C,H,W,O,KH,KW,pad', IGEMM_CASES)
+def test_conv_igemm_tcgen05(U, N, C, H, W, O, KH, KW, pad):
+  """Conv3D forward and data gradient on the tensor cores vs the float64 oracle (conv.py:245-269, 299-309)."""
+  rng = np.random.default_rng(N * 3 + C + H * 7 + O * 11 + KH)
+  x = f32(rng.standard_normal((N, C, H, W)))
+  w = f32(rng.standard_normal((O, C, KH, KW)) / np.sqrt(C * KH * KW))
+  b = f32(rng.standard_normal(O))
+  y = ops.conv3d_fwd(x, w, b, pad, 1)
+  ug = f32(rng.standard_normal(y.shape))
+  close(U.conv_fprop(x, w, b, pad, 1), y, TOLTF32)
+  close(U.conv_dgrad(ug, w, x.shape, pad, 1), ops.conv3d_dgrad(ug, w, x.shape, pad, 1), TOLTF32)
+  close(U.conv_wgrad(ug, x, w.shape, pad, 1), ops.conv3d_wgrad(ug, x, w.shape, pad, 1), TOLTF32)
+
+
+def test_conv_igemm_exact_on_small_integers(U):
+  """TF32-representable inputs -> the tensor-core convolution must be exact (catches any tap / layout mix-up)."""
+  rng = np.random.default_rng(12)
+  x = rng.integers(-3, 4, (16, 32, 16, 16)).astype(np.float64)
+  w = rng.integers(-2, 3, (32, 32, 3, 3)).astype(np.float64)
+  b = rng.integers(-5, 6, 32).astype(np.float64)
+  y = ops.conv3d_fwd(x, w, b, 1, 1)
+  assert np.array_equal(U.conv_fprop(x, w, b, 1, 1), y.astype(np.float32))
+  ug = rng.integers(-3, 4, y.shape).astype(np.float64)
+  assert np.array_equal(U.conv_dgrad(ug, w, x.shape, 1, 1), ops.conv3d_dgrad(ug, w, x.shape, 1, 1).astype(np.float32))
+
+
 def test_conv_errors(U):
   x, w, b = np.zeros((1, 1, 5, 5)), np.zeros((1, 1, 3, 3)), np.zeros(1)
   import torch
