@@ -18,6 +18,8 @@ int conv_igemm_fprop(const float* x, const float* w, const float* b, float* y, i
                      int64_t O, int64_t KH, int64_t KW, int64_t pad, cudaStream_t st);
 int conv_igemm_dgrad(const float* ug, const float* w, float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O,
                      int64_t KH, int64_t KW, int64_t pad, int accumulate, cudaStream_t st);
+int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O,
+                     int64_t KH, int64_t KW, int64_t pad, int accumulate, cudaStream_t st);
 
 constexpr int OT = 8;  // output channels per thread (register tile)
 
@@ -348,6 +350,8 @@ extern "C" int ngb_conv_wgrad(const float* ug, const float* x, float* dw, int64_
     if (!accumulate) return ngb_fill(dw, 0.f, nw, stream);
     return NGB_OK;
   }
+  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(ug) && aligned16(x) && aligned16(dw))
+    return conv_igemm_wgrad(ug, x, dw, N, C, H, W, O, KH, KW, pad, accumulate, st);
   rc = ensure_init();
   if (rc) return rc;
   const int64_t xblocks = ceil_div<int64_t>(nw, 256);

@@ -377,6 +377,217 @@ int run_igemm(const float* in, const float* w, const float* bias, float* out, in
   return rc;
 }
 
+
+// ---------------------------------------------------------------------------------------------- weight gradient
+// dw[o,c,kh,kw] = sum_{n,p,q} ug[n,o,p,q] * x[n,c,p+kh-pad,q+kw-pad]   (conv.py:311-321)
+// GEMM per tap: D_tap[o, c] = sum_pos UGs[pos, o] * Xs[pos + tap, c] with K = positions and both operands MN-major
+// (channels contiguous per position).  A K-block is 32 consecutive q at one (n, p): the ug chunk is loaded once and
+// multiplied against G shifted x chunks (one per tap of the CTA's tap group, each with its own TMEM accumulator).
+// Work item = (128-wide o tile, BN-wide c tile, tap group, K split); partials go to the scratch arena and a second pass
+// sums the splits deterministically into dw's (o,c,kh,kw) layout.
+struct WgradArgs {
+  int N, O, C, Ho, Wo, KH, KW, pad;
+  int o_tiles, c_tiles, tap_groups, splits;
+  int qblocks;               // ceil(Wo / 32)
+  int64_t kblocks;           // N * Ho * qblocks
+  int64_t kb_per_split;
+  float* partial;            // [split][tap][O][C]
+};
+
+template <int BLOCK_N, int G>
+struct WCfg {
+  static constexpr int kABytes = 128 * 32 * 4;              // 4 chunks [32 pos][32 o]
+  static constexpr int kBBytes = G * BLOCK_N * 32 * 4;      // G taps x (BN/32) chunks [32 pos][32 c]
+  static constexpr int kStageBytes = kABytes + kBBytes;
+  static constexpr int kStages = (200 * 1024) / kStageBytes > 6 ? 6 : (200 * 1024) / kStageBytes;
+  static constexpr int kTmemCols = G * BLOCK_N < 32 ? 32 : G * BLOCK_N;
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(G * BLOCK_N <= 512 && (kTmemCols & (kTmemCols - 1)) == 0, "TMEM budget / power of two");
+};
+
+template <int BLOCK_N, int G>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_ug, const __grid_constant__ CUtensorMap tmap_x, const WgradArgs g) {
+  using C_ = WCfg<BLOCK_N, G>;
+  constexpr int kStages = C_::kStages;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* smem_a = smem;
+  uint8_t* smem_b = smem + kStages * C_::kABytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes);
+  uint64_t* full = bars;
+  uint64_t* empty = bars + kStages;
+  uint64_t* tmem_full = bars + 2 * kStages;
+  uint64_t* tmem_empty = bars + 2 * kStages + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * kStages + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tmap_ug);
+    prefetch_tmap(&tmap_x);
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(tmem_full, 1);
+    mbar_init(tmem_empty, 4);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, C_::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int taps = g.KH * g.KW;
+  const int64_t num_work = (int64_t)g.o_tiles * g.c_tiles * g.tap_groups * g.splits;
+
+  auto decode = [&](int64_t w, int& o0, int& c0, int& tap0, int& ntap, int& split) {
+    split = (int)(w % g.splits);
+    int64_t r = w / g.splits;
+    const int tg = (int)(r % g.tap_groups);
+    r /= g.tap_groups;
+    c0 = (int)(r % g.c_tiles) * BLOCK_N;
+    o0 = (int)(r / g.c_tiles) * 128;
+    tap0 = tg * G;
+    ntap = min(G, taps - tap0);
+  };
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (lane == 0) {
+      uint32_t it = 0;
+      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+        int o0, c0, tap0, ntap, split;
+        decode(w, o0, c0, tap0, ntap, split);
+        const int64_t kb0 = (int64_t)split * g.kb_per_split;
+        const int64_t kb1 = min(g.kblocks, kb0 + g.kb_per_split);
+        for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
+          const int qb = (int)(kb % g.qblocks);
+          const int64_t r = kb / g.qblocks;
+          const int p = (int)(r % g.Ho), n = (int)(r / g.Ho);
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&empty[s], ph ^ 1, 11);
+          mbar_arrive_expect_tx(&full[s], C_::kABytes + ntap * BLOCK_N * 128);
+          uint8_t* sa = smem_a + s * C_::kABytes;
+          uint8_t* sb = smem_b + s * C_::kBBytes;
+          // staged ug dims {O, Wo (q), Ho (p), N}: box {32 o, 32 q, 1, 1}
+#pragma unroll
+          for (int j = 0; j < 4; ++j) tma_load_4d(sa + j * 4096, &tmap_ug, &full[s], o0 + 32 * j, qb * 32, p, n);
+          // staged x dims {C, H, W, N}: box {32 c, 1 (h), 32 (w), 1}: rows ordered by w, matching the q order above
+          for (int t = 0; t < ntap; ++t) {
+            const int tap = tap0 + t, kh = tap / g.KW, kw = tap - kh * g.KW;
+#pragma unroll
+            for (int j = 0; j < BLOCK_N / 32; ++j)
+              tma_load_4d(sb + (t * (BLOCK_N / 32) + j) * 4096, &tmap_x, &full[s], c0 + 32 * j, p + kh - g.pad, qb * 32 + kw - g.pad, n);
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 1, 1);
+      constexpr uint64_t desc_base = make_smem_desc_base(4096, 512, kLayoutSW128Base32B);   // MN-major, 32B-atom swizzle
+      uint32_t it = 0, tile_it = 0;
+      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+        int o0, c0, tap0, ntap, split;
+        decode(w, o0, c0, tap0, ntap, split);
+        const int64_t kb0 = (int64_t)split * g.kb_per_split;
+        const int64_t kb1 = min(g.kblocks, kb0 + g.kb_per_split);
+        mbar_wait(tmem_empty, (tile_it & 1) ^ 1, 12);
+        tc_fence_after();
+        for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(&full[s], ph, 13);
+          tc_fence_after();
+          const uint32_t a_addr = smem_u32(smem_a + s * C_::kABytes);
+          const uint32_t b_addr = smem_u32(smem_b + s * C_::kBBytes);
+          for (int t = 0; t < ntap; ++t) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              umma_tf32(tmem_base + t * BLOCK_N, smem_desc(desc_base, a_addr + k * 1024),
+                        smem_desc(desc_base, b_addr + t * (BLOCK_N / 32) * 4096 + k * 1024), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
+          }
+          umma_commit(&empty[s]);
+        }
+        umma_commit(tmem_full);
+      }
+    }
+    __syncwarp();
+  } else {
+    // ===================================================================== epilogue: TMEM lane = o, column = c
+    const int quad = warp & 3;
+    uint32_t tile_it = 0;
+    for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+      int o0, c0, tap0, ntap, split;
+      decode(w, o0, c0, tap0, ntap, split);
+      const int64_t kb0 = (int64_t)split * g.kb_per_split;
+      const bool has_k = kb0 < g.kblocks;
+      mbar_wait(tmem_full, tile_it & 1, 14);
+      tc_fence_after();
+      const int o = o0 + quad * 32 + lane;
+      for (int t = 0; t < ntap; ++t) {
+        float* prow = g.partial + (((int64_t)split * taps + tap0 + t) * g.O + o) * g.C + c0;
+#pragma unroll 1
+        for (int cc = 0; cc < BLOCK_N; cc += 32) {
+          float v[32];
+          tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + t * BLOCK_N + cc, v);
+          tmem_ld_wait();
+          if (o < g.O) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (c0 + cc + j < g.C) {   // C % 32 == 0: whole float4 groups
+                const float4 o4 = has_k ? make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+                *reinterpret_cast<float4*>(prow + cc + j) = o4;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tmem_empty);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C_::kTmemCols);
+  }
+}
+
+// dw[o][c][tap] (+)= sum_split partial[split][tap][o][c]
+__global__ void __launch_bounds__(256) wgrad_reduce_kernel(const float* __restrict__ part, float* __restrict__ dw, int splits, int taps,
+                                                           int O, int C, int accumulate) {
+  const int64_t total = (int64_t)taps * O * C;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    float s = 0.f;
+    for (int z = 0; z < splits; ++z) s += part[(int64_t)z * total + i];
+    const int c = (int)(i % C);
+    const int o = (int)((i / C) % O);
+    const int tap = (int)(i / ((int64_t)C * O));
+    float* d = dw + ((int64_t)o * C + c) * taps + tap;
+    *d = accumulate ? *d + s : s;
+  }
+}
+
+template <int BN, int G>
+int launch_wgrad(const CUtensorMap& tu, const CUtensorMap& tx, const WgradArgs& g, int grid, cudaStream_t st) {
+  using C_ = WCfg<BN, G>;
+  auto kern = conv_wgrad_igemm_kernel<BN, G>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
+    attr_set = true;
+  }
+  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(tu, tx, g);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
 }  // namespace
 
 int conv_igemm_eligible(int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW, int64_t pad,
@@ -404,6 +615,67 @@ int conv_igemm_dgrad(const float* ug, const float* w, float* dx, int64_t N, int6
   // in = ug (neograd order): i0 = p (taps along kh, flipped), i1 = q (taps along kw, flipped)
   return run_igemm(ug, w, nullptr, dx, N, O, C, /*I0=*/Ho, /*I1=*/Wo, /*T0=*/KH, /*T1=*/KW, KH - 1 - pad, KW - 1 - pad, O, C, KH,
                    KW, 1, accumulate, st);
+}
+
+int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O,
+                     int64_t KH, int64_t KW, int64_t pad, int accumulate, cudaStream_t st) {
+  int rc = ensure_init();
+  if (rc) return rc;
+  const int64_t Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
+  const int taps = (int)(KH * KW);
+  // staged copies: UGs[n][p][q][o] and Xs[n][w][h][c]
+  float* ws = nullptr;
+  const int64_t ug_elems = N * O * Ho * Wo, x_elems = N * C * H * W;
+  rc = workspace((ug_elems + x_elems) * 4, &ws, st);
+  if (rc) return rc;
+  float* UGs = ws;
+  float* Xs = ws + ug_elems;
+  rc = stage(ug, UGs, N, O, /*I1=*/Wo, /*I0=*/Ho, st);   // ug is [n][o][q][p]: i0 = p, i1 = q
+  if (rc) return rc;
+  rc = stage(x, Xs, N, C, /*I1=*/H, /*I0=*/W, st);       // x is [n][c][h][w]:  i0 = w, i1 = h
+  if (rc) return rc;
+
+  WgradArgs g;
+  g.N = (int)N; g.O = (int)O; g.C = (int)C; g.Ho = (int)Ho; g.Wo = (int)Wo; g.KH = (int)KH; g.KW = (int)KW; g.pad = (int)pad;
+  const int BN = C <= 64 ? 64 : (C <= 128 ? 128 : 256);
+  const int G = 256 / BN;
+  g.o_tiles = (int)ceil_div<int64_t>(O, 128);
+  g.c_tiles = (int)ceil_div<int64_t>(C, BN);
+  g.tap_groups = ceil_div(taps, G);
+  g.qblocks = (int)ceil_div<int64_t>(Wo, 32);
+  g.kblocks = N * Ho * g.qblocks;
+  const int64_t items = (int64_t)g.o_tiles * g.c_tiles * g.tap_groups;
+  int64_t splits = ceil_div<int64_t>(2 * kNumSMs, items);
+  const int64_t per_split_bytes = (int64_t)taps * O * C * 4;
+  if (splits * per_split_bytes > scratch_bytes()) splits = scratch_bytes() / per_split_bytes;
+  if (splits > g.kblocks) splits = g.kblocks;
+  if (splits < 1) return fail(NGB_ERR_SCRATCH, "conv wgrad igemm: scratch arena too small");
+  g.kb_per_split = ceil_div<int64_t>(g.kblocks, splits);
+  g.splits = (int)ceil_div<int64_t>(g.kblocks, g.kb_per_split);
+  g.partial = scratch_ptr();
+
+  CUtensorMap tu, tx;
+  {
+    const uint64_t ud[4] = {(uint64_t)O, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
+    const uint64_t us[3] = {(uint64_t)O * 4, (uint64_t)O * Wo * 4, (uint64_t)O * Wo * Ho * 4};
+    const uint32_t ub[4] = {32, 32, 1, 1};
+    rc = make_tmap_f32(&tu, UGs, 4, ud, us, ub, true);
+    if (rc) return rc;
+    const uint64_t xd[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)W, (uint64_t)N};
+    const uint64_t xs[3] = {(uint64_t)C * 4, (uint64_t)C * H * 4, (uint64_t)C * H * W * 4};
+    const uint32_t xb[4] = {32, 1, 32, 1};
+    rc = make_tmap_f32(&tx, Xs, 4, xd, xs, xb, true);
+    if (rc) return rc;
+  }
+  const int64_t work = items * g.splits;
+  const int grid = (int)(work < kNumSMs ? work : kNumSMs);
+  if (BN == 64) rc = launch_wgrad<64, 4>(tu, tx, g, grid, st);
+  else if (BN == 128) rc = launch_wgrad<128, 2>(tu, tx, g, grid, st);
+  else rc = launch_wgrad<256, 1>(tu, tx, g, grid, st);
+  if (rc) return rc;
+  wgrad_reduce_kernel<<<grid_for((int64_t)taps * O * C, 256), 256, 0, st>>>(g.partial, dw, g.splits, taps, (int)O, (int)C, accumulate);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
 }
 
 }  // namespace ngb

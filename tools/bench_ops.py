@@ -89,7 +89,7 @@ def bench_conv(quick):
   cases = [(256, 64, 32), (256, 128, 32), (256, 256, 32), (256, 64, 64), (256, 128, 64), (256, 256, 64), (256, 64, 128),
            (256, 128, 128), (256, 256, 128)]
   if quick:
-    cases = [(64, 64, 32), (64, 128, 32)]
+    cases = [(256, 64, 32), (256, 128, 64)]
   for N, C, H in cases:
     O, W, KH, KW, pad, stride = C, H, 3, 3, 1, 1
     x, w, b = rnd(N, C, H, W), rnd(O, C, KH, KW) / np.sqrt(9 * C), torch.zeros(O, device='cuda')
