@@ -244,18 +244,158 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(const float* __r
   part[(int64_t)blockIdx.y * nw + e] = acc;
 }
 
+
+// ---------------------------------------------------------------------------------------------- wgrad, small layers
+// The LeNet / digits layers (C*KH*O <= 512 filter rows, images of a few KB).  A CTA walks its share of the batch one image
+// at a time: x[n] and ug[n] (un-scrambled to [o][p][q]) are staged in smem, thread <-> (filter row (o,c,kh), slice of
+// output rows p) keeps the KW taps of its filter row in registers and slides a KW-wide window of x along q, so the
+// inner step is 2 smem loads for KW FMAs.  Slices are reduced through smem at the end; per-CTA partials are summed by
+// the deterministic second pass.  (The thread-per-filter-element kernel below ran at 0.7 % of its roofline here.)
+template <int KW>
+__global__ void __launch_bounds__(512) conv_wgrad_small_kernel(const float* __restrict__ ug, const float* __restrict__ x,
+                                                               float* __restrict__ part, ConvGeo g, int rows_t, int slices,
+                                                               int imgs_per_cta, FastDiv d_hw, FastDiv d_howo, FastDiv d_ho) {
+  extern __shared__ float sm[];
+  const int HW = g.H * g.W, HoWo = g.Ho * g.Wo;
+  const int xs = HW + 1, us = HoWo + 1;            // padded plane strides (bank spread)
+  float* sx = sm;                                   // [C][xs]
+  float* su = sm + g.C * xs;                        // [O][us], natural (p,q) order
+  const int t = threadIdx.x;
+  const int row = t % rows_t, slice = t / rows_t;   // row = (o*C + c)*KH + kh
+  const bool active = slice < slices;
+  const int kh = row % g.KH;
+  const int c = (row / g.KH) % g.C;
+  const int o = row / (g.KH * g.C);
+  float acc[KW];
+#pragma unroll
+  for (int j = 0; j < KW; ++j) acc[j] = 0.f;
+  const int n0 = blockIdx.x * imgs_per_cta, n1 = min(g.N, n0 + imgs_per_cta);
+  for (int n = n0; n < n1; ++n) {
+    __syncthreads();
+    const float* xn = x + (int64_t)n * g.C * HW;
+#pragma unroll 4
+    for (int e = t; e < g.C * HW; e += blockDim.x) {
+      uint32_t cc, f;
+      d_hw.divmod(e, cc, f);
+      sx[cc * xs + f] = __ldg(xn + e);
+    }
+    const float* un = ug + (int64_t)n * g.O * HoWo;
+#pragma unroll 4
+    for (int e = t; e < g.O * HoWo; e += blockDim.x) {   // global (o, q, p) -> smem (o, p, q)
+      uint32_t oo, f, q, p;
+      d_howo.divmod(e, oo, f);
+      d_ho.divmod(f, q, p);
+      su[oo * us + p * g.Wo + q] = __ldg(un + e);
+    }
+    __syncthreads();
+    if (active) {
+      const float* xc = sx + c * xs;
+      const float* uo = su + o * us;
+      for (int p = slice; p < g.Ho; p += slices) {
+        const int h = p * g.stride + kh - g.pad;
+        if (h < 0 || h >= g.H) continue;
+        const float* xr = xc + h * g.W;
+        const float* ur = uo + p * g.Wo;
+        if (g.stride == 1) {
+          float win[KW];                                 // win[j] = x[h][q + j - pad]
+#pragma unroll
+          for (int j = 0; j < KW - 1; ++j) { const int w = j - g.pad; win[j + 1] = (w >= 0 && w < g.W) ? xr[w] : 0.f; }
+          for (int q = 0; q < g.Wo; ++q) {
+#pragma unroll
+            for (int j = 0; j < KW - 1; ++j) win[j] = win[j + 1];
+            const int w = q + KW - 1 - g.pad;
+            win[KW - 1] = (w >= 0 && w < g.W) ? xr[w] : 0.f;
+            const float gv = ur[q];
+#pragma unroll
+            for (int j = 0; j < KW; ++j) acc[j] = fmaf(gv, win[j], acc[j]);
+          }
+        } else {
+          for (int q = 0; q < g.Wo; ++q) {
+            const float gv = ur[q];
+#pragma unroll
+            for (int j = 0; j < KW; ++j) {
+              const int w = q * g.stride + j - g.pad;
+              if (w >= 0 && w < g.W) acc[j] = fmaf(gv, xr[w], acc[j]);
+            }
+          }
+        }
+      }
+    }
+  }
+  // reduce the slices (fixed order -> deterministic) and emit this CTA's partial
+  __syncthreads();
+  float* red = sm;                                  // [slices][rows_t][KW]
+  if (active) {
+#pragma unroll
+    for (int j = 0; j < KW; ++j) red[(slice * rows_t + row) * KW + j] = acc[j];
+  }
+  __syncthreads();
+  for (int e = t; e < rows_t * KW; e += blockDim.x) {
+    float s2 = 0.f;
+    for (int sl = 0; sl < slices; ++sl) s2 += red[sl * rows_t * KW + e];
+    part[(int64_t)blockIdx.x * rows_t * KW + e] = s2;   // e = ((o*C + c)*KH + kh)*KW + kw: dw's own layout
+  }
+}
+
+// returns true when the small-layer kernel was launched
+static int conv_wgrad_small(const float* ug, const float* x, float* dw, const ConvGeo& g, int accumulate, cudaStream_t st, bool* done) {
+  *done = false;
+  const int rows_t = g.O * g.C * g.KH;
+  if (rows_t > 512 || (g.KW != 2 && g.KW != 3 && g.KW != 5 && g.KW != 7)) return NGB_OK;
+  const int threads = rows_t > 256 ? 512 : 256;
+  const int slices = threads / rows_t;
+  const size_t smem_stage = ((size_t)g.C * (g.H * g.W + 1) + (size_t)g.O * (g.Ho * g.Wo + 1)) * 4;
+  const size_t smem_red = (size_t)slices * rows_t * g.KW * 4;
+  const size_t smem = smem_stage > smem_red ? smem_stage : smem_red;
+  if (smem > 46 * 1024) return NGB_OK;
+  int rc = ensure_init();
+  if (rc) return rc;
+  const int64_t nw = (int64_t)rows_t * g.KW;
+  int64_t ctas = (int64_t)kNumSMs * (smem > 20 * 1024 ? 2 : 4);
+  if (ctas > g.N) ctas = g.N;
+  if (ctas * nw * 4 > scratch_bytes()) ctas = scratch_bytes() / (nw * 4);
+  if (ctas < 1) return NGB_OK;
+  const int ipc = (int)ceil_div<int64_t>(g.N, ctas);
+  ctas = ceil_div<int64_t>(g.N, ipc);
+  const FastDiv dhw((uint32_t)(g.H * g.W)), dhowo((uint32_t)(g.Ho * g.Wo)), dho((uint32_t)g.Ho);
+  switch (g.KW) {
+    case 2: conv_wgrad_small_kernel<2><<<(unsigned)ctas, threads, smem, st>>>(ug, x, scratch_ptr(), g, rows_t, slices, ipc, dhw, dhowo, dho); break;
+    case 3: conv_wgrad_small_kernel<3><<<(unsigned)ctas, threads, smem, st>>>(ug, x, scratch_ptr(), g, rows_t, slices, ipc, dhw, dhowo, dho); break;
+    case 5: conv_wgrad_small_kernel<5><<<(unsigned)ctas, threads, smem, st>>>(ug, x, scratch_ptr(), g, rows_t, slices, ipc, dhw, dhowo, dho); break;
+    default: conv_wgrad_small_kernel<7><<<(unsigned)ctas, threads, smem, st>>>(ug, x, scratch_ptr(), g, rows_t, slices, ipc, dhw, dhowo, dho); break;
+  }
+  NGB_LAUNCH_CHECK();
+  *done = true;
+  return launch_sum_partials(scratch_ptr(), (int)ctas, nw, dw, accumulate, st);
+}
+
 // ---------------------------------------------------------------------------------------------- bgrad
-// db[o] = sum_{n,f} ug[n,o,f].  grid = (O, splits over N); contiguous HoWo runs -> coalesced float loads.
+// db[o] = sum_{n,f} ug[n,o,f].  grid = (O, splits over N); every image contributes one contiguous HoWo run: 128-bit loads,
+// four in flight per thread, no 64-bit divides.
 __global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict__ ug, float* __restrict__ part, int64_t N,
-                                                         int64_t O, int64_t HW, int64_t imgs_per_split) {
+                                                         int64_t O, int64_t HW, int64_t imgs_per_split, FastDiv d_hw4, int vec) {
   __shared__ float red[32];
   const int64_t o = blockIdx.x;
   const int64_t nb = (int64_t)blockIdx.y * imgs_per_split, ne = min(N, nb + imgs_per_split);
   float acc = 0.f;
-  const int64_t span = (ne - nb) * HW;
-  for (int64_t i = threadIdx.x; i < span; i += blockDim.x) {
-    const int64_t n = nb + i / HW, f = i % HW;
-    acc += ug[(n * O + o) * HW + f];
+  if (vec) {
+    const uint32_t hw4 = (uint32_t)(HW >> 2);
+    const uint32_t span4 = (uint32_t)((ne - nb) * hw4);
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (uint32_t i = threadIdx.x; i < span4; i += 256) {
+      uint32_t n, f4;
+      d_hw4.divmod(i, n, f4);
+      const float4 v = ld_stream4(ug + ((nb + n) * O + o) * HW + 4 * (int64_t)f4);
+      a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
+    }
+    acc = (a0 + a1) + (a2 + a3);
+  } else {
+    const int64_t span = (ne - nb) * HW;
+    for (int64_t i = threadIdx.x; i < span; i += blockDim.x) {
+      const int64_t n = nb + i / HW, f = i % HW;
+      acc += ug[(n * O + o) * HW + f];
+    }
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) part[(int64_t)blockIdx.y * O + o] = acc;
@@ -352,6 +492,11 @@ extern "C" int ngb_conv_wgrad(const float* ug, const float* x, float* dw, int64_
   }
   if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(ug) && aligned16(x) && aligned16(dw))
     return conv_igemm_wgrad(ug, x, dw, N, C, H, W, O, KH, KW, pad, accumulate, st);
+  {
+    bool done = false;
+    rc = conv_wgrad_small(ug, x, dw, g, accumulate, st, &done);
+    if (rc || done) return rc;
+  }
   rc = ensure_init();
   if (rc) return rc;
   const int64_t xblocks = ceil_div<int64_t>(nw, 256);
@@ -378,7 +523,7 @@ extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, 
   }
   int rc = ensure_init();
   if (rc) return rc;
-  int64_t splits = ceil_div<int64_t>(4 * kNumSMs, O);
+  int64_t splits = ceil_div<int64_t>(8 * kNumSMs, O);
   if (splits > N) splits = N;
   // keep at least ~4K elements per CTA
   const int64_t min_imgs = ceil_div<int64_t>(4096, HoWo);
@@ -387,7 +532,8 @@ extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, 
   const int64_t ips = ceil_div<int64_t>(N, splits);
   splits = ceil_div<int64_t>(N, ips);
   dim3 grid((unsigned)O, (unsigned)splits);
-  conv_bgrad_kernel<<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips);
+  const int vec = (HoWo % 4 == 0) && aligned16(ug) && (ips * (HoWo / 4) < (int64_t(1) << 32));
+  conv_bgrad_kernel<<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips, FastDiv((uint32_t)(vec ? HoWo / 4 : 1)), vec);
   NGB_LAUNCH_CHECK();
   return launch_sum_partials(scratch_ptr(), (int)splits, O, db, accumulate, st);
 }

@@ -99,6 +99,46 @@ __global__ void __launch_bounds__(256) stage_channels_last_kernel(const float* _
   }
 }
 
+// Same re-layout with 64 x 64 (c, i0) tiles and 128-bit global accesses on both sides (I0 % 4 == 0, C % 64 == 0):
+// 16 KB per CTA iteration and four independent 128-bit loads in flight per thread.
+__global__ void __launch_bounds__(256) stage_channels_last_v4_kernel(const float* __restrict__ in, float* __restrict__ S, int N, int C,
+                                                                     int I1, int I0, FastDiv d_t0, FastDiv d_tc, FastDiv d_i1) {
+  __shared__ float tile[64][65];
+  const int l16 = threadIdx.x & 15, r16 = threadIdx.x >> 4;   // 16 float4 columns x 16 rows per pass
+  const int t0n = (I0 + 63) >> 6, tcn = C >> 6;
+  const int64_t items = (int64_t)N * I1 * tcn * t0n;
+  for (int64_t it = blockIdx.x; it < items; it += gridDim.x) {
+    uint32_t r, b0, bc, n, i1;
+    d_t0.divmod((uint32_t)it, r, b0);
+    d_tc.divmod(r, r, bc);
+    d_i1.divmod(r, n, i1);
+    const int c0 = bc * 64, i00 = b0 * 64;
+    float4 v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int c = c0 + r16 + 16 * k, i0 = i00 + 4 * l16;
+      v[k] = i0 < I0 ? ld_stream4(in + (((int64_t)n * C + c) * I1 + i1) * I0 + i0) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      float* d = &tile[r16 + 16 * k][4 * l16];
+      d[0] = v[k].x; d[1] = v[k].y; d[2] = v[k].z; d[3] = v[k].w;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int i0l = r16 + 16 * k, i0 = i00 + i0l;
+      if (i0 < I0) {
+        float4 o;
+        o.x = to_tf32(tile[4 * l16 + 0][i0l]); o.y = to_tf32(tile[4 * l16 + 1][i0l]);
+        o.z = to_tf32(tile[4 * l16 + 2][i0l]); o.w = to_tf32(tile[4 * l16 + 3][i0l]);
+        *reinterpret_cast<float4*>(S + (((int64_t)n * I0 + i0) * I1 + i1) * C + c0 + 4 * l16) = o;
+      }
+    }
+    __syncthreads();
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- fprop / dgrad kernel
 template <int BLOCK_N>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -301,6 +341,17 @@ int workspace(int64_t bytes, float** out, cudaStream_t st) {
 }
 
 int stage(const float* in, float* S, int64_t N, int64_t C, int64_t I1, int64_t I0, cudaStream_t st) {
+  if (C % 64 == 0 && I0 % 4 == 0 && aligned16(in) && aligned16(S)) {
+    const int64_t t0v = ceil_div<int64_t>(I0, 64), tcv = C / 64;
+    const int64_t itemsv = N * I1 * tcv * t0v;
+    if (itemsv < (int64_t(1) << 32)) {
+      const int gridv = (int)(itemsv < (int64_t)kNumSMs * 8 ? itemsv : (int64_t)kNumSMs * 8);
+      stage_channels_last_v4_kernel<<<gridv, 256, 0, st>>>(in, S, (int)N, (int)C, (int)I1, (int)I0, FastDiv((uint32_t)t0v),
+                                                          FastDiv((uint32_t)tcv), FastDiv((uint32_t)I1));
+      NGB_LAUNCH_CHECK();
+      return NGB_OK;
+    }
+  }
   const int64_t t0n = ceil_div<int64_t>(I0, 32), tcn = ceil_div<int64_t>(C, 32);
   const int64_t items = N * I1 * tcn * t0n;
   if (items >= (int64_t(1) << 32)) return fail(NGB_ERR_UNSUPPORTED, "conv igemm: tensor too large to stage");
@@ -439,13 +490,15 @@ conv_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_ug, const __gri
   const int taps = g.KH * g.KW;
   const int64_t num_work = (int64_t)g.o_tiles * g.c_tiles * g.tap_groups * g.splits;
 
+  // tap group fastest: CTAs that run side by side stream the SAME K range (the same ug / x positions) for different
+  // taps, so the re-reads across tap groups are L2 hits instead of HBM traffic
   auto decode = [&](int64_t w, int& o0, int& c0, int& tap0, int& ntap, int& split) {
-    split = (int)(w % g.splits);
-    int64_t r = w / g.splits;
-    const int tg = (int)(r % g.tap_groups);
-    r /= g.tap_groups;
+    const int tg = (int)(w % g.tap_groups);
+    int64_t r = w / g.tap_groups;
     c0 = (int)(r % g.c_tiles) * BLOCK_N;
-    o0 = (int)(r / g.c_tiles) * 128;
+    r /= g.c_tiles;
+    o0 = (int)(r % g.o_tiles) * 128;
+    split = (int)(r / g.o_tiles);
     tap0 = tg * G;
     ntap = min(G, taps - tap0);
   };
