@@ -12,6 +12,7 @@ from .autograd.graph import Graph
 _NG_GRAPH = Graph()   # the global graph (neograd/__init__.py:9-10)
 
 from . import autograd, nn, distributed  # noqa: E402
+from .nn import Checkpoint  # noqa: E402
 from .autograd import tensor, new_graph, no_track  # noqa: E402
 from .autograd import add, sub, mul, div, pow, exp, log, dot, sum, transpose, flatten, reshape  # noqa: E402
 from .autograd.utils import grad_check, fn_grad_check  # noqa: E402
