@@ -490,7 +490,7 @@ extern "C" int ngb_conv_wgrad(const float* ug, const float* x, float* dw, int64_
     if (!accumulate) return ngb_fill(dw, 0.f, nw, stream);
     return NGB_OK;
   }
-  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(ug) && aligned16(x) && aligned16(dw))
+  if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && g.Ho % 4 == 0 && aligned16(ug) && aligned16(x) && aligned16(dw))
     return conv_igemm_wgrad(ug, x, dw, N, C, H, W, O, KH, KW, pad, accumulate, st);
   {
     bool done = false;

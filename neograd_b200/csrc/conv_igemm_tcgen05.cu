@@ -431,16 +431,17 @@ int run_igemm(const float* in, const float* w, const float* bias, float* out, in
 
 // ---------------------------------------------------------------------------------------------- weight gradient
 // dw[o,c,kh,kw] = sum_{n,p,q} ug[n,o,p,q] * x[n,c,p+kh-pad,q+kw-pad]   (conv.py:311-321)
-// GEMM per tap: D_tap[o, c] = sum_pos UGs[pos, o] * Xs[pos + tap, c] with K = positions and both operands MN-major
-// (channels contiguous per position).  A K-block is 32 consecutive q at one (n, p): the ug chunk is loaded once and
-// multiplied against G shifted x chunks (one per tap of the CTA's tap group, each with its own TMEM accumulator).
+// GEMM per tap: D_tap[o, c] = sum_pos ug[o, pos] * Xs[pos + tap, c] with K = positions.  ug is read IN PLACE (its p axis
+// is contiguous, i.e. K-major); x comes from its channels-last staged copy (MN-major).  A K-block is 32 consecutive p
+// at one (n, q): the ug tile is loaded once (one 4-D box) and multiplied against G shifted x tiles (one 5-D box per
+// tap of the CTA's tap group, each tap with its own TMEM accumulator).
 // Work item = (128-wide o tile, BN-wide c tile, tap group, K split); partials go to the scratch arena and a second pass
 // sums the splits deterministically into dw's (o,c,kh,kw) layout.
 struct WgradArgs {
   int N, O, C, Ho, Wo, KH, KW, pad;
   int o_tiles, c_tiles, tap_groups, splits;
-  int qblocks;               // ceil(Wo / 32)
-  int64_t kblocks;           // N * Ho * qblocks
+  int qblocks;               // ceil(Ho / 32): K-blocks of 32 consecutive p per (n, q)
+  int64_t kblocks;           // N * Wo * qblocks
   int64_t kb_per_split;
   float* partial;            // [split][tap][O][C]
 };
@@ -512,34 +513,34 @@ conv_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_ug, const __gri
         decode(w, o0, c0, tap0, ntap, split);
         const int64_t kb0 = (int64_t)split * g.kb_per_split;
         const int64_t kb1 = min(g.kblocks, kb0 + g.kb_per_split);
+        // (n, q, pb) of the first K-block; advanced incrementally (no 64-bit divides in the issue loop)
+        int pb = (int)(kb0 % g.qblocks);
+        int64_t r0 = kb0 / g.qblocks;
+        int q = (int)(r0 % g.Wo), n = (int)(r0 / g.Wo);
         for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
-          const int qb = (int)(kb % g.qblocks);
-          const int64_t r = kb / g.qblocks;
-          const int p = (int)(r % g.Ho), n = (int)(r / g.Ho);
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1, 11);
           mbar_arrive_expect_tx(&full[s], C_::kABytes + ntap * BLOCK_N * 128);
           uint8_t* sa = smem_a + s * C_::kABytes;
           uint8_t* sb = smem_b + s * C_::kBBytes;
-          // staged ug dims {O, Wo (q), Ho (p), N}: box {32 o, 32 q, 1, 1}
-#pragma unroll
-          for (int j = 0; j < 4; ++j) tma_load_4d(sa + j * 4096, &tmap_ug, &full[s], o0 + 32 * j, qb * 32, p, n);
-          // staged x dims {C, H, W, N}: box {32 c, 1 (h), 32 (w), 1}: rows ordered by w, matching the q order above
+          // A straight from ug [n][o][q][p] (p contiguous = K-major): box {32 p, 1 q, 128 o, 1}: no staging pass for ug
+          tma_load_4d(sa, &tmap_ug, &full[s], pb * 32, q, o0, n);
+          // staged x viewed as {32 c_in, H, W, N, C/32 c_out}: one box {32, 32 (h), 1 (w), 1, BN/32} per tap, rows ordered by h
           for (int t = 0; t < ntap; ++t) {
             const int tap = tap0 + t, kh = tap / g.KW, kw = tap - kh * g.KW;
-#pragma unroll
-            for (int j = 0; j < BLOCK_N / 32; ++j)
-              tma_load_4d(sb + (t * (BLOCK_N / 32) + j) * 4096, &tmap_x, &full[s], c0 + 32 * j, p + kh - g.pad, qb * 32 + kw - g.pad, n);
+            tma_load_5d(sb + t * (BLOCK_N / 32) * 4096, &tmap_x, &full[s], 0, pb * 32 + kh - g.pad, q + kw - g.pad, n, c0 / 32);
           }
+          if (++pb == g.qblocks) { pb = 0; if (++q == g.Wo) { q = 0; ++n; } }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 1, 1);
-      constexpr uint64_t desc_base = make_smem_desc_base(4096, 512, kLayoutSW128Base32B);   // MN-major, 32B-atom swizzle
+      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 1);
+      constexpr uint64_t adesc_base = make_smem_desc_base(16, 1024);                          // ug: K-major, 128B swizzle
+      constexpr uint64_t desc_base = make_smem_desc_base(4096, 512, kLayoutSW128Base32B);   // x: MN-major, 32B-atom swizzle
       uint32_t it = 0, tile_it = 0;
       for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
         int o0, c0, tap0, ntap, split;
@@ -558,7 +559,7 @@ conv_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_ug, const __gri
           for (int t = 0; t < ntap; ++t) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              umma_tf32(tmem_base + t * BLOCK_N, smem_desc(desc_base, a_addr + k * 1024),
+              umma_tf32(tmem_base + t * BLOCK_N, smem_desc(adesc_base, a_addr + k * UMMA_K * 4),
                         smem_desc(desc_base, b_addr + t * (BLOCK_N / 32) * 4096 + k * 1024), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             }
           }
@@ -676,14 +677,9 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
   if (rc) return rc;
   const int64_t Ho = H + 2 * pad - KH + 1, Wo = W + 2 * pad - KW + 1;
   const int taps = (int)(KH * KW);
-  // staged copies: UGs[n][p][q][o] and Xs[n][w][h][c]
-  float* ws = nullptr;
-  const int64_t ug_elems = N * O * Ho * Wo, x_elems = N * C * H * W;
-  rc = workspace((ug_elems + x_elems) * 4, &ws, st);
-  if (rc) return rc;
-  float* UGs = ws;
-  float* Xs = ws + ug_elems;
-  rc = stage(ug, UGs, N, O, /*I1=*/Wo, /*I0=*/Ho, st);   // ug is [n][o][q][p]: i0 = p, i1 = q
+  // x staged channels-last as Xs[n][w][h][c]; ug is consumed in place (its p axis is contiguous = K-major)
+  float* Xs = nullptr;
+  rc = workspace(N * C * H * W * 4, &Xs, st);
   if (rc) return rc;
   rc = stage(x, Xs, N, C, /*I1=*/H, /*I0=*/W, st);       // x is [n][c][h][w]:  i0 = w, i1 = h
   if (rc) return rc;
@@ -695,8 +691,8 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
   g.o_tiles = (int)ceil_div<int64_t>(O, 128);
   g.c_tiles = (int)ceil_div<int64_t>(C, BN);
   g.tap_groups = ceil_div(taps, G);
-  g.qblocks = (int)ceil_div<int64_t>(Wo, 32);
-  g.kblocks = N * Ho * g.qblocks;
+  g.qblocks = (int)ceil_div<int64_t>(Ho, 32);
+  g.kblocks = N * Wo * g.qblocks;
   const int64_t items = (int64_t)g.o_tiles * g.c_tiles * g.tap_groups;
   int64_t splits = ceil_div<int64_t>(2 * kNumSMs, items);
   const int64_t per_split_bytes = (int64_t)taps * O * C * 4;
@@ -709,15 +705,16 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
 
   CUtensorMap tu, tx;
   {
-    const uint64_t ud[4] = {(uint64_t)O, (uint64_t)Wo, (uint64_t)Ho, (uint64_t)N};
-    const uint64_t us[3] = {(uint64_t)O * 4, (uint64_t)O * Wo * 4, (uint64_t)O * Wo * Ho * 4};
-    const uint32_t ub[4] = {32, 32, 1, 1};
-    rc = make_tmap_f32(&tu, UGs, 4, ud, us, ub, true);
+    const uint64_t ud[4] = {(uint64_t)Ho, (uint64_t)Wo, (uint64_t)O, (uint64_t)N};
+    const uint64_t us[3] = {(uint64_t)Ho * 4, (uint64_t)Ho * Wo * 4, (uint64_t)Ho * Wo * O * 4};
+    const uint32_t ub[4] = {32, 1, 128, 1};
+    rc = make_tmap_f32(&tu, ug, 4, ud, us, ub, false);
     if (rc) return rc;
-    const uint64_t xd[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)W, (uint64_t)N};
-    const uint64_t xs[3] = {(uint64_t)C * 4, (uint64_t)C * H * 4, (uint64_t)C * H * W * 4};
-    const uint32_t xb[4] = {32, 1, 32, 1};
-    rc = make_tmap_f32(&tx, Xs, 4, xd, xs, xb, true);
+    // channel dim split into (32 inner, C/32 outer) so that one 5-D box delivers BN/32 [32 pos][32 ch] chunks back to back
+    const uint64_t xd[5] = {32, (uint64_t)H, (uint64_t)W, (uint64_t)N, (uint64_t)(C / 32)};
+    const uint64_t xs[4] = {(uint64_t)C * 4, (uint64_t)C * H * 4, (uint64_t)C * H * W * 4, 128};
+    const uint32_t xb[5] = {32, 32, 1, 1, (uint32_t)(BN / 32)};
+    rc = make_tmap_f32(&tx, Xs, 5, xd, xs, xb, true);
     if (rc) return rc;
   }
   const int64_t work = items * g.splits;

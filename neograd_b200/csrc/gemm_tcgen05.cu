@@ -80,6 +80,7 @@ struct GemmArgs {
   int64_t ldc;
   float* partial;      // ... or split partials [split][M*N] (ld = N)
   int accumulate;
+  int a_3d, b_3d;      // MN-major operand described by a 3-D map {32, K, MN/32}: one TMA box per stage instead of MN/32
 };
 
 // A_MN / B_MN: operand is MN-major in global memory (1) or K-major (0).
@@ -135,14 +136,22 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const int k0 = kb * BLOCK_K;
           if (A_MN) {
             // global dims {M, K}: one {32 x 32} box per 32-wide M chunk; chunk c lands at sa + c*4096
+            if (g.a_3d) {
+              tma_load_3d(sa, &tmap_a, &full[s], 0, k0, m0 / 32);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_M / 32; ++c) tma_load_2d(sa + c * 4096, &tmap_a, &full[s], m0 + c * 32, k0);
+              for (int c = 0; c < BLOCK_M / 32; ++c) tma_load_2d(sa + c * 4096, &tmap_a, &full[s], m0 + c * 32, k0);
+            }
           } else {
             tma_load_2d(sa, &tmap_a, &full[s], k0, m0);  // global dims {K, M}: box {32, 128}
           }
           if (B_MN) {
+            if (g.b_3d) {
+              tma_load_3d(sb, &tmap_b, &full[s], 0, k0, n0 / 32);
+            } else {
 #pragma unroll
-            for (int c = 0; c < BLOCK_N / 32; ++c) tma_load_2d(sb + c * 4096, &tmap_b, &full[s], n0 + c * 32, k0);
+              for (int c = 0; c < BLOCK_N / 32; ++c) tma_load_2d(sb + c * 4096, &tmap_b, &full[s], n0 + c * 32, k0);
+            }
           } else {
             tma_load_2d(sb, &tmap_b, &full[s], k0, n0);
           }
@@ -284,18 +293,34 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
 
   CUtensorMap ta, tb;
+  // An MN-major operand whose MN extent is a multiple of 32 is described as {32, K, MN/32} (outer stride 128 B) so that a
+  // single 3-D box brings the whole [MN/32 chunks][32 k][32 mn] stage; otherwise one 2-D box per chunk (zero-filled tails).
+  const int a_3d = a_mn && (M % 32 == 0), b_3d = b_mn && (N % 32 == 0);
   {
-    uint64_t dims[2], str[1];
-    uint32_t box[2];
-    if (a_mn) { dims[0] = M; dims[1] = K; box[0] = 32; box[1] = BLOCK_K; }
-    else { dims[0] = K; dims[1] = M; box[0] = BLOCK_K; box[1] = BLOCK_M; }
-    str[0] = (uint64_t)lda * 4;
-    int rc = make_tmap_f32(&ta, A, 2, dims, str, box, a_mn);
+    uint64_t dims[3], str[2];
+    uint32_t box[3];
+    int rc;
+    if (a_3d) {
+      dims[0] = 32; dims[1] = K; dims[2] = M / 32; str[0] = (uint64_t)lda * 4; str[1] = 128;
+      box[0] = 32; box[1] = BLOCK_K; box[2] = BLOCK_M / 32;
+      rc = make_tmap_f32(&ta, A, 3, dims, str, box, true);
+    } else {
+      if (a_mn) { dims[0] = M; dims[1] = K; box[0] = 32; box[1] = BLOCK_K; }
+      else { dims[0] = K; dims[1] = M; box[0] = BLOCK_K; box[1] = BLOCK_M; }
+      str[0] = (uint64_t)lda * 4;
+      rc = make_tmap_f32(&ta, A, 2, dims, str, box, a_mn);
+    }
     if (rc) return rc;
-    if (b_mn) { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = BLOCK_K; }
-    else { dims[0] = K; dims[1] = N; box[0] = BLOCK_K; box[1] = (uint32_t)BN; }
-    str[0] = (uint64_t)ldb * 4;
-    rc = make_tmap_f32(&tb, B, 2, dims, str, box, b_mn);
+    if (b_3d) {
+      dims[0] = 32; dims[1] = K; dims[2] = N / 32; str[0] = (uint64_t)ldb * 4; str[1] = 128;
+      box[0] = 32; box[1] = BLOCK_K; box[2] = (uint32_t)(BN / 32);
+      rc = make_tmap_f32(&tb, B, 3, dims, str, box, true);
+    } else {
+      if (b_mn) { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = BLOCK_K; }
+      else { dims[0] = K; dims[1] = N; box[0] = BLOCK_K; box[1] = (uint32_t)BN; }
+      str[0] = (uint64_t)ldb * 4;
+      rc = make_tmap_f32(&tb, B, 2, dims, str, box, b_mn);
+    }
     if (rc) return rc;
   }
 
@@ -321,6 +346,7 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   g.C = C; g.ldc = ldc;
   g.partial = g.splits > 1 ? scratch_ptr() : nullptr;
   g.accumulate = accumulate;
+  g.a_3d = a_3d; g.b_3d = b_3d;
   const int work = tiles * g.splits;
   const int grid = work < kNumSMs ? work : kNumSMs;
 
