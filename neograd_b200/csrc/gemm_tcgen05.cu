@@ -14,6 +14,7 @@
 
 #include <mutex>
 #include <stdlib.h>
+#include <string.h>
 
 namespace ngb {
 
@@ -38,10 +39,11 @@ EncodeTiledFn get_encode_tiled() {
 }
 
 int make_tmap_f32(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                  const uint32_t* box, bool atom32b) {
+                  const uint32_t* box, bool atom32b, bool plain_f32_arg) {
   EncodeTiledFn enc = get_encode_tiled();
   if (!enc) return fail(NGB_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
-  static const bool plain_f32 = getenv("NGB_TMAP_FLOAT32") != nullptr;  // debug switch: no TF32 rounding in the TMA unit
+  static const bool plain_env = getenv("NGB_TMAP_FLOAT32") != nullptr;  // debug switch: no TF32 rounding in the TMA unit
+  const bool plain_f32 = plain_env || plain_f32_arg;
   cuuint64_t gdims[5], gstr[4];
   cuuint32_t bdims[5], estr[5];
   for (int i = 0; i < rank; ++i) { gdims[i] = dims[i]; bdims[i] = box[i]; estr[i] = 1; }
@@ -65,9 +67,10 @@ struct Cfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 2 accumulator stages (power of two >= 32)
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kEpiBytes = 2 * 128 * 128;                        // two [128 rows][32 cols] staging tiles for TMA stores
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmArgs {
@@ -81,19 +84,22 @@ struct GemmArgs {
   float* partial;      // ... or split partials [split][M*N] (ld = N)
   int accumulate;
   int a_3d, b_3d;      // MN-major operand described by a 3-D map {32, K, MN/32}: one TMA box per stage instead of MN/32
+  int tma_store;       // epilogue goes registers -> swizzled smem -> TMA store (coalesced 128B lines); needs ldc % 4 == 0
 };
 
 // A_MN / B_MN: operand is MN-major in global memory (1) or K-major (0).
 template <int BLOCK_N, int A_MN, int B_MN>
 __global__ void __launch_bounds__(kThreads, 1)
-gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b, const GemmArgs g) {
+gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
+                 const __grid_constant__ CUtensorMap tmap_c, const GemmArgs g) {
   using C_ = Cfg<BLOCK_N>;
   constexpr int kStages = C_::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * C_::kABytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes);
+  uint8_t* smem_epi = smem + kStages * C_::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes + C_::kEpiBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -199,7 +205,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int quad = warp & 3;  // TMEM lane quadrant this warp may access
-    uint32_t tile_it = 0;
+    const int et = (warp - 2) * 32 + lane;
+    uint32_t tile_it = 0, chunk_it = 0;
     const bool vec_ok = g.partial ? (g.N % 4 == 0) : ((g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0));
     for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
       const int split = w % g.splits, tile = w / g.splits;
@@ -207,7 +214,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
-      const int row = m0 + quad * 32 + lane;
+      const int lrow = quad * 32 + lane;
+      const int row = m0 + lrow;
       float* out_row;
       int64_t ld;
       if (g.partial) { ld = g.N; out_row = g.partial + (int64_t)split * g.M * g.N + (int64_t)row * ld; }
@@ -223,7 +231,28 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (row < g.M) {
+        if (g.tma_store) {
+          // registers -> smem tile [128 rows][32 cols] in the 128B-swizzle the store tensor map expects -> one TMA store
+          // (whole 128-byte lines, M / N tails clipped by the tensor map).  Two tiles alternate so the store of chunk i
+          // overlaps the TMEM reads of chunk i+1.
+          if (n0 + c0 < g.N) {
+            uint8_t* tile_s = smem_epi + (chunk_it & 1) * (128 * 128);
+            if (et == 0) tma_store_wait_read<1>();          // the store that last read this tile has drained it
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            uint8_t* rp = tile_s + lrow * 128;
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              *reinterpret_cast<float4*>(rp + ((j ^ (lrow & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            fence_proxy_async();
+            asm volatile("bar.sync 1, 128;" ::: "memory");
+            if (et == 0) {
+              if (g.partial) tma_store_3d(&tmap_c, tile_s, n0 + c0, m0, split);
+              else tma_store_2d(&tmap_c, tile_s, n0 + c0, m0, accum);
+              tma_store_commit();
+            }
+            ++chunk_it;
+          }
+        } else if (row < g.M) {
           const int nbase = n0 + c0;
           if (vec_ok && nbase + 32 <= g.N) {
 #pragma unroll
@@ -242,6 +271,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         }
       }
     }
+    if (g.tma_store && et == 0) tma_store_wait_all();   // global writes complete before the kernel (and the split-K pass) moves on
   }
 
   tc_fence_before();
@@ -254,7 +284,8 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 
 // ---------------------------------------------------------------------------------------------- host launch
 template <int BLOCK_N, int A_MN, int B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int grid, cudaStream_t st) {
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const GemmArgs& g, int grid,
+                  cudaStream_t st) {
   using C_ = Cfg<BLOCK_N>;
   auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
   static bool attr_set = false;
@@ -262,18 +293,18 @@ static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& 
     NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(ta, tb, g);
+  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(ta, tb, tc_, g);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
 
 template <int BLOCK_N>
-static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const GemmArgs& g, int grid,
-                        cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BLOCK_N, 0, 0>(ta, tb, g, grid, st);
-  if (!a_mn && b_mn) return launch<BLOCK_N, 0, 1>(ta, tb, g, grid, st);
-  if (a_mn && !b_mn) return launch<BLOCK_N, 1, 0>(ta, tb, g, grid, st);
-  return launch<BLOCK_N, 1, 1>(ta, tb, g, grid, st);
+static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const GemmArgs& g,
+                        int grid, cudaStream_t st) {
+  if (!a_mn && !b_mn) return launch<BLOCK_N, 0, 0>(ta, tb, tc_, g, grid, st);
+  if (!a_mn && b_mn) return launch<BLOCK_N, 0, 1>(ta, tb, tc_, g, grid, st);
+  if (a_mn && !b_mn) return launch<BLOCK_N, 1, 0>(ta, tb, tc_, g, grid, st);
+  return launch<BLOCK_N, 1, 1>(ta, tb, tc_, g, grid, st);
 }
 
 bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc) {
@@ -350,10 +381,25 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   const int work = tiles * g.splits;
   const int grid = work < kNumSMs ? work : kNumSMs;
 
+  // output tensor map for the TMA-store epilogue: C itself, or the split partials as {N, M, splits}
+  CUtensorMap tcm;
+  memset(&tcm, 0, sizeof(tcm));
+  g.tma_store = 0;
+  {
+    const bool to_partial = g.splits > 1;
+    const float* obase = to_partial ? g.partial : C;
+    const int64_t old = to_partial ? N : ldc;
+    static const bool no_tma_store = getenv("NGB_NO_TMA_STORE") != nullptr;
+    if (!no_tma_store && old % 4 == 0 && aligned16(obase)) {
+      uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)g.splits}, str[2] = {(uint64_t)old * 4, (uint64_t)M * N * 4};
+      uint32_t box[3] = {32, 128, 1};
+      if (make_tmap_f32(&tcm, obase, to_partial ? 3 : 2, dims, str, box, false, /*plain_f32=*/true) == NGB_OK) g.tma_store = 1;
+    }
+  }
   int rc;
-  if (BN == 64) rc = launch_major<64>(a_mn, b_mn, ta, tb, g, grid, st);
-  else if (BN == 128) rc = launch_major<128>(a_mn, b_mn, ta, tb, g, grid, st);
-  else rc = launch_major<256>(a_mn, b_mn, ta, tb, g, grid, st);
+  if (BN == 64) rc = launch_major<64>(a_mn, b_mn, ta, tb, tcm, g, grid, st);
+  else if (BN == 128) rc = launch_major<128>(a_mn, b_mn, ta, tb, tcm, g, grid, st);
+  else rc = launch_major<256>(a_mn, b_mn, ta, tb, tcm, g, grid, st);
   if (rc) return rc;
   if (g.splits > 1) return launch_splitk_reduce(g.partial, g.splits, M, N, C, ldc, accumulate, st);
   return NGB_OK;
