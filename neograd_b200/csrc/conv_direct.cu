@@ -245,6 +245,200 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(const float* __r
 }
 
 
+
+// ---------------------------------------------------------------------------------------------- fprop / dgrad, small layers
+// Register-tiled kernels for the LeNet / digits layers (stride 1, a few channels, images of a few KB).  A CTA stages G
+// images (zero-padded) and the whole filter bank in smem; each thread owns 4 output channels x 8 consecutive outputs along
+// the OUTPUT's contiguous axis and slides an 8+K-1 window of the input through registers, so the inner step is one
+// broadcast 128-bit weight load per tap for 32 FMAs (the generic kernels above issue 3 smem loads per 8 FMAs and are
+// LSU-bound).  Forward: outputs run along p (neograd order), window slides along kh.  Data gradient: outputs run along
+// w, window slides along kw over the un-scrambled upstream gradient.
+constexpr int RT = 8;   // outputs per thread along the contiguous axis
+constexpr int CT = 4;   // channels per thread
+
+struct SmallGeo {
+  int N, Cin, Cout;      // input / output channels of THIS pass (dgrad: Cin = O, Cout = C)
+  int A, Bx;             // input plane: A rows x Bx contiguous columns AS STAGED (zero padded)
+  int JA, JB;            // output plane extents: JB contiguous
+  int KA, KB;            // filter extents along the staged input's row / column axes
+  int G, tpi;            // images per CTA pass, threads per image
+  int jb_blocks, co_groups;
+  int in_plane, in_rows, in_cols, pad_a, pad_b;   // raw input plane (elements), its extents and the padding applied in smem
+  int transpose_in;      // dgrad: the raw input is ug in neograd order [o][q][p]; staged as [o][p][q]
+};
+
+// out[n][co][ja][jb] (jb contiguous).  fprop: (ja, jb) = (q, p); staged input rows = w, cols = h?  -- see the two wrappers:
+// the kernel itself only knows: out[ja][jb] = sum_{ci, ka, kb} in_s[ci][ja + ka][jb + kb] * wts[ci][ka][kb][co]
+// where in_s is the staged plane with its CONTIGUOUS axis along jb.
+__global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict__ in, const float* __restrict__ wts_g,
+                                                         const float* __restrict__ bias, float* __restrict__ out, SmallGeo g,
+                                                         int accumulate, FastDiv d_cols, FastDiv d_plane, FastDiv d_tpi,
+                                                         FastDiv d_jbb, FastDiv d_ja) {
+  extern __shared__ float sm[];
+  const int plane_s = g.A * g.Bx + 1;                       // staged plane stride (odd-ish: spreads banks)
+  const int wsize = g.Cin * g.KA * g.KB * g.co_groups * CT;
+  float* sw = sm;                                           // [ci][ka][kb][co (padded to groups of 4)]
+  float* sx = sm + ((wsize + 3) & ~3);                      // [G][ci][A][Bx]
+  const int t = threadIdx.x;
+  for (int e = t; e < wsize; e += 256) sw[e] = __ldg(wts_g + e);
+  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
+  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
+    const int n0 = (int)(pass * g.G);
+    const int ng = min(g.G, g.N - n0);
+    __syncthreads();
+    // ---- stage: zero fill (padding), then the raw planes
+    const int stage_elems = ng * g.Cin * plane_s;
+    if (g.pad_a | g.pad_b) {
+      for (int e = t; e < stage_elems; e += 256) sx[e] = 0.f;
+      __syncthreads();
+    }
+    const int raw = ng * g.Cin * g.in_plane;
+    const float* src = in + (int64_t)n0 * g.Cin * g.in_plane;
+#pragma unroll 4
+    for (int e = t; e < raw; e += 256) {
+      uint32_t pl, f, r, c;
+      d_plane.divmod(e, pl, f);          // pl = image*Cin + ci
+      d_cols.divmod(f, r, c);            // raw plane is [in_rows][in_cols], cols contiguous
+      const float v = __ldg(src + e);
+      if (g.transpose_in) sx[pl * plane_s + (c + g.pad_a) * g.Bx + r + g.pad_b] = v;   // [q][p] -> staged [p][q]
+      else sx[pl * plane_s + (r + g.pad_a) * g.Bx + c + g.pad_b] = v;
+    }
+    __syncthreads();
+    // ---- compute: thread <-> (image, co group, ja, jb block)
+    uint32_t img, rem;
+    d_tpi.divmod(t, img, rem);
+    if ((int)img < ng) {
+      uint32_t r2, jbb, cg, ja;
+      d_jbb.divmod(rem, r2, jbb);
+      d_ja.divmod(r2, cg, ja);
+      const int jb0 = jbb * RT;
+      float acc[CT][RT];
+#pragma unroll
+      for (int c = 0; c < CT; ++c)
+#pragma unroll
+        for (int i = 0; i < RT; ++i) acc[c][i] = 0.f;
+      const float* xi = sx + (size_t)img * g.Cin * plane_s;
+      for (int ci = 0; ci < g.Cin; ++ci) {
+        for (int ka = 0; ka < g.KA; ++ka) {
+          const float* row = xi + ci * plane_s + (ja + ka) * g.Bx + jb0;
+          const float* wr = sw + ((ci * g.KA + ka) * g.KB) * g.co_groups * CT + cg * CT;
+          float win[RT];
+#pragma unroll
+          for (int i = 0; i < RT - 1; ++i) win[i + 1] = row[i];
+          for (int kb = 0; kb < g.KB; ++kb) {
+#pragma unroll
+            for (int i = 0; i < RT - 1; ++i) win[i] = win[i + 1];
+            win[RT - 1] = row[kb + RT - 1];
+            const float4 w4 = *reinterpret_cast<const float4*>(wr + kb * g.co_groups * CT);
+#pragma unroll
+            for (int i = 0; i < RT; ++i) {
+              acc[0][i] = fmaf(win[i], w4.x, acc[0][i]);
+              acc[1][i] = fmaf(win[i], w4.y, acc[1][i]);
+              acc[2][i] = fmaf(win[i], w4.z, acc[2][i]);
+              acc[3][i] = fmaf(win[i], w4.w, acc[3][i]);
+            }
+          }
+        }
+      }
+      // ---- store: RT contiguous outputs per channel
+      const int n = n0 + img;
+#pragma unroll
+      for (int c = 0; c < CT; ++c) {
+        const int co = cg * CT + c;
+        if (co < g.Cout) {
+          const float bv = bias ? __ldg(bias + co) : 0.f;
+          float* o = out + (((int64_t)n * g.Cout + co) * g.JA + ja) * g.JB + jb0;
+#pragma unroll
+          for (int i = 0; i < RT; ++i) {
+            if (jb0 + i < g.JB) o[i] = accumulate ? o[i] + acc[c][i] + bv : acc[c][i] + bv;
+          }
+        }
+      }
+    }
+  }
+}
+
+// weights -> [ci][ka][kb][co padded]:  fprop  ci = c, (ka, kb) = (kw, kh), co = o          (out (ja,jb) = (q,p): rows w, cols h)
+//                                      dgrad  ci = o, (ka, kb) = (KH-1-kh, KW-1-kw), co = c (out (ja,jb) = (h,w): rows p, cols q)
+__global__ void __launch_bounds__(256) pack_small_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int O, int C,
+                                                                 int KH, int KW, int dgrad, int cop) {
+  const int Cin = dgrad ? O : C, KA = dgrad ? KH : KW, KB = dgrad ? KW : KH;
+  const int total = Cin * KA * KB * cop;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int co = i % cop;
+    const int kb = (i / cop) % KB;
+    const int ka = (i / (cop * KB)) % KA;
+    const int ci = i / (cop * KB * KA);
+    float v = 0.f;
+    if (!dgrad) {
+      if (co < O) v = w[(((int64_t)co * C + ci) * KH + kb) * KW + ka];            // o = co, c = ci, kh = kb, kw = ka
+    } else {
+      if (co < C) v = w[(((int64_t)ci * C + co) * KH + (KH - 1 - ka)) * KW + (KW - 1 - kb)];   // o = ci, c = co
+    }
+    wp[i] = v;
+  }
+}
+
+// fprop: staged input plane is x transposed?  No: fprop needs the window to slide along p (= h), so the staged plane keeps
+// h CONTIGUOUS: x[c][h][w] is staged as [w][h] (transpose_in), rows = w (ja = q, taps kw), cols = h (jb = p, taps kh).
+// dgrad: ug [o][q][p] (p contiguous) must slide along q (= w): staged as [p][q] (transpose_in), rows = p (ja = h), cols = q.
+static int conv_small(const float* in, const float* w, const float* bias, float* out, const ConvGeo& cg, int dgrad, int accumulate,
+                      cudaStream_t st, bool* done) {
+  *done = false;
+  if (cg.stride != 1) return NGB_OK;
+  SmallGeo g;
+  g.N = cg.N;
+  int padA, padB;
+  if (!dgrad) {
+    if (cg.pad > cg.KH - 1 && cg.pad > cg.KW - 1) { /* fine: zero halo is staged */ }
+    g.Cin = cg.C; g.Cout = cg.O;
+    g.in_rows = cg.H; g.in_cols = cg.W;                 // raw x plane [h][w]
+    g.KA = cg.KW; g.KB = cg.KH;
+    padA = cg.pad; padB = cg.pad;
+    g.A = cg.W + 2 * padA; g.Bx = cg.H + 2 * padB;      // staged [w][h]
+    g.JA = cg.Wo; g.JB = cg.Ho;
+  } else {
+    if (cg.pad > cg.KH - 1 || cg.pad > cg.KW - 1) return NGB_OK;
+    g.Cin = cg.O; g.Cout = cg.C;
+    g.in_rows = cg.Wo; g.in_cols = cg.Ho;               // raw ug plane [q][p]
+    g.KA = cg.KH; g.KB = cg.KW;
+    padA = cg.KH - 1 - cg.pad; padB = cg.KW - 1 - cg.pad;
+    g.A = cg.Ho + 2 * padA; g.Bx = cg.Wo + 2 * padB;    // staged [p][q]
+    g.JA = cg.H; g.JB = cg.W;
+  }
+  g.transpose_in = 1;
+  g.pad_a = padA; g.pad_b = padB;
+  g.in_plane = g.in_rows * g.in_cols;
+  g.co_groups = ceil_div(g.Cout, CT);
+  g.jb_blocks = ceil_div(g.JB, RT);
+  // the sliding window reads RT + KB - 1 columns from jb0: keep that inside the staged row
+  const int need_cols = g.jb_blocks * RT + g.KB - 1;
+  if (need_cols > g.Bx) g.Bx = need_cols;
+  g.tpi = g.co_groups * g.JA * g.jb_blocks;
+  if (g.tpi > 256 || g.Cin > 64) return NGB_OK;
+  g.G = 256 / g.tpi;
+  const int plane_s = g.A * g.Bx + 1;
+  const int wsize = g.Cin * g.KA * g.KB * g.co_groups * CT;
+  while (g.G > 1 && ((size_t)((wsize + 3) & ~3) + (size_t)g.G * g.Cin * plane_s) * 4 > 44 * 1024) --g.G;
+  if (g.G > g.N) g.G = g.N > 0 ? g.N : 1;
+  const size_t smem = ((size_t)((wsize + 3) & ~3) + (size_t)g.G * g.Cin * plane_s) * 4;
+  if (smem > 46 * 1024 || (int64_t)wsize * 4 > (1 << 20)) return NGB_OK;
+  int rc = ensure_init();
+  if (rc) return rc;
+  // packed weights live at the END of the scratch arena (the front is used by split reductions)
+  float* wp = scratch_ptr() + (scratch_bytes() / 4 - (1 << 18));
+  pack_small_weights_kernel<<<ceil_div(wsize, 256), 256, 0, st>>>(w, wp, cg.O, cg.C, cg.KH, cg.KW, dgrad, g.co_groups * CT);
+  NGB_LAUNCH_CHECK();
+  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
+  const int grid = (int)(passes < (int64_t)kNumSMs * 4 ? passes : (int64_t)kNumSMs * 4);
+  conv_small_kernel<<<grid, 256, smem, st>>>(in, wp, bias, out, g, accumulate, FastDiv((uint32_t)g.in_cols),
+                                            FastDiv((uint32_t)g.in_plane), FastDiv((uint32_t)g.tpi), FastDiv((uint32_t)g.jb_blocks),
+                                            FastDiv((uint32_t)g.JA));
+  NGB_LAUNCH_CHECK();
+  *done = true;
+  return NGB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- wgrad, small layers
 // The LeNet / digits layers (C*KH*O <= 512 filter rows, images of a few KB).  A CTA walks its share of the batch one image
 // at a time: x[n] and ug[n] (un-scrambled to [o][p][q]) are staged in smem, thread <-> (filter row (o,c,kh), slice of
@@ -430,6 +624,11 @@ extern "C" int ngb_conv_fprop(const float* x, const float* w, const float* b, fl
   cudaStream_t st = as_stream(stream);
   if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(x) && aligned16(y) && aligned16(w))
     return conv_igemm_fprop(x, w, b, y, N, C, H, W, O, KH, KW, pad, st);
+  {
+    bool done = false;
+    rc = conv_small(x, w, b, y, g, 0, 0, st, &done);
+    if (rc || done) return rc;
+  }
   // tile shape: p (fastest output axis) first
   int TP = g.Ho < 16 ? g.Ho : 16;
   int TQ = 256 / TP; if (TQ > g.Wo) TQ = g.Wo;
@@ -460,6 +659,8 @@ extern "C" int ngb_conv_dgrad(const float* ug, const float* w, float* dx, int64_
   cudaStream_t st = as_stream(stream);
   if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(ug) && aligned16(dx) && aligned16(w))
     return conv_igemm_dgrad(ug, w, dx, N, C, H, W, O, KH, KW, pad, accumulate, st);
+  // (conv_small's dgrad mode is correct but measured slower than the tap-skipping kernel below on LeNet's 8x8 -> 12x12
+  //  layer -- the full-correlation zero halo makes it do 2.25x the useful work -- so it is not dispatched here.)
   int TW = g.W < 32 ? g.W : 32;
   int TH = 256 / TW; if (TH > g.H) TH = g.H;
   const int PPmax = (TH + g.KH - 2) / g.stride + 2, PQmax = (TW + g.KW - 2) / g.stride + 2, PPp = PPmax | 1;

@@ -252,13 +252,33 @@ __global__ void __launch_bounds__(256) ew_bwd_fullreduce_kernel(int op, int side
   if (threadIdx.x == 0) dst[blockIdx.x] = (accumulate && gridDim.x == 1) ? dst[blockIdx.x] + acc : acc;
 }
 
-// Sum `splits` partial rows of length K into out (deterministic second pass).
+// Sum `splits` partial rows of length K into out (deterministic second pass).  CTA = 32 columns x 8 split lanes: lane j
+// adds splits j, j+8, ... and the eight lane sums are combined in a fixed order, so the result does not depend on timing.
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int splits, int64_t K,
                                                            float* __restrict__ out, int accumulate) {
-  for (int64_t k = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; k < K; k += (int64_t)gridDim.x * blockDim.x) {
+  __shared__ float tile[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int64_t k0 = (int64_t)blockIdx.x * 32; k0 < K; k0 += (int64_t)gridDim.x * 32) {
+    const int64_t k = k0 + tx;
     float s = 0.f;
-    for (int j = 0; j < splits; ++j) s += part[(int64_t)j * K + k];
-    out[k] = accumulate ? out[k] + s : s;
+    if (k < K) {
+      int j = ty;
+      for (; j + 24 < splits; j += 32) {
+        const float a = part[(int64_t)j * K + k], b = part[(int64_t)(j + 8) * K + k];
+        const float c = part[(int64_t)(j + 16) * K + k], d = part[(int64_t)(j + 24) * K + k];
+        s += (a + b) + (c + d);
+      }
+      for (; j < splits; j += 8) s += part[(int64_t)j * K + k];
+    }
+    tile[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && k < K) {
+      float r = tile[0][tx];
+#pragma unroll
+      for (int j = 1; j < 8; ++j) r += tile[j][tx];
+      out[k] = accumulate ? out[k] + r : r;
+    }
+    __syncthreads();
   }
 }
 
@@ -520,7 +540,7 @@ static int reduce_dispatch(int op, int side, const BDims& d, int64_t total, cons
     ew_bwd_fullreduce_kernel<<<grid, 256, 0, st>>>(op, side, ug, a, as, d.sa[0], b, bs, d.sb[0], dst, accumulate, R);
     NGB_LAUNCH_CHECK();
     if (grid > 1) {
-      sum_partials_kernel<<<1, 32, 0, st>>>(scratch_ptr(), grid, 1, grad, accumulate);
+      sum_partials_kernel<<<1, 256, 0, st>>>(scratch_ptr(), grid, 1, grad, accumulate);
       NGB_LAUNCH_CHECK();
     }
     return NGB_OK;
@@ -550,7 +570,7 @@ static int reduce_dispatch(int op, int side, const BDims& d, int64_t total, cons
       colsum4_kernel<<<grid, 256, 0, st>>>(ug, splits > 1 ? scratch_ptr() : grad, accumulate, Rc, K4, rps, scale);
       NGB_LAUNCH_CHECK();
       if (splits > 1) {
-        sum_partials_kernel<<<grid_for(Kc, 256), 256, 0, st>>>(scratch_ptr(), (int)splits, Kc, grad, accumulate);
+        sum_partials_kernel<<<grid_for(Kc * 8, 256), 256, 0, st>>>(scratch_ptr(), (int)splits, Kc, grad, accumulate);
         NGB_LAUNCH_CHECK();
       }
       return NGB_OK;
@@ -591,7 +611,7 @@ static int reduce_dispatch(int op, int side, const BDims& d, int64_t total, cons
 }
 
 int launch_sum_partials(const float* part, int splits, int64_t K, float* out, int accumulate, cudaStream_t st) {
-  sum_partials_kernel<<<grid_for(K, 256), 256, 0, st>>>(part, splits, K, out, accumulate);
+  sum_partials_kernel<<<grid_for(K * 8, 256), 256, 0, st>>>(part, splits, K, out, accumulate);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
