@@ -314,7 +314,13 @@ def run_device(args):
       roofline = {'kernel': top, 'bound': 'tensor', 'achieved': fl / mean_s / 1e12, 'peak': pk['tf32_tflops'], 'unit': 'TFLOP/s'}
     else:
       roofline = {'kernel': top, 'bound': 'hbm', 'achieved': by / mean_s / 1e9, 'peak': pk['hbm_gbs'], 'unit': 'GB/s'}
-    roofline.update(frac=roofline['achieved'] / roofline['peak'], traffic=None, peak_source=pk['source'],
+    traffic = None
+    try:   # DRAM bytes per launch of this kernel at this shape from the committed ncu --set full capture, if there is one
+      with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as f:
+        traffic = json.load(f).get(top + ':' + ','.join(str(v) for v in gkey))
+    except Exception:
+      pass
+    roofline.update(frac=roofline['achieved'] / roofline['peak'], traffic=traffic, peak_source=pk['source'],
                     algorithmic_bytes=by, algorithmic_flops=fl, mean_launch_us=mean_s * 1e6, shape_args=list(gkey),
                     share_of_eager_step=g['ms'] / total_ms)
 
