@@ -53,6 +53,9 @@ const char* ngb_last_error(void);
 /* Allocates the per-device scratch arena (bytes; 0 = default 64 MiB). Idempotent; must run before graph capture. */
 int ngb_init(int64_t scratch_bytes);
 int ngb_shutdown(void);
+/* Debug aid: synchronises the device and reports (NGB_ERR_CUDA + ngb_last_error) if a tcgen05 producer / MMA / epilogue
+ * warp gave up waiting on a pipeline barrier since the last call (such waits are bounded so a bug cannot hang the GPU). */
+int ngb_debug_check_pipelines(void);
 /* Pre-sizes the grow-on-demand workspace the tensor-core convolutions stage their channels-last operand copies in
  * (N*C*H*W*4 bytes of the largest staged tensor).  Only needed before CUDA-graph capture, where growing is not allowed. */
 int ngb_workspace_reserve(int64_t bytes);

@@ -50,6 +50,7 @@ SIGNATURES = {
   'ngb_last_error': ([], c_char_p),
   'ngb_init': ([c_int64], c_int),
   'ngb_shutdown': ([], c_int),
+  'ngb_debug_check_pipelines': ([], c_int),
   'ngb_workspace_reserve': ([c_int64], c_int),
   'ngb_set_default_engine': ([c_int], c_int),
   'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
@@ -138,7 +139,7 @@ class profile_calls:
   `records` is a list of (name, args, start_event, end_event); call `summary()` after the block (it synchronises).
   Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
   SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
-          'ngb_set_default_engine', 'ngb_workspace_reserve')
+          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines')
 
   def __enter__(self):
     import torch

@@ -728,6 +728,8 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
   return NGB_OK;
 }
 
+unsigned long long conv_take_timeout() { return tc::take_mbar_timeout(); }
+
 }  // namespace ngb
 
 using namespace ngb;

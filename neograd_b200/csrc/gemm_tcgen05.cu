@@ -410,7 +410,10 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
 
 using namespace ngb;
 
-namespace ngb { std::atomic<int> g_default_engine{NGB_GEMM_AUTO}; }
+namespace ngb {
+std::atomic<int> g_default_engine{NGB_GEMM_AUTO};
+unsigned long long gemm_take_timeout() { return tc::take_mbar_timeout(); }
+}
 
 extern "C" int ngb_set_default_engine(int engine) {
   if (engine != NGB_GEMM_AUTO && engine != NGB_GEMM_SIMT) return g_default_engine.load();

@@ -64,6 +64,25 @@ extern "C" int ngb_init(int64_t scratch_bytes) {
   return NGB_OK;
 }
 
+namespace ngb {
+unsigned long long gemm_take_timeout();
+unsigned long long conv_take_timeout();
+}
+
+// A producer / MMA / epilogue warp that waits on an mbarrier for more than a second records where and leaves the kernel
+// instead of hanging the GPU.  Returns 0 if no tcgen05 pipeline timed out since the last call, else NGB_ERR_CUDA with the
+// location in ngb_last_error().  Synchronises the device (debug / test use).
+extern "C" int ngb_debug_check_pipelines(void) {
+  NGB_CUDA(cudaDeviceSynchronize());
+  const unsigned long long a = gemm_take_timeout(), b = conv_take_timeout();
+  if (a | b) {
+    const unsigned long long v = a ? a : b;
+    return fail(NGB_ERR_CUDA, "tcgen05 pipeline timeout in %s kernel: wait tag %llu, block %llu, thread %llu", a ? "gemm" : "conv",
+                (v >> 48) & 0x7fff, (v >> 16) & 0xffffffffull, v & 0xffff);
+  }
+  return NGB_OK;
+}
+
 extern "C" int ngb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (g_scratch) {

@@ -54,3 +54,20 @@ def test_product_never_imports_oracle():
         if re.search(r'^\s*(from|import)\s+oracle\b', src, flags=re.M) or 'oracle/' in src and f.endswith('.py') and 'import' in src and re.search(r'import.*oracle', src):
           bad.append(os.path.join(dp, f))
   assert not bad, bad
+
+
+def test_neograd_alias_package():
+  """`import neograd as ng` (the reference's import name) resolves to the device backend, sub-modules included."""
+  import neograd as ng
+  from neograd import nn
+  from neograd.nn import loss, optim
+  from neograd.autograd.utils import grad_check, fn_grad_check
+  import neograd_b200
+  assert ng is neograd_b200 and nn is neograd_b200.nn and loss.SoftmaxCE is neograd_b200.nn.loss.SoftmaxCE
+  assert optim.Adam is neograd_b200.nn.optim.Adam and callable(grad_check) and callable(fn_grad_check)
+  for name in ('tensor', 'new_graph', 'no_track', 'add', 'sub', 'mul', 'div', 'pow', 'exp', 'log', 'dot', 'sum', 'transpose',
+               'flatten', 'reshape', 'load', 'save', 'Checkpoint', 'nn', 'autograd'):   # neograd/__init__.py:1-6
+    assert hasattr(ng, name), name
+  for name in ('Model', 'Sequential', 'Dropout', 'Linear', 'Conv2D', 'Conv3D', 'MaxPool2D', 'MaxPool3D', 'ReLU', 'Sigmoid', 'Tanh',
+               'Softmax', 'LeakyReLU', 'Checkpoint', 'save_model', 'load_model'):       # neograd/nn/__init__.py:1-5
+    assert hasattr(nn, name), name

@@ -282,6 +282,11 @@ def test_conv_igemm_exact_on_small_integers(U):
   assert np.array_equal(U.conv_dgrad(ug, w, x.shape, 1, 1), ops.conv3d_dgrad(ug, w, x.shape, 1, 1).astype(np.float32))
 
 
+def test_no_pipeline_timeouts(U):
+  """Runs last in this file's conv / gemm group: no tcgen05 warp gave up on a barrier during the tests above."""
+  U.call('ngb_debug_check_pipelines')
+
+
 def test_conv_errors(U):
   x, w, b = np.zeros((1, 1, 5, 5)), np.zeros((1, 1, 3, 3)), np.zeros(1)
   import torch
