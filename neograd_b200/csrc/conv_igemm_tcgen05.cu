@@ -538,7 +538,6 @@ conv_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_ug, const __gri
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(128, BLOCK_N, 0, 1);
       constexpr uint64_t adesc_base = make_smem_desc_base(16, 1024);                          // ug: K-major, 128B swizzle
       constexpr uint64_t desc_base = make_smem_desc_base(4096, 512, kLayoutSW128Base32B);   // x: MN-major, 32B-atom swizzle
       uint32_t it = 0, tile_it = 0;
@@ -549,6 +548,7 @@ conv_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_ug, const __gri
         const int64_t kb1 = min(g.kblocks, kb0 + g.kb_per_split);
         mbar_wait(tmem_empty, (tile_it & 1) ^ 1, 12);
         tc_fence_after();
+        const uint32_t idesc_n = make_idesc_tf32(128, ntap * BLOCK_N, 0, 1);
         for (int64_t kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -556,12 +556,12 @@ conv_wgrad_igemm_kernel(const __grid_constant__ CUtensorMap tmap_ug, const __gri
           tc_fence_after();
           const uint32_t a_addr = smem_u32(smem_a + s * C_::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + s * C_::kBBytes);
-          for (int t = 0; t < ntap; ++t) {
+          // the ntap x-tiles sit back to back as [tap][c chunk][32 pos][32 c] = ONE MN-major B operand with N = ntap*BN
+          // columns, so a single MMA per k-step covers every tap of the group (A is read once, not once per tap)
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_tf32(tmem_base + t * BLOCK_N, smem_desc(adesc_base, a_addr + k * UMMA_K * 4),
-                        smem_desc(desc_base, b_addr + t * (BLOCK_N / 32) * 4096 + k * 1024), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
-            }
+          for (int k = 0; k < 4; ++k) {
+            umma_tf32(tmem_base, smem_desc(adesc_base, a_addr + k * UMMA_K * 4), smem_desc(desc_base, b_addr + k * 1024), idesc_n,
+                      (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);
         }
