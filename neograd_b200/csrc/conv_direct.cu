@@ -439,6 +439,144 @@ static int conv_small(const float* in, const float* w, const float* bias, float*
   return NGB_OK;
 }
 
+
+// ---------------------------------------------------------------------------------------------- dgrad, small layers
+// dx[n][c][h][w] = sum_{o,kh,kw} ug[n][o][p = h+pad-kh][q = w+pad-kw] * w[o][c][kh][kw]   (conv.py:299-309)
+// Thread <-> (image, h, block of DW consecutive w) and ALL input channels c (<= 8) in registers.  ug is staged
+// un-scrambled as [o][p][q] with a zero halo of KW-1 columns only; rows p outside the image are skipped (no work on the
+// vertical halo), and a DW+KW-1 register window slides along kw.  Weights sit in smem as [o][kh][kw][8 c] (two broadcast
+// 128-bit loads per tap for 8*DW FMAs).
+constexpr int DW = 4;
+template <int KW>
+__global__ void __launch_bounds__(256) conv_dgrad_small_kernel(const float* __restrict__ ug, const float* __restrict__ wts_g,
+                                                               float* __restrict__ dx, ConvGeo g, int G, int tpi, int wblocks,
+                                                               int accumulate, FastDiv d_howo, FastDiv d_ho, FastDiv d_tpi,
+                                                               FastDiv d_wb) {
+  extern __shared__ float sm[];
+  const int halo = KW - 1;
+  const int Bq = g.Wo + 2 * halo;                      // staged row: [halo | q = 0..Wo-1 | halo]
+  const int plane_s = g.Ho * Bq + 1;
+  const int wsize = g.O * g.KH * KW * 8;
+  float* sw = sm;                                      // [o][kh][kw][8]
+  float* su = sm + wsize;                              // [G][o][Ho][Bq]
+  const int t = threadIdx.x;
+  for (int e = t; e < wsize; e += 256) sw[e] = __ldg(wts_g + e);
+  const int HoWo = g.Ho * g.Wo;
+  const int64_t passes = ceil_div<int64_t>(g.N, G);
+  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
+    const int n0 = (int)(pass * G);
+    const int ng = min(G, g.N - n0);
+    __syncthreads();
+    for (int e = t; e < ng * g.O * plane_s; e += 256) su[e] = 0.f;
+    __syncthreads();
+    const float* src = ug + (int64_t)n0 * g.O * HoWo;
+    const int raw = ng * g.O * HoWo;
+#pragma unroll 4
+    for (int e = t; e < raw; e += 256) {                 // global [o][q][p] -> smem [o][p][halo + q]
+      uint32_t pl, f, q, p;
+      d_howo.divmod(e, pl, f);
+      d_ho.divmod(f, q, p);
+      su[pl * plane_s + p * Bq + halo + q] = __ldg(src + e);
+    }
+    __syncthreads();
+    uint32_t img, rem;
+    d_tpi.divmod(t, img, rem);
+    if ((int)img < ng) {
+      uint32_t h, wb;
+      d_wb.divmod(rem, h, wb);
+      const int w0 = wb * DW;
+      float acc[8][DW];
+#pragma unroll
+      for (int c = 0; c < 8; ++c)
+#pragma unroll
+        for (int i = 0; i < DW; ++i) acc[c][i] = 0.f;
+      // dx[h][w0+i] needs ug[p][q = w0 + i + pad - kw]; with j = KW-1-kw the staged column is (w0 + pad) + i + j
+      const int col0 = w0 + g.pad;
+      int kh_lo = (int)h + g.pad - (g.Ho - 1); if (kh_lo < 0) kh_lo = 0;
+      int kh_hi = (int)h + g.pad; if (kh_hi > g.KH - 1) kh_hi = g.KH - 1;
+      for (int o = 0; o < g.O; ++o) {
+        const float* up = su + ((size_t)img * g.O + o) * plane_s;
+        for (int kh = kh_lo; kh <= kh_hi; ++kh) {
+          const int p = (int)h + g.pad - kh;
+          const float* row = up + p * Bq + col0;
+          const float* wr = sw + ((o * g.KH + kh) * KW) * 8;
+          float win[DW + KW - 1];
+#pragma unroll
+          for (int i = 0; i < DW + KW - 1; ++i) win[i] = row[i];
+#pragma unroll
+          for (int j = 0; j < KW; ++j) {                  // j = KW-1-kw
+            const float4 wa = *reinterpret_cast<const float4*>(wr + (KW - 1 - j) * 8);
+            const float4 wb4 = *reinterpret_cast<const float4*>(wr + (KW - 1 - j) * 8 + 4);
+#pragma unroll
+            for (int i = 0; i < DW; ++i) {
+              const float v = win[i + j];
+              acc[0][i] = fmaf(v, wa.x, acc[0][i]); acc[1][i] = fmaf(v, wa.y, acc[1][i]);
+              acc[2][i] = fmaf(v, wa.z, acc[2][i]); acc[3][i] = fmaf(v, wa.w, acc[3][i]);
+              acc[4][i] = fmaf(v, wb4.x, acc[4][i]); acc[5][i] = fmaf(v, wb4.y, acc[5][i]);
+              acc[6][i] = fmaf(v, wb4.z, acc[6][i]); acc[7][i] = fmaf(v, wb4.w, acc[7][i]);
+            }
+          }
+        }
+      }
+      const int n = n0 + img;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        if (c < g.C) {
+          float* d = dx + (((int64_t)n * g.C + c) * g.H + h) * g.W + w0;
+#pragma unroll
+          for (int i = 0; i < DW; ++i)
+            if (w0 + i < g.W) d[i] = accumulate ? d[i] + acc[c][i] : acc[c][i];
+        }
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) pack_dgrad_small_weights_kernel(const float* __restrict__ w, float* __restrict__ wp, int O,
+                                                                       int C, int KH, int KW) {
+  const int total = O * KH * KW * 8;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int c = i & 7;
+    const int tap = (i >> 3) % (KH * KW);
+    const int o = (i >> 3) / (KH * KW);
+    wp[i] = c < C ? w[((int64_t)o * C + c) * KH * KW + tap] : 0.f;
+  }
+}
+
+static int conv_dgrad_small(const float* ug, const float* w, float* dx, const ConvGeo& g, int accumulate, cudaStream_t st, bool* done) {
+  *done = false;
+  if (g.stride != 1 || g.C > 8 || g.O > 64 || (g.KW != 3 && g.KW != 5)) return NGB_OK;
+  if (g.pad > g.KW - 1) return NGB_OK;                  // the staged column halo is KW-1 wide
+  const int wblocks = ceil_div(g.W, DW);
+  const int tpi = g.H * wblocks;
+  if (tpi > 256) return NGB_OK;
+  // every window read must stay inside the staged row: col0 + DW + KW - 2 <= Bq - 1 for the last block
+  const int Bq = g.Wo + 2 * (g.KW - 1);
+  if ((wblocks - 1) * DW + g.pad + DW + g.KW - 2 > Bq - 1) return NGB_OK;
+  int G = 256 / tpi;
+  const int plane_s = g.Ho * Bq + 1;
+  const int wsize = g.O * g.KH * g.KW * 8;
+  while (G > 1 && ((size_t)wsize + (size_t)G * g.O * plane_s) * 4 > 44 * 1024) --G;
+  if (G > g.N) G = g.N > 0 ? g.N : 1;
+  const size_t smem = ((size_t)wsize + (size_t)G * g.O * plane_s) * 4;
+  if (smem > 46 * 1024 || wsize * 4 > (1 << 20)) return NGB_OK;
+  int rc = ensure_init();
+  if (rc) return rc;
+  float* wp = scratch_ptr() + (scratch_bytes() / 4 - (1 << 18));
+  pack_dgrad_small_weights_kernel<<<ceil_div(wsize, 256), 256, 0, st>>>(w, wp, g.O, g.C, g.KH, g.KW);
+  NGB_LAUNCH_CHECK();
+  const int64_t passes = ceil_div<int64_t>(g.N, G);
+  const int grid = (int)(passes < (int64_t)kNumSMs * 4 ? passes : (int64_t)kNumSMs * 4);
+  const FastDiv dhowo((uint32_t)(g.Ho * g.Wo)), dho((uint32_t)g.Ho), dtpi((uint32_t)tpi), dwb((uint32_t)wblocks);
+  if (g.KW == 3)
+    conv_dgrad_small_kernel<3><<<grid, 256, smem, st>>>(ug, wp, dx, g, G, tpi, wblocks, accumulate, dhowo, dho, dtpi, dwb);
+  else
+    conv_dgrad_small_kernel<5><<<grid, 256, smem, st>>>(ug, wp, dx, g, G, tpi, wblocks, accumulate, dhowo, dho, dtpi, dwb);
+  NGB_LAUNCH_CHECK();
+  *done = true;
+  return NGB_OK;
+}
+
 // ---------------------------------------------------------------------------------------------- wgrad, small layers
 // The LeNet / digits layers (C*KH*O <= 512 filter rows, images of a few KB).  A CTA walks its share of the batch one image
 // at a time: x[n] and ug[n] (un-scrambled to [o][p][q]) are staged in smem, thread <-> (filter row (o,c,kh), slice of
@@ -659,8 +797,13 @@ extern "C" int ngb_conv_dgrad(const float* ug, const float* w, float* dx, int64_
   cudaStream_t st = as_stream(stream);
   if (conv_igemm_eligible(N, C, H, W, O, KH, KW, pad, stride) && aligned16(ug) && aligned16(dx) && aligned16(w))
     return conv_igemm_dgrad(ug, w, dx, N, C, H, W, O, KH, KW, pad, accumulate, st);
-  // (conv_small's dgrad mode is correct but measured slower than the tap-skipping kernel below on LeNet's 8x8 -> 12x12
-  //  layer -- the full-correlation zero halo makes it do 2.25x the useful work -- so it is not dispatched here.)
+  // (conv_small's dgrad mode is correct but measured slower than tap skipping on LeNet's 8x8 -> 12x12 layer -- the
+  //  full-correlation zero halo makes it do 2.25x the useful work -- so small layers use conv_dgrad_small instead.)
+  {
+    bool done = false;
+    rc = conv_dgrad_small(ug, w, dx, g, accumulate, st, &done);
+    if (rc || done) return rc;
+  }
   int TW = g.W < 32 ? g.W : 32;
   int TH = 256 / TW; if (TH > g.H) TH = g.H;
   const int PPmax = (TH + g.KH - 2) / g.stride + 2, PQmax = (TW + g.KW - 2) / g.stride + 2, PPp = PPmax | 1;
