@@ -21,6 +21,12 @@ int conv_igemm_dgrad(const float* ug, const float* w, float* dx, int64_t N, int6
 int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O,
                      int64_t KH, int64_t KW, int64_t pad, int accumulate, cudaStream_t st);
 
+// conv_small_mma.cu: TF32 mma.sync kernels for small-channel layers (fprop mode 0 / dgrad mode 1, wgrad)
+int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
+                    int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done);
+int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int H, int W, int O, int KH, int KW, int pad,
+                   int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done);
+
 constexpr int OT = 8;  // output channels per thread (register tile)
 
 struct ConvGeo {
@@ -764,6 +770,8 @@ extern "C" int ngb_conv_fprop(const float* x, const float* w, const float* b, fl
     return conv_igemm_fprop(x, w, b, y, N, C, H, W, O, KH, KW, pad, st);
   {
     bool done = false;
+    rc = conv_mma_gather(x, w, b, y, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, 0, 0, st, &done);
+    if (rc || done) return rc;
     rc = conv_small(x, w, b, y, g, 0, 0, st, &done);
     if (rc || done) return rc;
   }
@@ -801,6 +809,8 @@ extern "C" int ngb_conv_dgrad(const float* ug, const float* w, float* dx, int64_
   //  full-correlation zero halo makes it do 2.25x the useful work -- so small layers use conv_dgrad_small instead.)
   {
     bool done = false;
+    rc = conv_mma_gather(ug, w, nullptr, dx, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, 1, accumulate, st, &done);
+    if (rc || done) return rc;
     rc = conv_dgrad_small(ug, w, dx, g, accumulate, st, &done);
     if (rc || done) return rc;
   }
@@ -838,6 +848,8 @@ extern "C" int ngb_conv_wgrad(const float* ug, const float* x, float* dw, int64_
     return conv_igemm_wgrad(ug, x, dw, N, C, H, W, O, KH, KW, pad, accumulate, st);
   {
     bool done = false;
+    rc = conv_mma_wgrad(ug, x, dw, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, accumulate, st, &done);
+    if (rc || done) return rc;
     rc = conv_wgrad_small(ug, x, dw, g, accumulate, st, &done);
     if (rc || done) return rc;
   }

@@ -1,0 +1,584 @@
+// Tensor-core convolution kernels for SMALL-CHANNEL layers (LeNet / digits family: C or O below the 32-channel
+// granularity the tcgen05 implicit GEMM in conv_igemm_tcgen05.cu needs).
+// Reference: neograd/autograd/ops/conv.py:245-269 (fprop), 299-309 (dgrad), 311-321 (wgrad).
+//
+// Why not tcgen05 here: with C = 1..8 input channels a filter tap contributes fewer than 8 K-elements, and a UMMA
+// shared-memory descriptor can only describe operands whose rows are 16-byte chunks at a constant stride -- an im2col
+// view of a 6-channel 12x12 image is not such an operand without first materialising it (25x the bytes).  The warp-level
+// mma.sync.m16n8k8 TF32 instruction takes its fragments from registers, so every lane can GATHER its elements straight
+// from the staged image:      A[f][k] = img_s[ aoff[f] + koff[k] ]
+// (offset of output position f plus offset of tap/channel k -- the im2col matrix is never built).  These layers are
+// memory/LSU bound (150..400 MACs per output), the tensor pipe only has to stop being the limiter: the CUDA-core
+// kernels in conv_direct.cu ran at 8-10 TFLOP/s = 4 % of the HBM roofline of the layer.
+//
+// All kernels: a persistent CTA stages G whole images (TF32-rounded, zero halo for padding) in shared memory and walks
+// its share of the batch.  Exact-fp32 mode (ngb_set_default_engine(NGB_GEMM_SIMT)) never comes here.
+#include "common.cuh"
+
+namespace ngb {
+
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+
+// D(16x8) += A(16x8, row) * B(8x8, col); lane = 4*g + t:
+//   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g);  d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1)
+// The k labels are only names: both operands use the same permutation of the reduction index.
+__device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
+                                         uint32_t b1) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+      : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+      : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// ------------------------------------------------------------------------------------------------ fprop / dgrad
+// out[n][co][f] = bias[co] + sum_k img_s[n][aoff[f] + koff[k]] * Wp[k][co]
+//   fprop: f = q*Ho + p (neograd order), k = (c,kh,kw);      img = x natural [c][h+pad][w+pad]
+//   dgrad: f = h*W + w,               k = (kh,kw,o padded); img = ug un-scrambled [o][p+KH-1-pad][q+KW-1-pad]
+struct GatherGeo {
+  int N, Cin, Cout;
+  int raw_rows, raw_cols, raw_plane;   // raw input plane as stored in HBM (cols contiguous)
+  int transpose;                       // staged plane = raw plane transposed (dgrad: [q][p] -> [p][q])
+  int halo_r, halo_c;                  // zero halo of the staged plane
+  int spitch, splane, img_stride;      // staged row pitch, plane pitch, image pitch (floats)
+  int F, F16, MTI;                     // outputs per (image, channel); padded to 16; m-tiles per image
+  int fdiv, a_mod, a_div;              // aoff(f) = (f % fdiv) * a_mod + (f / fdiv) * a_div
+  int K, Kp;                           // reduction length, padded to 8
+  int NP, NPp;                         // Cout padded to 8; smem pitch of the packed weights (NP + 4)
+  int mode;                            // 0 fprop, 1 dgrad
+  int C, O, KH, KW, Op8;
+  int G;                               // images per pass
+};
+
+template <int MT, int NT>
+__global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __restrict__ in, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* __restrict__ out,
+                                                              GatherGeo g, int accumulate, FastDiv d_plane, FastDiv d_cols,
+                                                              FastDiv d_fdiv, FastDiv d_mti, FastDiv d_npp, FastDiv d_op8,
+                                                              FastDiv d_kw, FastDiv d_kk) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  uint32_t* wp = smem_u;                         // [Kp/8][4 t][NPp][2]: (k = 8ks+t, k = 8ks+t+4) adjacent -> one LDS.64
+  int* kpair = reinterpret_cast<int*>(wp + g.Kp * g.NPp);   // [Kp/8][4 t][2]
+  int* aoff = kpair + g.Kp;                      // [F16]
+  uint32_t* xs = reinterpret_cast<uint32_t*>(aoff + g.F16);  // [G][img_stride]  (16-byte aligned: all sizes are multiples of 4)
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5, nwarps = nthr >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int KK = g.KH * g.KW;
+
+  // ---- prologue: tables, packed weights, zero halo (once: staging only ever rewrites the interior)
+  for (int e = tid; e < g.Kp * g.NPp; e += nthr) {
+    const int half = e & 1;
+    uint32_t r, n;
+    d_npp.divmod((uint32_t)e >> 1, r, n);
+    const int k = ((int)r >> 2) * 8 + ((int)r & 3) + 4 * half;
+    float v = 0.f;
+    if (g.mode == 0) {
+      if (k < g.K && (int)n < g.O) v = __ldg(w + (int64_t)n * g.K + k);
+    } else {
+      uint32_t tap, o;
+      d_op8.divmod((uint32_t)k, tap, o);
+      if ((int)o < g.O && (int)n < g.C) v = __ldg(w + ((int64_t)o * g.C + n) * KK + tap);
+    }
+    wp[e] = to_tf32(v);
+  }
+  for (int k = tid; k < g.Kp; k += nthr) {
+    int off = 0;
+    if (g.mode == 0) {
+      if (k < g.K) {
+        uint32_t c, tap, kh, kw;
+        d_kk.divmod((uint32_t)k, c, tap);
+        d_kw.divmod(tap, kh, kw);
+        off = (int)c * g.splane + (int)kh * g.spitch + (int)kw;
+      }
+    } else {
+      uint32_t tap, o, kh, kw;
+      d_op8.divmod((uint32_t)k, tap, o);
+      d_kw.divmod(tap, kh, kw);
+      if ((int)o < g.O) off = (int)o * g.splane + (g.KH - 1 - (int)kh) * g.spitch + (g.KW - 1 - (int)kw);
+    }
+    kpair[(k >> 3) * 8 + (k & 3) * 2 + ((k >> 2) & 1)] = off;
+  }
+  for (int f = tid; f < g.F16; f += nthr) {
+    int off = 0;
+    if (f < g.F) {
+      uint32_t hi, lo;
+      d_fdiv.divmod((uint32_t)f, hi, lo);
+      off = (int)lo * g.a_mod + (int)hi * g.a_div;
+    }
+    aoff[f] = off;
+  }
+  if (g.halo_r | g.halo_c) {
+    for (int e = tid; e < g.G * g.img_stride; e += nthr) xs[e] = 0u;
+  }
+
+  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
+  const int raw_img = g.Cin * g.raw_plane;
+  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
+    const int n0 = (int)(pass * g.G);
+    const int ng = min(g.G, g.N - n0);
+    __syncthreads();   // previous pass's fragments are consumed (first pass: the prologue's zero fill is complete)
+    // ---- stage ng images, rounded to TF32
+    const float* src = in + (int64_t)n0 * raw_img;
+    const int raw = ng * raw_img;
+    if (g.transpose) {
+      // consecutive lanes walk the raw contiguous axis = the staged ROW axis: pitch = 4 (mod 8) keeps the stores spread
+#pragma unroll 4
+      for (int e = tid; e < raw; e += nthr) {
+        uint32_t pl, f, r, c;
+        d_plane.divmod((uint32_t)e, pl, f);
+        d_cols.divmod(f, r, c);
+        xs[pl * g.splane + (c + g.halo_r) * g.spitch + r + g.halo_c] = to_tf32(__ldg(src + e));
+      }
+    } else {
+      const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+      const int raw4 = vec ? (raw >> 2) : 0;
+#pragma unroll 2
+      for (int e4 = tid; e4 < raw4; e4 += nthr) {
+        const float4 v = ld_stream4(src + 4 * (int64_t)e4);
+        uint32_t pl, f, r, c;
+        d_plane.divmod((uint32_t)e4 * 4u, pl, f);
+        d_cols.divmod(f, r, c);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xs[pl * g.splane + (r + g.halo_r) * g.spitch + c + g.halo_c] = to_tf32(vv[j]);
+          if (++c == (uint32_t)g.raw_cols) {
+            c = 0;
+            if (++r == (uint32_t)g.raw_rows) { r = 0; ++pl; }
+          }
+        }
+      }
+      for (int e = raw4 * 4 + tid; e < raw; e += nthr) {
+        uint32_t pl, f, r, c;
+        d_plane.divmod((uint32_t)e, pl, f);
+        d_cols.divmod(f, r, c);
+        xs[pl * g.splane + (r + g.halo_r) * g.spitch + c + g.halo_c] = to_tf32(__ldg(src + e));
+      }
+    }
+    __syncthreads();
+
+    // ---- compute: a warp owns MT m-tiles (16 consecutive outputs of one image each) x all NT channel tiles
+    const int units = ng * g.MTI;
+    for (int u0 = warp * MT; u0 < units; u0 += nwarps * MT) {
+      int A0[MT], A1[MT], img_of[MT], f0_of[MT];
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        const int u = (u0 + i < units) ? u0 + i : u0;
+        uint32_t img, tile;
+        d_mti.divmod((uint32_t)u, img, tile);
+        img_of[i] = (int)img;
+        f0_of[i] = (int)tile * 16;
+        A0[i] = (int)img * g.img_stride + aoff[f0_of[i] + gq];
+        A1[i] = (int)img * g.img_stride + aoff[f0_of[i] + gq + 8];
+      }
+      float acc[MT][NT][4];
+#pragma unroll
+      for (int i = 0; i < MT; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+
+      const int ksteps = g.Kp >> 3;
+#pragma unroll 2
+      for (int ks = 0; ks < ksteps; ++ks) {
+        const int2 ko = *reinterpret_cast<const int2*>(kpair + ks * 8 + t * 2);
+        uint2 b[NT];
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+          b[j] = *reinterpret_cast<const uint2*>(wp + (((ks * 4 + t) * g.NPp) + j * 8 + gq) * 2);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const uint32_t a0 = xs[A0[i] + ko.x], a1 = xs[A1[i] + ko.x], a2 = xs[A0[i] + ko.y], a3 = xs[A1[i] + ko.y];
+#pragma unroll
+          for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, b[j].x, b[j].y);
+        }
+      }
+
+      // ---- epilogue: lanes of equal t hold 8 consecutive outputs of one channel -> 32-byte store segments
+#pragma unroll
+      for (int i = 0; i < MT; ++i) {
+        if (u0 + i >= units) continue;
+        const int n = n0 + img_of[i];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) {
+#pragma unroll
+          for (int r = 0; r < 4; ++r) {
+            const int co = j * 8 + 2 * t + (r & 1);
+            const int f = f0_of[i] + gq + ((r & 2) ? 8 : 0);
+            if (co < g.Cout && f < g.F) {
+              float v = acc[i][j][r];
+              if (bias) v += __ldg(bias + co);
+              float* o = out + ((int64_t)n * g.Cout + co) * g.F + f;
+              *o = accumulate ? *o + v : v;
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+static inline int round_up_mod(int v, int m, int r) {   // smallest v' >= v with v' % m == r
+  int d = (r - v % m + m) % m;
+  return v + d;
+}
+
+template <int MT, int NT>
+static int launch_gather(const float* in, const float* w, const float* bias, float* out, const GatherGeo& g, int accumulate,
+                         int nwarps, size_t smem, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  int occ = 1;   // persistent grid: exactly the CTAs that are resident at once
+  NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gather_mma_kernel<MT, NT>, nwarps * 32, smem));
+  if (occ < 1) occ = 1;
+  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
+  const int grid = (int)(passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ);
+  conv_gather_mma_kernel<MT, NT><<<grid, nwarps * 32, smem, st>>>(
+      in, w, bias, out, g, accumulate, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.fdiv),
+      FastDiv((uint32_t)g.MTI), FastDiv((uint32_t)g.NPp), FastDiv((uint32_t)g.Op8), FastDiv((uint32_t)g.KW),
+      FastDiv((uint32_t)(g.KH * g.KW)));
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+// mode 0 = fprop (in = x, out = y), mode 1 = dgrad (in = ug, out = dx).  *done tells whether the kernel was launched.
+int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
+                    int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done) {
+  *done = false;
+  if (g_default_engine.load() == NGB_GEMM_SIMT) return NGB_OK;
+  GatherGeo g;
+  g.N = N; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.mode = mode;
+  g.Op8 = (O + 7) & ~7;
+  int srows;
+  if (mode == 0) {
+    if (O < 4 || O > 32) return NGB_OK;                   // one channel tile is 8 wide: below 4 the CUDA-core kernels win
+    g.Cin = C; g.Cout = O;
+    g.raw_rows = H; g.raw_cols = W; g.transpose = 0;
+    g.halo_r = pad; g.halo_c = pad;
+    srows = H + 2 * pad;
+    g.spitch = round_up_mod(W + 2 * pad, 8, 4);
+    g.splane = srows * g.spitch;
+    g.F = Ho * Wo; g.fdiv = Ho; g.a_mod = stride * g.spitch; g.a_div = stride;
+    g.K = C * KH * KW;
+  } else {
+    if (stride != 1 || pad > KH - 1 || pad > KW - 1) return NGB_OK;
+    if (C < 4 || C > 32) return NGB_OK;
+    g.Cin = O; g.Cout = C;
+    g.raw_rows = Wo; g.raw_cols = Ho; g.transpose = 1;   // raw ug plane is [q][p]
+    g.halo_r = KH - 1 - pad; g.halo_c = KW - 1 - pad;
+    srows = Ho + 2 * g.halo_r;
+    g.spitch = round_up_mod(Wo + 2 * g.halo_c, 8, 4);
+    g.splane = round_up_mod(srows * g.spitch, 32, 8);    // lanes t walk the planes: 8 banks apart
+    g.F = H * W; g.fdiv = W; g.a_mod = 1; g.a_div = g.spitch;
+    g.K = KH * KW * g.Op8;
+  }
+  g.raw_plane = g.raw_rows * g.raw_cols;
+  g.Kp = (g.K + 7) & ~7;
+  g.NP = (g.Cout + 7) & ~7;
+  g.NPp = g.NP + 4;
+  g.MTI = ceil_div(g.F, 16);
+  g.F16 = g.MTI * 16;
+  g.img_stride = g.Cin * g.splane;   // splane is a multiple of 4
+  const int NT = g.NP / 8;
+  if (NT != 1 && NT != 2 && NT != 4) return NGB_OK;
+  const size_t fixed = ((size_t)g.Kp * g.NPp + g.Kp + g.F16) * 4;
+  const size_t per_img = (size_t)g.img_stride * 4;
+  const size_t budget = 72 * 1024;
+  if (fixed + per_img > 96 * 1024 || g.Kp > 4096) return NGB_OK;
+  int G = 8;
+  while (G > 1 && fixed + G * per_img > budget) --G;
+  if (G > N) G = N;
+  g.G = G;
+  const size_t smem = fixed + (size_t)G * per_img;
+  // warps x m-tiles per warp: cover the G*MTI tiles of a pass with as little idle tail as possible
+  const int MTmax = NT == 4 ? 2 : 4;
+  const int units = G * g.MTI;
+  int best_mt = 2, best_nw = 8;
+  double best_eff = -1.0;
+  for (int mt = MTmax; mt >= 2; mt >>= 1) {
+    const int cand[] = {8, 9, 10, 12, 7, 6, 11};
+    for (int nw : cand) {
+      const int rounds = ceil_div(units, nw * mt);
+      const double eff = (double)units / ((double)rounds * nw * mt);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best_mt = mt; best_nw = nw; }
+    }
+  }
+  int rc = ensure_init();
+  if (rc) return rc;
+#define NGB_GATHER(MT_, NT_) rc = launch_gather<MT_, NT_>(in, w, bias, out, g, accumulate, best_nw, smem, st)
+  if (NT == 1) { if (best_mt == 4) NGB_GATHER(4, 1); else NGB_GATHER(2, 1); }
+  else if (NT == 2) { if (best_mt == 4) NGB_GATHER(4, 2); else NGB_GATHER(2, 2); }
+  else NGB_GATHER(2, 4);
+#undef NGB_GATHER
+  if (rc) return rc;
+  *done = true;
+  return NGB_OK;
+}
+
+// ------------------------------------------------------------------------------------------------ wgrad
+// dw[o][m] = sum_n sum_f ug[n][o][f] * xs[n][moff[m] + poff[f]],   m = (c,kh,kw) (dw's own inner layout), f = q*Ho + p.
+// GEMM view: D[m][o], reduction over the output positions of every image.  The 8 positions of a k-step are consecutive
+// f; lane label t stands for position f0+2t and label t+4 for f0+2t+1, so the ug fragment is ONE 64-bit load and the
+// x fragment rows sit 2 staged rows (= 8 banks mod 32) apart.  Warps = MS row splits x KS position splits; partial
+// tiles are summed across KS in a fixed order, per-CTA partials by the deterministic second pass.
+struct WgradGeo {
+  int N, C, O, KH, KW, Ho;
+  int raw_rows, raw_cols, raw_plane, halo;   // x plane
+  int spitch, splane, ximg;                  // staged x
+  int F, F8, KSI, Up, NP, uimg;              // staged ug: [NP][Up] per image, zero tail
+  int CKK, Mrows;                            // filter elements per output channel; rows covered by the warps (MS*MTW*16)
+  int a_mod, a_div;                          // poff(f) = (f % Ho) * a_mod + (f / Ho) * a_div
+  int MS, KS, G;
+};
+
+template <int MTW, int NT>
+__global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __restrict__ ug, const float* __restrict__ x,
+                                                             float* __restrict__ part, WgradGeo g, FastDiv d_plane,
+                                                             FastDiv d_cols, FastDiv d_ho, FastDiv d_ksi, FastDiv d_kk,
+                                                             FastDiv d_kw, FastDiv d_f, FastDiv d_ckk) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  int* moff = reinterpret_cast<int*>(smem_u);          // [Mrows]
+  int* poff = moff + g.Mrows;                          // [F8]
+  uint32_t* xs = reinterpret_cast<uint32_t*>(poff + g.F8);   // [G][ximg]
+  uint32_t* us = xs + g.G * g.ximg;                    // [G][uimg]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int ms = warp % g.MS, kq = warp / g.MS;
+
+  for (int m = tid; m < g.Mrows; m += nthr) {
+    int off = 0;
+    if (m < g.CKK) {
+      uint32_t c, tap, kh, kw;
+      d_kk.divmod((uint32_t)m, c, tap);
+      d_kw.divmod(tap, kh, kw);
+      off = (int)c * g.splane + (int)kh * g.spitch + (int)kw;
+    }
+    moff[m] = off;
+  }
+  for (int f = tid; f < g.F8; f += nthr) {
+    int off = 0;
+    if (f < g.F) {
+      uint32_t q, p;
+      d_ho.divmod((uint32_t)f, q, p);
+      off = (int)p * g.a_mod + (int)q * g.a_div;
+    }
+    poff[f] = off;
+  }
+  // zero once: x halo, ug tails (f >= F) and padded channels (o >= O) are never rewritten by the staging below
+  for (int e = tid; e < g.G * (g.ximg + g.uimg); e += nthr) xs[e] = 0u;
+
+  float acc[MTW][NT][4];
+#pragma unroll
+  for (int i = 0; i < MTW; ++i)
+#pragma unroll
+    for (int j = 0; j < NT; ++j)
+#pragma unroll
+      for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
+
+  __syncthreads();
+  int M0[MTW], M1[MTW];
+#pragma unroll
+  for (int i = 0; i < MTW; ++i) {
+    M0[i] = moff[(ms * MTW + i) * 16 + gq];
+    M1[i] = moff[(ms * MTW + i) * 16 + gq + 8];
+  }
+
+  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
+  const int xraw_img = g.C * g.raw_plane, uraw_img = g.O * g.F;
+  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
+    const int n0 = (int)(pass * g.G);
+    const int ng = min(g.G, g.N - n0);
+    __syncthreads();
+    {  // ---- x: natural layout + halo
+      const float* src = x + (int64_t)n0 * xraw_img;
+      const int raw = ng * xraw_img;
+      const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+      const int raw4 = vec ? (raw >> 2) : 0;
+#pragma unroll 2
+      for (int e4 = tid; e4 < raw4; e4 += nthr) {
+        const float4 v = ld_stream4(src + 4 * (int64_t)e4);
+        uint32_t pl, f, r, c;
+        d_plane.divmod((uint32_t)e4 * 4u, pl, f);
+        d_cols.divmod(f, r, c);
+        const float vv[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          xs[pl * g.splane + (r + g.halo) * g.spitch + c + g.halo] = to_tf32(vv[j]);
+          if (++c == (uint32_t)g.raw_cols) {
+            c = 0;
+            if (++r == (uint32_t)g.raw_rows) { r = 0; ++pl; }
+          }
+        }
+      }
+      for (int e = raw4 * 4 + tid; e < raw; e += nthr) {
+        uint32_t pl, f, r, c;
+        d_plane.divmod((uint32_t)e, pl, f);
+        d_cols.divmod(f, r, c);
+        xs[pl * g.splane + (r + g.halo) * g.spitch + c + g.halo] = to_tf32(__ldg(src + e));
+      }
+    }
+    {  // ---- ug: [o][f] as stored (neograd order), plane pitch Up
+      const float* src = ug + (int64_t)n0 * uraw_img;
+      const int raw = ng * uraw_img;
+      const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (g.F % 4 == 0);
+      if (vec) {
+#pragma unroll 2
+        for (int e4 = tid; e4 < (raw >> 2); e4 += nthr) {
+          const float4 v = ld_stream4(src + 4 * (int64_t)e4);
+          uint32_t pl, f;
+          d_f.divmod((uint32_t)e4 * 4u, pl, f);      // pl = img*O + o
+          uint32_t img, o;
+          // O is small: one more divide by O via the plane count
+          img = pl / (uint32_t)g.O; o = pl - img * (uint32_t)g.O;
+          uint4 tv = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+          *reinterpret_cast<uint4*>(us + img * g.uimg + o * g.Up + f) = tv;
+        }
+      } else {
+        for (int e = tid; e < raw; e += nthr) {
+          uint32_t pl, f;
+          d_f.divmod((uint32_t)e, pl, f);
+          const uint32_t img = pl / (uint32_t)g.O, o = pl - img * (uint32_t)g.O;
+          us[img * g.uimg + o * g.Up + f] = to_tf32(__ldg(src + e));
+        }
+      }
+    }
+    __syncthreads();
+
+    const int units = ng * g.KSI;
+    for (int u = kq; u < units; u += g.KS) {
+      uint32_t img, ks;
+      d_ksi.divmod((uint32_t)u, img, ks);
+      const int f0 = (int)ks * 8;
+      const int2 pp = *reinterpret_cast<const int2*>(poff + f0 + 2 * t);
+      const uint32_t* xb = xs + img * g.ximg;
+      const uint32_t* ub = us + img * g.uimg + f0 + 2 * t;
+      uint2 b[NT];
+#pragma unroll
+      for (int j = 0; j < NT; ++j) b[j] = *reinterpret_cast<const uint2*>(ub + (j * 8 + gq) * g.Up);
+#pragma unroll
+      for (int i = 0; i < MTW; ++i) {
+        const uint32_t a0 = xb[M0[i] + pp.x], a1 = xb[M1[i] + pp.x], a2 = xb[M0[i] + pp.y], a3 = xb[M1[i] + pp.y];
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, b[j].x, b[j].y);
+      }
+    }
+  }
+
+  // ---- reduce the KS position splits in a fixed order, then emit this CTA's partial in dw's layout
+  __syncthreads();
+  float* red = reinterpret_cast<float*>(xs);          // [Mrows][NT*8]
+  constexpr int NR = NT * 8;
+  for (int r = 0; r < g.KS; ++r) {
+    if (kq == r) {
+#pragma unroll
+      for (int i = 0; i < MTW; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j)
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int m = (ms * MTW + i) * 16 + gq + ((e & 2) ? 8 : 0);
+            const int n = j * 8 + 2 * t + (e & 1);
+            float* p = red + m * NR + n;
+            *p = (r == 0) ? acc[i][j][e] : *p + acc[i][j][e];
+          }
+    }
+    __syncthreads();
+  }
+  const int nw = g.O * g.CKK;
+  for (int e = tid; e < nw; e += nthr) {
+    uint32_t o, m;
+    d_ckk.divmod((uint32_t)e, o, m);
+    part[(int64_t)blockIdx.x * nw + e] = red[m * NR + o];
+  }
+}
+
+template <int MTW, int NT>
+static int launch_wgrad(const float* ug, const float* x, float* part, const WgradGeo& g, int nwarps, size_t smem, int* grid_out,
+                        cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  int occ = 1;
+  NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_wgrad_mma_kernel<MTW, NT>, nwarps * 32, smem));
+  if (occ < 1) occ = 1;
+  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
+  const int64_t nwts = (int64_t)g.O * g.CKK;
+  int64_t grid = passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ;
+  if (grid * nwts * 4 > scratch_bytes()) grid = scratch_bytes() / (nwts * 4);
+  if (grid < 1) return fail(NGB_ERR_SCRATCH, "conv wgrad: scratch arena too small for %lld filter elements", (long long)nwts);
+  *grid_out = (int)grid;
+  conv_wgrad_mma_kernel<MTW, NT><<<(unsigned)grid, nwarps * 32, smem, st>>>(
+      ug, x, part, g, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.Ho),
+      FastDiv((uint32_t)g.KSI), FastDiv((uint32_t)(g.KH * g.KW)), FastDiv((uint32_t)g.KW), FastDiv((uint32_t)g.F),
+      FastDiv((uint32_t)g.CKK));
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int H, int W, int O, int KH, int KW, int pad,
+                   int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done) {
+  *done = false;
+  if (g_default_engine.load() == NGB_GEMM_SIMT) return NGB_OK;
+  if (O < 4 || O > 16) return NGB_OK;
+  WgradGeo g;
+  g.N = N; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.Ho = Ho;
+  g.raw_rows = H; g.raw_cols = W; g.raw_plane = H * W; g.halo = pad;
+  g.spitch = round_up_mod(W + 2 * pad, 8, 4);
+  g.splane = (H + 2 * pad) * g.spitch;
+  g.ximg = C * g.splane;               // multiple of 4 (spitch is)
+  g.F = Ho * Wo; g.F8 = (g.F + 7) & ~7; g.KSI = g.F8 / 8;
+  g.Up = round_up_mod(g.F8, 32, 8);
+  g.NP = (O + 7) & ~7;
+  g.uimg = g.NP * g.Up;
+  g.CKK = C * KH * KW;
+  g.a_mod = stride * g.spitch; g.a_div = stride;
+  const int NT = g.NP / 8;
+  const int mt_total = ceil_div(g.CKK, 16);
+  g.MS = ceil_div(mt_total, 5);
+  if (g.MS > 8) return NGB_OK;
+  const int MTW = ceil_div(mt_total, g.MS);
+  g.Mrows = g.MS * MTW * 16;
+  g.KS = 8 / g.MS; if (g.KS < 1) g.KS = 1;
+  const int nwarps = g.MS * g.KS;
+  const size_t fixed = ((size_t)g.Mrows + g.F8) * 4;
+  const size_t per_img = ((size_t)g.ximg + g.uimg) * 4;
+  const size_t red_bytes = (size_t)g.Mrows * NT * 8 * 4;
+  if (fixed + per_img > 96 * 1024) return NGB_OK;
+  int G = 8;
+  while (G > 1 && fixed + G * per_img > 48 * 1024) --G;
+  if (G > N) G = N;
+  if ((size_t)G * per_img < red_bytes) return NGB_OK;       // the reduction tile reuses the staging area
+  g.G = G;
+  const size_t smem = fixed + (size_t)G * per_img;
+  int rc = ensure_init();
+  if (rc) return rc;
+  const int64_t nw = (int64_t)O * g.CKK;
+  if (nw * 4 * kNumSMs * 4 > scratch_bytes()) return NGB_OK;
+  int grid = 0;
+  float* part = scratch_ptr();
+#define NGB_WGRAD(M_, N_) rc = launch_wgrad<M_, N_>(ug, x, part, g, nwarps, smem, &grid, st)
+  if (NT == 1) {
+    switch (MTW) { case 1: NGB_WGRAD(1, 1); break; case 2: NGB_WGRAD(2, 1); break; case 3: NGB_WGRAD(3, 1); break;
+                   case 4: NGB_WGRAD(4, 1); break; default: NGB_WGRAD(5, 1); break; }
+  } else {
+    switch (MTW) { case 1: NGB_WGRAD(1, 2); break; case 2: NGB_WGRAD(2, 2); break; case 3: NGB_WGRAD(3, 2); break;
+                   case 4: NGB_WGRAD(4, 2); break; default: NGB_WGRAD(5, 2); break; }
+  }
+#undef NGB_WGRAD
+  if (rc) return rc;
+  *done = true;
+  return launch_sum_partials(part, grid, nw, dw, accumulate, st);
+}
+
+}  // namespace ngb

@@ -289,39 +289,42 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __rest
     }
     __syncthreads();
     // each thread owns a 2-row x 4-column block of dx = two complete windows: one smem lookup, two 128-bit stores
-    const int per_plane = tp * g.w4;
-    for (int gi = 0; gi < ng; ++gi) {
+    const int total_w = ng * g.TP * g.w4;
 #pragma unroll 2
-      for (int e = threadIdx.x; e < per_plane; e += 256) {
-        uint32_t lp, c4;
-        g.d_w4.divmod(e, lp, c4);
-        const int q = 2 * (int)c4;
-        const int s0 = (gi * g.Wo + q) * TPp + (int)lp;
-        float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
-        if (q < g.Wo) {
-          const float gv = sg[s0];
-          const int a = si[s0];
-          r0.x = a == 0 ? gv : 0.f; r0.y = a == 1 ? gv : 0.f; r1.x = a == 2 ? gv : 0.f; r1.y = a == 3 ? gv : 0.f;
-        }
-        if (q + 1 < g.Wo) {
-          const float gv = sg[s0 + TPp];
-          const int a = si[s0 + TPp];
-          r0.z = a == 0 ? gv : 0.f; r0.w = a == 1 ? gv : 0.f; r1.z = a == 2 ? gv : 0.f; r1.w = a == 3 ? gv : 0.f;
-        }
-        float* d0 = dx + ((o0 + gi) * g.H + 2 * (p0 + (int)lp)) * (int64_t)g.W + 4 * c4;
-        float* d1 = d0 + g.W;
-        if (accumulate) {
-          const float4 o0v = *reinterpret_cast<const float4*>(d0), o1v = *reinterpret_cast<const float4*>(d1);
-          r0.x += o0v.x; r0.y += o0v.y; r0.z += o0v.z; r0.w += o0v.w;
-          r1.x += o1v.x; r1.y += o1v.y; r1.z += o1v.z; r1.w += o1v.w;
-        }
-        st_stream4(d0, r0);
-        st_stream4(d1, r1);
+    for (int e = threadIdx.x; e < total_w; e += 256) {
+      uint32_t rest, c4, gi, lp;
+      g.d_w4.divmod(e, rest, c4);
+      g.d_tp.divmod(rest, gi, lp);
+      if ((int)lp >= tp) continue;
+      const int q = 2 * (int)c4;
+      const int s0 = ((int)gi * g.Wo + q) * TPp + (int)lp;
+      float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0;
+      if (q < g.Wo) {
+        const float gv = sg[s0];
+        const int a = si[s0];
+        r0.x = a == 0 ? gv : 0.f; r0.y = a == 1 ? gv : 0.f; r1.x = a == 2 ? gv : 0.f; r1.y = a == 3 ? gv : 0.f;
       }
-      // an odd H leaves one row no window covers: it receives zero gradient (the last strip owns it)
-      if ((g.H & 1) && strip == g.strips - 1 && !accumulate) {
-        for (int e = threadIdx.x; e < g.w4; e += 256)
-          st_stream4(dx + ((o0 + gi) * g.H + g.H - 1) * (int64_t)g.W + 4 * e, make_float4(0.f, 0.f, 0.f, 0.f));
+      if (q + 1 < g.Wo) {
+        const float gv = sg[s0 + TPp];
+        const int a = si[s0 + TPp];
+        r0.z = a == 0 ? gv : 0.f; r0.w = a == 1 ? gv : 0.f; r1.z = a == 2 ? gv : 0.f; r1.w = a == 3 ? gv : 0.f;
+      }
+      float* d0 = dx + ((o0 + gi) * g.H + 2 * (p0 + (int)lp)) * (int64_t)g.W + 4 * c4;
+      float* d1 = d0 + g.W;
+      if (accumulate) {
+        const float4 o0v = *reinterpret_cast<const float4*>(d0), o1v = *reinterpret_cast<const float4*>(d1);
+        r0.x += o0v.x; r0.y += o0v.y; r0.z += o0v.z; r0.w += o0v.w;
+        r1.x += o1v.x; r1.y += o1v.y; r1.z += o1v.z; r1.w += o1v.w;
+      }
+      st_stream4(d0, r0);
+      st_stream4(d1, r1);
+    }
+    // an odd H leaves one row no window covers: it receives zero gradient (the last strip owns it)
+    if ((g.H & 1) && strip == g.strips - 1 && !accumulate) {
+      for (int e = threadIdx.x; e < ng * g.w4; e += 256) {
+        uint32_t gi, c4;
+        g.d_w4.divmod(e, gi, c4);
+        st_stream4(dx + ((o0 + gi) * g.H + g.H - 1) * (int64_t)g.W + 4 * c4, make_float4(0.f, 0.f, 0.f, 0.f));
       }
     }
   }

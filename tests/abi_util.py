@@ -33,6 +33,19 @@ def call(name, *args):
   B.check(getattr(lib, name)(*args))
 
 
+class precision:
+  """with precision('fp32'): ... -- exact-fp32 CUDA-core kernels (ngb_set_default_engine, include/ngb200.h); 'tf32' = default."""
+
+  def __init__(self, mode):
+    self.engine = {'tf32': B.GEMM_AUTO, 'fp32': B.GEMM_SIMT}[mode]
+
+  def __enter__(self):
+    self.prev = lib.ngb_set_default_engine(self.engine)
+
+  def __exit__(self, *exc):
+    lib.ngb_set_default_engine(self.prev)
+
+
 def empty(*shape):
   return torch.empty(shape, device='cuda', dtype=torch.float32)
 

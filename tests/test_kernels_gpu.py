@@ -197,12 +197,17 @@ def test_conv3d_golden(U, name):
   g = load_golden(name)
   p, s = int(g['pad']), int(g['stride'])
   x, w, b, ug = f32(g['x']), f32(g['w']), f32(g['b']), f32(g['ug'])
-  close(U.conv_fprop(x, w, b, p, s), ops.conv3d_fwd(x, w, b, p, s), TOL32)
-  close(U.conv_dgrad(ug, w, x.shape, p, s), ops.conv3d_dgrad(ug, w, x.shape, p, s), TOL32)
-  close(U.conv_wgrad(ug, x, w.shape, p, s), ops.conv3d_wgrad(ug, x, w.shape, p, s), TOL32)
-  close(U.conv_bgrad(ug), ops.conv3d_bgrad(ug), TOL32)
-  close(U.conv_fprop(x, w, b, p, s), g['out'], 1e-5)
-  close(U.conv_wgrad(ug, x, w.shape, p, s), g['gw'], 1e-5)
+  with U.precision('fp32'):
+    close(U.conv_fprop(x, w, b, p, s), ops.conv3d_fwd(x, w, b, p, s), TOL32)
+    close(U.conv_dgrad(ug, w, x.shape, p, s), ops.conv3d_dgrad(ug, w, x.shape, p, s), TOL32)
+    close(U.conv_wgrad(ug, x, w.shape, p, s), ops.conv3d_wgrad(ug, x, w.shape, p, s), TOL32)
+    close(U.conv_bgrad(ug), ops.conv3d_bgrad(ug), TOL32)
+    close(U.conv_fprop(x, w, b, p, s), g['out'], 1e-5)
+    close(U.conv_wgrad(ug, x, w.shape, p, s), g['gw'], 1e-5)
+  # default precision: 2 -> 5 channels goes to the TF32 mma.sync kernels
+  close(U.conv_fprop(x, w, b, p, s), g['out'], TOLTF32)
+  close(U.conv_dgrad(ug, w, x.shape, p, s), ops.conv3d_dgrad(ug, w, x.shape, p, s), TOLTF32)
+  close(U.conv_wgrad(ug, x, w.shape, p, s), g['gw'], TOLTF32)
 
 
 @pytest.mark.parametrize('name', golden_names('conv2d_'))
@@ -231,18 +236,62 @@ CONV_CASES = [   # N, C, H, W, O, KH, KW, pad, stride
 ]
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])
 @pytest.mark.parametrize('N,C,H,W,O,KH,KW,pad,stride', CONV_CASES)
-def test_conv_direct(U, N, C, H, W, O, KH, KW, pad, stride):
+def test_conv_direct(U, N, C, H, W, O, KH, KW, pad, stride, precision):
+  """fp32 mode: the CUDA-core kernels (exact fp32).  tf32 mode: whatever the dispatcher picks for the geometry (the
+  small-channel mma.sync kernels for LeNet-B, CUDA cores for single-channel layers, tcgen05 for 32-multiples)."""
   rng = np.random.default_rng(N + C * 3 + H * 5 + O * 7 + KH)
   x = f32(rng.standard_normal((N, C, H, W)))
   w = f32(rng.standard_normal((O, C, KH, KW)) / np.sqrt(C * KH * KW))
   b = f32(rng.standard_normal(O))
   y = ops.conv3d_fwd(x, w, b, pad, stride)
   ug = f32(rng.standard_normal(y.shape))
-  close(U.conv_fprop(x, w, b, pad, stride), y, TOL32)
-  close(U.conv_dgrad(ug, w, x.shape, pad, stride), ops.conv3d_dgrad(ug, w, x.shape, pad, stride), TOL32)
-  close(U.conv_wgrad(ug, x, w.shape, pad, stride), ops.conv3d_wgrad(ug, x, w.shape, pad, stride), 2 * TOL32)
-  close(U.conv_bgrad(ug), ops.conv3d_bgrad(ug), 2 * TOL32)
+  tol = TOL32 if precision == 'fp32' else TOLTF32
+  with U.precision(precision):
+    close(U.conv_fprop(x, w, b, pad, stride), y, tol)
+    close(U.conv_dgrad(ug, w, x.shape, pad, stride), ops.conv3d_dgrad(ug, w, x.shape, pad, stride), tol)
+    close(U.conv_wgrad(ug, x, w.shape, pad, stride), ops.conv3d_wgrad(ug, x, w.shape, pad, stride), 2 * tol)
+    close(U.conv_bgrad(ug), ops.conv3d_bgrad(ug), 2 * tol)
+
+
+SMALL_MMA_CASES = [   # N, C, H, W, O, KH, KW, pad, stride: small-channel layers on the mma.sync TF32 kernels (conv_small_mma.cu)
+  (4096, 6, 12, 12, 16, 5, 5, 0, 1),   # LeNet-B conv2 at the bench's batch
+  (512, 1, 28, 28, 6, 5, 5, 0, 1),     # LeNet-B conv1
+  (37, 3, 11, 14, 5, 3, 3, 1, 1),      # ragged everything: batch not a multiple of the images per pass, F % 16 != 0, padding
+  (9, 5, 13, 9, 12, 2, 3, 1, 2),       # rectangular filter, stride 2 (fprop / wgrad on tensor cores, dgrad on CUDA cores)
+  (5, 8, 10, 10, 8, 3, 3, 2, 1),       # "full" padding = K-1: no halo in the data gradient
+  (3, 4, 16, 16, 32, 3, 3, 1, 1),      # O = 32: four channel tiles
+  (130, 16, 8, 8, 4, 3, 3, 0, 1),      # C = 16: two channel tiles in the data gradient, 9 filter m-tiles in wgrad
+]
+
+
+@pytest.mark.parametrize('N,C,H,W,O,KH,KW,pad,stride', SMALL_MMA_CASES)
+def test_conv_small_mma(U, N, C, H, W, O, KH, KW, pad, stride):
+  rng = np.random.default_rng(N * 5 + C * 3 + H + O * 7 + KH)
+  x = f32(rng.standard_normal((N, C, H, W)))
+  w = f32(rng.standard_normal((O, C, KH, KW)) / np.sqrt(C * KH * KW))
+  b = f32(rng.standard_normal(O))
+  y = ops.conv3d_fwd(x, w, b, pad, stride)
+  ug = f32(rng.standard_normal(y.shape))
+  close(U.conv_fprop(x, w, b, pad, stride), y, TOLTF32)
+  close(U.conv_dgrad(ug, w, x.shape, pad, stride), ops.conv3d_dgrad(ug, w, x.shape, pad, stride), TOLTF32)
+  close(U.conv_wgrad(ug, x, w.shape, pad, stride), ops.conv3d_wgrad(ug, x, w.shape, pad, stride), TOLTF32)
+
+
+@pytest.mark.parametrize('N,C,H,W,O,KH,KW,pad,stride', SMALL_MMA_CASES[2:])
+def test_conv_small_mma_exact_on_small_integers(U, N, C, H, W, O, KH, KW, pad, stride):
+  """TF32-representable inputs -> the mma.sync kernels must be bit-exact (any fragment / offset-table mix-up shows), incl.
+  accumulation into an existing gradient."""
+  rng = np.random.default_rng(7 + N)
+  x = rng.integers(-3, 4, (N, C, H, W)).astype(np.float64)
+  w = rng.integers(-2, 3, (O, C, KH, KW)).astype(np.float64)
+  b = rng.integers(-5, 6, O).astype(np.float64)
+  y = ops.conv3d_fwd(x, w, b, pad, stride)
+  ug = rng.integers(-3, 4, y.shape).astype(np.float64)
+  assert np.array_equal(U.conv_fprop(x, w, b, pad, stride), y.astype(np.float32))
+  assert np.array_equal(U.conv_dgrad(ug, w, x.shape, pad, stride), ops.conv3d_dgrad(ug, w, x.shape, pad, stride).astype(np.float32))
+  assert np.array_equal(U.conv_wgrad(ug, x, w.shape, pad, stride), ops.conv3d_wgrad(ug, x, w.shape, pad, stride).astype(np.float32))
 
 
 IGEMM_CASES = [   # N, C, H, W, O, KH, KW, pad  (stride 1, C % 32 == O % 32 == 0: tcgen05 implicit-GEMM path)
