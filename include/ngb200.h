@@ -59,6 +59,12 @@ int ngb_debug_check_pipelines(void);
 /* Pre-sizes the grow-on-demand workspace the tensor-core convolutions stage their channels-last operand copies in
  * (N*C*H*W*4 bytes of the largest staged tensor).  Only needed before CUDA-graph capture, where growing is not allowed. */
 int ngb_workspace_reserve(int64_t bytes);
+/* Lanes: the host may drive up to 4 streams concurrently (neograd_b200 runs the weight / bias gradients of
+ * Tensor.backward() -- tensor.py:93-100, whose results nothing downstream consumes -- beside the data-gradient chain).
+ * Kernels of different lanes can overlap on the GPU, so each lane owns its scratch arena and conv workspace.
+ * ngb_set_lane selects the lane of the CALLING THREAD's subsequent launches and returns the previous one (-1 on error);
+ * the first selection of a lane allocates its arena, so select every lane once before a CUDA-graph capture. */
+int ngb_set_lane(int lane);
 /* Process-wide precision mode: what NGB_GEMM_AUTO (and the conv dispatcher) resolve to.  NGB_GEMM_AUTO (default) = TF32
  * tensor cores whenever the shape qualifies; NGB_GEMM_SIMT = exact-fp32 CUDA-core kernels everywhere (parity runs,
  * grad_check); NGB_GEMM_TCGEN05 is not a valid default.  Returns the previous value. */

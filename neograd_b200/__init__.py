@@ -18,4 +18,4 @@ from .autograd import add, sub, mul, div, pow, exp, log, dot, sum, transpose, fl
 from .autograd.utils import grad_check, fn_grad_check  # noqa: E402
 from .nn.utils import load_model as load, save_model as save  # noqa: E402
 from .device import DeviceArray, synchronize  # noqa: E402
-from ._backend import set_precision  # noqa: E402
+from ._backend import set_precision, set_backward_lanes  # noqa: E402

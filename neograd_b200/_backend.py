@@ -53,6 +53,7 @@ SIGNATURES = {
   'ngb_debug_check_pipelines': ([], c_int),
   'ngb_workspace_reserve': ([c_int64], c_int),
   'ngb_set_default_engine': ([c_int], c_int),
+  'ngb_set_lane': ([c_int], c_int),
   'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
   'ngb_launch_count': ([], c_int64),
   'ngb_gemm': ([c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _S], c_int),
@@ -127,6 +128,97 @@ def stream():
   return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
 
 
+class _Lanes:
+  """Side streams for the leaf gradients of Tensor.backward() (tensor.py:93-100 of the reference).
+
+  The gradient of a graph LEAF (a Param: weight / bias gradient) is consumed by nothing else in the backward pass, so
+  its kernels need not sit on the data-gradient chain.  `run` issues them on one of `n` side streams (after the
+  upstream gradient is complete on the main stream), `join` makes the main stream wait for them at the end of
+  backward().  Under CUDA-graph capture the fork/join becomes parallel branches of the graph.  Each side stream is a
+  library lane (ngb_set_lane: private scratch arena).  Buffers the side kernels read are kept referenced until the
+  join, so the stream-ordered allocator cannot hand them to a later main-stream allocation."""
+
+  def __init__(self):
+    self.n = 2
+    self.streams = None
+    self.used = set()
+    self.keep = []
+    self.assign = {}
+    self.rr = 0
+
+  def active(self):
+    return self.n > 0
+
+  def _init(self):
+    import torch
+    ensure_runtime()
+    self.streams = {}
+    for lane in range(1, self.n + 1):
+      self.streams[lane] = torch.cuda.Stream()
+      prev = lib.ngb_set_lane(lane)          # allocates the lane's arena now (not inside a later capture)
+      if prev < 0:
+        raise NgbError(lib.ngb_last_error().decode('utf-8', 'replace'))
+      lib.ngb_set_lane(prev)
+
+  def mark_ready(self):
+    """Event on the current (main) stream: everything issued so far -- in particular the gradient of the tensor the
+    engine has just finished -- is complete.  Side-lane work that consumes that gradient waits on THIS event, not on the
+    main stream's tail at the time it is issued (leaves are visited last, long after their upstream gradient exists)."""
+    import torch
+    ev = torch.cuda.Event()
+    ev.record()
+    return ev
+
+  def run(self, key, fn, keep, ready=None):
+    import torch
+    if self.streams is None or len(self.streams) != self.n:
+      self._init()
+    lane = self.assign.get(id(key))
+    if lane is None:                         # all accumulations into one tensor stay on one stream (ordered)
+      lane = 1 + self.rr % self.n
+      self.rr += 1
+      self.assign[id(key)] = lane
+    side = self.streams[lane]
+    if ready is not None:
+      side.wait_event(ready)
+    else:
+      side.wait_stream(torch.cuda.current_stream())
+    prev = lib.ngb_set_lane(lane)
+    try:
+      with torch.cuda.stream(side):
+        fn()
+    finally:
+      lib.ngb_set_lane(prev)
+    self.used.add(lane)
+    self.keep.append(keep)
+
+  def join(self):
+    if not self.used:
+      return
+    import torch
+    main = torch.cuda.current_stream()
+    for lane in sorted(self.used):
+      main.wait_stream(self.streams[lane])
+    self.used.clear()
+    self.keep.clear()
+    self.assign.clear()
+    self.rr = 0
+
+
+lanes = _Lanes()
+
+
+def set_backward_lanes(n):
+  """Number of side streams Tensor.backward() may use for weight / bias gradients (0 = everything on one stream, the
+  reference's order of execution; default 2).  Returns the previous setting."""
+  n = int(n)
+  if not 0 <= n <= 3:
+    raise ValueError('set_backward_lanes: n must be 0..3')
+  lanes.join()
+  prev, lanes.n = lanes.n, n
+  return prev
+
+
 def set_precision(mode):
   """'tf32' (default): Dot / multi-channel conv run on the tcgen05 tensor cores when the shape qualifies;
   'fp32': exact-fp32 CUDA-core kernels everywhere (parity runs, grad_check).  Returns the previous mode."""
@@ -139,7 +231,7 @@ class profile_calls:
   `records` is a list of (name, args, start_event, end_event); call `summary()` after the block (it synchronises).
   Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
   SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
-          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines')
+          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane')
 
   def __enter__(self):
     import torch

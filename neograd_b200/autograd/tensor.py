@@ -12,6 +12,7 @@
 """
 import numpy as np
 
+from .._backend import lanes as _lanes
 from ..device import DeviceArray
 from .utils import process_data, unbroadcast_data
 
@@ -131,34 +132,70 @@ class Tensor:
         raise ValueError("Shapes of grad and Tensor data must match!")
     self.accumulate_grad(upper_grad)
     node = graph.get_node(self)
-    node.backward(retain_graph)
+    try:
+      node.backward(retain_graph)
+    finally:
+      from .._backend import lanes
+      lanes.join()               # weight / bias gradients issued on side streams are complete for whatever follows
     if not retain_graph:
       graph.reset_graph()
 
   def _backward(self, node, retain_graph, calculate_grads=True):
     """tensor.py:75-104.  For every child (an op that consumed this tensor): install the grad_fns, run this operand's
-    grad_fn on the child's gradient, unbroadcast, reshape, accumulate."""
+    grad_fn on the child's gradient, unbroadcast, reshape, accumulate.
+
+    Backward lanes (new): once this tensor's own gradient is final, the gradients of the LEAF operands of the op that
+    produced it (weights, biases) are issued right away on side streams -- nothing else in the pass consumes them, so
+    they run beside the data-gradient chain instead of after it.  The leaf's own visit then finds that contribution
+    already accumulated."""
     from .utils import get_graph
     graph = get_graph()
     for child in node.children:
       if self.requires_grad and calculate_grads:
-        child.backward_fn(*[n.tens for n in child.parents])
-        ct = child.tens
-        upper_grad = ct._grad if ct._grad_live else DeviceArray.zeros(ct.shape)
-        gf = self.grad_fn
-        if isinstance(gf, GradFn):
-          self._ensure_grad_buffer()
-          gf.into(upper_grad, self._grad, self._grad_live)
-          self._grad_live = True
+        if child.lane_done is not None and id(self) in child.lane_done:
+          child.lane_done.discard(id(self))          # accumulated when the child's gradient became final
         else:
-          grad = gf(upper_grad)
-          grad = unbroadcast_data(grad, self.shape, child.parent_broadcast_shape)
-          grad = process_data(grad) if not isinstance(grad, DeviceArray) else grad
-          self.accumulate_grad(grad.reshape(self.shape))
+          child.backward_fn(*[n.tens for n in child.parents])
+          ct = child.tens
+          upper_grad = ct._grad if ct._grad_live else DeviceArray.zeros(ct.shape)
+          gf = self.grad_fn
+          if isinstance(gf, GradFn):
+            self._ensure_grad_buffer()
+            gf.into(upper_grad, self._grad, self._grad_live)
+            self._grad_live = True
+          else:
+            grad = gf(upper_grad)
+            grad = unbroadcast_data(grad, self.shape, child.parent_broadcast_shape)
+            grad = process_data(grad) if not isinstance(grad, DeviceArray) else grad
+            self.accumulate_grad(grad.reshape(self.shape))
       if not retain_graph and child.are_parents_visited():
         graph.remove_tensor(child.tens)
+    if node.parents and self.requires_grad and _lanes.active():
+      self._issue_leaf_grads(node)
     if not retain_graph and node.are_parents_visited():
       graph.remove_tensor(node.tens)
+
+  def _issue_leaf_grads(self, node):
+    leaves = [p for p in node.parents if not p.parents and p.tens.requires_grad and p.tens is not self]
+    if not leaves:
+      return
+    node.backward_fn(*[n.tens for n in node.parents])
+    upper_grad = self._grad if self._grad_live else DeviceArray.zeros(self.shape)
+    ready = None
+    for p in leaves:
+      t = p.tens
+      gf = t.grad_fn
+      if not isinstance(gf, GradFn) or (node.lane_done is not None and id(t) in node.lane_done):
+        continue                                     # user-defined grad_fn: the reference's path at the leaf's own visit
+      if ready is None:
+        ready = _lanes.mark_ready()                  # main stream: this tensor's gradient is complete
+      t._ensure_grad_buffer()
+      dst, live = t._grad, t._grad_live
+      _lanes.run(t, lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live), (upper_grad, gf, node), ready)
+      t._grad_live = True
+      if node.lane_done is None:
+        node.lane_done = set()
+      node.lane_done.add(id(t))
 
   def _ensure_grad_buffer(self):
     if self._grad is None:

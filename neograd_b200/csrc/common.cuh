@@ -16,8 +16,10 @@ void set_error(const std::string& msg);
 int fail(int code, const char* fmt, ...);
 
 // Per-device scratch arena (split-K partials, reduction partials). Allocated by ngb_init().
-float* scratch_ptr();
+constexpr int kLanes = 4;     // concurrent host-driven streams with private scratch (ngb_set_lane)
+float* scratch_ptr();          // arena of the calling thread's current lane
 int64_t scratch_bytes();
+int current_lane();
 int ensure_init();
 
 extern std::atomic<int64_t> g_launches;

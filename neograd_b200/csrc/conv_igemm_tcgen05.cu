@@ -315,11 +315,13 @@ __global__ void __launch_bounds__(256) pack_weights_kernel(const float* __restri
 // than in the fixed scratch arena.  Growing allocates, so it must not happen inside a CUDA-graph capture: callers that
 // capture call ngb_workspace_reserve() first.
 std::mutex g_ws_mu;
-float* g_ws = nullptr;
-int64_t g_ws_bytes = 0;
+float* g_ws_lane[kLanes] = {nullptr, nullptr, nullptr, nullptr};   // one per lane (ngb_set_lane): lanes overlap on the GPU
+int64_t g_ws_bytes_lane[kLanes] = {0, 0, 0, 0};
 
 int workspace(int64_t bytes, float** out, cudaStream_t st) {
   std::lock_guard<std::mutex> lk(g_ws_mu);
+  float*& g_ws = g_ws_lane[current_lane()];
+  int64_t& g_ws_bytes = g_ws_bytes_lane[current_lane()];
   if (bytes > g_ws_bytes) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cs);

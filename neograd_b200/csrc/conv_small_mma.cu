@@ -23,12 +23,24 @@ __device__ __forceinline__ uint32_t to_tf32(float x) {
   return r;
 }
 
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ uint2 lds64(uint32_t addr) {
+  uint2 v;
+  asm volatile("ld.shared.v2.b32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(addr));
+  return v;
+}
+
 // D(16x8) += A(16x8, row) * B(8x8, col); lane = 4*g + t:
 //   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g);  d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1)
 // The k labels are only names: both operands use the same permutation of the reduction index.
 __device__ __forceinline__ void mma_tf32(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0,
                                          uint32_t b1) {
-  asm volatile(
+  asm(
       "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
       : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
       : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
@@ -49,6 +61,7 @@ struct GatherGeo {
   int K, Kp;                           // reduction length, padded to 8
   int NP, NPp;                         // Cout padded to 8; smem pitch of the packed weights (NP + 4)
   int mode;                            // 0 fprop, 1 dgrad
+  int contig;                          // staged images == raw images (no halo, pitch == row length)
   int C, O, KH, KW, Op8;
   int G;                               // images per pass
 };
@@ -100,7 +113,7 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
       d_kw.divmod(tap, kh, kw);
       if ((int)o < g.O) off = (int)o * g.splane + (g.KH - 1 - (int)kh) * g.spitch + (g.KW - 1 - (int)kw);
     }
-    kpair[(k >> 3) * 8 + (k & 3) * 2 + ((k >> 2) & 1)] = off;
+    kpair[(k >> 3) * 8 + (k & 3) * 2 + ((k >> 2) & 1)] = off * 4;   // byte offset
   }
   for (int f = tid; f < g.F16; f += nthr) {
     int off = 0;
@@ -109,11 +122,30 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
       d_fdiv.divmod((uint32_t)f, hi, lo);
       off = (int)lo * g.a_mod + (int)hi * g.a_div;
     }
-    aoff[f] = off;
+    aoff[f] = off * 4;   // byte offset
   }
   if (g.halo_r | g.halo_c) {
     for (int e = tid; e < g.G * g.img_stride; e += nthr) xs[e] = 0u;
   }
+
+  // per-thread constants of the fragment loads and of the epilogue
+  const uint32_t xs_sa = smem_u32(xs);
+  const uint32_t kp_sa = smem_u32(kpair) + t * 8;
+  const uint32_t wp_sa = smem_u32(wp) + (uint32_t)(t * g.NPp + gq) * 8u;
+  const uint32_t wstep = 32u * (uint32_t)g.NPp;          // one k-step of packed weights: 4 x NPp x 2 words
+  const bool full_tiles = (g.F16 == g.F);
+  int coff[NT][2];
+  bool cvalid[NT][2];
+  float bv[NT][2];
+#pragma unroll
+  for (int j = 0; j < NT; ++j)
+#pragma unroll
+    for (int b2 = 0; b2 < 2; ++b2) {
+      const int co = j * 8 + 2 * t + b2;
+      cvalid[j][b2] = co < g.Cout;
+      coff[j][b2] = co * g.F;
+      bv[j][b2] = (bias != nullptr && co < g.Cout) ? __ldg(bias + co) : 0.f;
+    }
 
   const int64_t passes = ceil_div<int64_t>(g.N, g.G);
   const int raw_img = g.Cin * g.raw_plane;
@@ -124,7 +156,17 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
     // ---- stage ng images, rounded to TF32
     const float* src = in + (int64_t)n0 * raw_img;
     const int raw = ng * raw_img;
-    if (g.transpose) {
+    if (g.contig) {
+      // no halo, pitch == row length: the staged images ARE the raw images -> straight 128-bit copy + TF32 rounding
+      const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+      const int raw4 = vec ? (raw >> 2) : 0;
+#pragma unroll 4
+      for (int e4 = tid; e4 < raw4; e4 += nthr) {
+        const float4 v = ld_stream4(src + 4 * (int64_t)e4);
+        *reinterpret_cast<uint4*>(xs + 4 * e4) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      }
+      for (int e = raw4 * 4 + tid; e < raw; e += nthr) xs[e] = to_tf32(__ldg(src + e));
+    } else if (g.transpose) {
       // consecutive lanes walk the raw contiguous axis = the staged ROW axis: pitch = 4 (mod 8) keeps the stores spread
 #pragma unroll 4
       for (int e = tid; e < raw; e += nthr) {
@@ -161,19 +203,27 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
     }
     __syncthreads();
 
-    // ---- compute: a warp owns MT m-tiles (16 consecutive outputs of one image each) x all NT channel tiles
+    // ---- compute: a warp owns MT m-tiles (16 consecutive outputs of one image each) x all NT channel tiles.
+    // All shared-memory operands are addressed by 32-bit BYTE addresses (tables hold byte offsets): one add per load.
     const int units = ng * g.MTI;
+    float* const obase = out + (int64_t)n0 * g.Cout * g.F;
     for (int u0 = warp * MT; u0 < units; u0 += nwarps * MT) {
-      int A0[MT], A1[MT], img_of[MT], f0_of[MT];
-#pragma unroll
-      for (int i = 0; i < MT; ++i) {
-        const int u = (u0 + i < units) ? u0 + i : u0;
+      uint32_t A0[MT], A1[MT];
+      int eo[MT], tile_f[MT];                   // element offset of (image, f0 + g) inside this pass's output block; f0
+      {
         uint32_t img, tile;
-        d_mti.divmod((uint32_t)u, img, tile);
-        img_of[i] = (int)img;
-        f0_of[i] = (int)tile * 16;
-        A0[i] = (int)img * g.img_stride + aoff[f0_of[i] + gq];
-        A1[i] = (int)img * g.img_stride + aoff[f0_of[i] + gq + 8];
+        d_mti.divmod((uint32_t)u0, img, tile);
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const int f0 = (int)tile * 16;
+          const uint32_t ib = xs_sa + (uint32_t)((int)img * g.img_stride) * 4u;
+          A0[i] = ib + (uint32_t)aoff[f0 + gq];
+          A1[i] = ib + (uint32_t)aoff[f0 + gq + 8];
+          eo[i] = (u0 + i < units) ? (int)img * g.Cout * g.F + f0 + gq : -1;
+          tile_f[i] = f0;
+          if (++tile == (uint32_t)g.MTI) { tile = 0; ++img; }
+          if (u0 + i + 1 >= units) { img = 0; tile = 0; }   // idle tail tiles recompute tile 0 (never stored)
+        }
       }
       float acc[MT][NT][4];
 #pragma unroll
@@ -184,37 +234,43 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
           for (int r = 0; r < 4; ++r) acc[i][j][r] = 0.f;
 
       const int ksteps = g.Kp >> 3;
+      uint32_t kp = kp_sa, wq = wp_sa;
 #pragma unroll 2
       for (int ks = 0; ks < ksteps; ++ks) {
-        const int2 ko = *reinterpret_cast<const int2*>(kpair + ks * 8 + t * 2);
+        const uint2 ko = lds64(kp);
         uint2 b[NT];
 #pragma unroll
-        for (int j = 0; j < NT; ++j)
-          b[j] = *reinterpret_cast<const uint2*>(wp + (((ks * 4 + t) * g.NPp) + j * 8 + gq) * 2);
+        for (int j = 0; j < NT; ++j) b[j] = lds64(wq + j * 64);
+        kp += 32;
+        wq += wstep;
+        uint32_t a[MT][4];
 #pragma unroll
-        for (int i = 0; i < MT; ++i) {
-          const uint32_t a0 = xs[A0[i] + ko.x], a1 = xs[A1[i] + ko.x], a2 = xs[A0[i] + ko.y], a3 = xs[A1[i] + ko.y];
-#pragma unroll
-          for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, b[j].x, b[j].y);
+        for (int i = 0; i < MT; ++i) {          // all gathers first: 4*MT loads in flight before the first MMA needs one
+          a[i][0] = lds32(A0[i] + ko.x); a[i][1] = lds32(A1[i] + ko.x);
+          a[i][2] = lds32(A0[i] + ko.y); a[i][3] = lds32(A1[i] + ko.y);
         }
+#pragma unroll
+        for (int i = 0; i < MT; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a[i][0], a[i][1], a[i][2], a[i][3], b[j].x, b[j].y);
       }
 
       // ---- epilogue: lanes of equal t hold 8 consecutive outputs of one channel -> 32-byte store segments
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
-        if (u0 + i >= units) continue;
-        const int n = n0 + img_of[i];
+        if (eo[i] < 0) continue;
 #pragma unroll
-        for (int j = 0; j < NT; ++j) {
+        for (int h = 0; h < 2; ++h) {            // rows g, g+8
+          if (!full_tiles && tile_f[i] + gq + 8 * h >= g.F) continue;
 #pragma unroll
-          for (int r = 0; r < 4; ++r) {
-            const int co = j * 8 + 2 * t + (r & 1);
-            const int f = f0_of[i] + gq + ((r & 2) ? 8 : 0);
-            if (co < g.Cout && f < g.F) {
-              float v = acc[i][j][r];
-              if (bias) v += __ldg(bias + co);
-              float* o = out + ((int64_t)n * g.Cout + co) * g.F + f;
-              *o = accumulate ? *o + v : v;
+          for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+              if (cvalid[j][b2]) {
+                float* o = obase + (eo[i] + coff[j][b2] + 8 * h);
+                const float v = acc[i][j][2 * h + b2] + bv[j][b2];
+                *o = accumulate ? *o + v : v;
+              }
             }
           }
         }
@@ -281,6 +337,7 @@ int conv_mma_gather(const float* in, const float* w, const float* bias, float* o
     g.K = KH * KW * g.Op8;
   }
   g.raw_plane = g.raw_rows * g.raw_cols;
+  g.contig = (!g.transpose && g.halo_r == 0 && g.halo_c == 0 && g.spitch == g.raw_cols && g.splane == g.raw_plane) ? 1 : 0;
   g.Kp = (g.K + 7) & ~7;
   g.NP = (g.Cout + 7) & ~7;
   g.NPp = g.NP + 4;
@@ -337,13 +394,14 @@ struct WgradGeo {
   int CKK, Mrows;                            // filter elements per output channel; rows covered by the warps (MS*MTW*16)
   int a_mod, a_div;                          // poff(f) = (f % Ho) * a_mod + (f / Ho) * a_div
   int MS, KS, G;
+  int xcontig;                               // staged x == raw x (no halo, pitch == row length)
 };
 
 template <int MTW, int NT>
 __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __restrict__ ug, const float* __restrict__ x,
                                                              float* __restrict__ part, WgradGeo g, FastDiv d_plane,
                                                              FastDiv d_cols, FastDiv d_ho, FastDiv d_ksi, FastDiv d_kk,
-                                                             FastDiv d_kw, FastDiv d_f, FastDiv d_ckk) {
+                                                             FastDiv d_kw, FastDiv d_f, FastDiv d_ckk, FastDiv d_o) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   int* moff = reinterpret_cast<int*>(smem_u);          // [Mrows]
   int* poff = moff + g.Mrows;                          // [F8]
@@ -362,7 +420,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
       d_kw.divmod(tap, kh, kw);
       off = (int)c * g.splane + (int)kh * g.spitch + (int)kw;
     }
-    moff[m] = off;
+    moff[m] = off * 4;   // byte offset
   }
   for (int f = tid; f < g.F8; f += nthr) {
     int off = 0;
@@ -371,7 +429,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
       d_ho.divmod((uint32_t)f, q, p);
       off = (int)p * g.a_mod + (int)q * g.a_div;
     }
-    poff[f] = off;
+    poff[f] = off * 4;   // byte offset
   }
   // zero once: x halo, ug tails (f >= F) and padded channels (o >= O) are never rewritten by the staging below
   for (int e = tid; e < g.G * (g.ximg + g.uimg); e += nthr) xs[e] = 0u;
@@ -392,13 +450,27 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
     M1[i] = moff[(ms * MTW + i) * 16 + gq + 8];
   }
 
+  const uint32_t xs_sa = smem_u32(xs), po_sa = smem_u32(poff);
+  const uint32_t us_sa = smem_u32(us) + (uint32_t)(gq * g.Up) * 4u;       // this lane's channel row of the ug fragment
+  const uint32_t ximg_b = (uint32_t)g.ximg * 4u, uimg_b = (uint32_t)g.uimg * 4u, up8_b = (uint32_t)g.Up * 32u;
   const int64_t passes = ceil_div<int64_t>(g.N, g.G);
   const int xraw_img = g.C * g.raw_plane, uraw_img = g.O * g.F;
   for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
     const int n0 = (int)(pass * g.G);
     const int ng = min(g.G, g.N - n0);
     __syncthreads();
-    {  // ---- x: natural layout + halo
+    if (g.xcontig) {  // ---- x: staged image == raw image
+      const float* src = x + (int64_t)n0 * xraw_img;
+      const int raw = ng * xraw_img;
+      const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+      const int raw4 = vec ? (raw >> 2) : 0;
+#pragma unroll 4
+      for (int e4 = tid; e4 < raw4; e4 += nthr) {
+        const float4 v = ld_stream4(src + 4 * (int64_t)e4);
+        *reinterpret_cast<uint4*>(xs + 4 * e4) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+      }
+      for (int e = raw4 * 4 + tid; e < raw; e += nthr) xs[e] = to_tf32(__ldg(src + e));
+    } else {  // ---- x: natural layout + halo
       const float* src = x + (int64_t)n0 * xraw_img;
       const int raw = ng * xraw_img;
       const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
@@ -430,24 +502,23 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
       const float* src = ug + (int64_t)n0 * uraw_img;
       const int raw = ng * uraw_img;
       const bool vec = ((reinterpret_cast<uintptr_t>(src) & 15u) == 0) && (g.F % 4 == 0);
+      const int pad_planes = g.NP - g.O;             // zero planes between images in the staged copy
       if (vec) {
-#pragma unroll 2
+#pragma unroll 4
         for (int e4 = tid; e4 < (raw >> 2); e4 += nthr) {
           const float4 v = ld_stream4(src + 4 * (int64_t)e4);
           uint32_t pl, f;
           d_f.divmod((uint32_t)e4 * 4u, pl, f);      // pl = img*O + o
-          uint32_t img, o;
-          // O is small: one more divide by O via the plane count
-          img = pl / (uint32_t)g.O; o = pl - img * (uint32_t)g.O;
+          const uint32_t img = d_o.div(pl);
           uint4 tv = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
-          *reinterpret_cast<uint4*>(us + img * g.uimg + o * g.Up + f) = tv;
+          *reinterpret_cast<uint4*>(us + (pl + img * pad_planes) * g.Up + f) = tv;
         }
       } else {
         for (int e = tid; e < raw; e += nthr) {
           uint32_t pl, f;
           d_f.divmod((uint32_t)e, pl, f);
-          const uint32_t img = pl / (uint32_t)g.O, o = pl - img * (uint32_t)g.O;
-          us[img * g.uimg + o * g.Up + f] = to_tf32(__ldg(src + e));
+          const uint32_t img = d_o.div(pl);
+          us[(pl + img * pad_planes) * g.Up + f] = to_tf32(__ldg(src + e));
         }
       }
     }
@@ -457,19 +528,23 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
     for (int u = kq; u < units; u += g.KS) {
       uint32_t img, ks;
       d_ksi.divmod((uint32_t)u, img, ks);
-      const int f0 = (int)ks * 8;
-      const int2 pp = *reinterpret_cast<const int2*>(poff + f0 + 2 * t);
-      const uint32_t* xb = xs + img * g.ximg;
-      const uint32_t* ub = us + img * g.uimg + f0 + 2 * t;
+      const uint32_t f0b = ks * 32u + (uint32_t)t * 8u;                      // byte offset of position f0 + 2t
+      const uint2 pp = lds64(po_sa + f0b);
+      const uint32_t xb = xs_sa + img * ximg_b;
+      const uint32_t ub = us_sa + img * uimg_b + f0b;
       uint2 b[NT];
 #pragma unroll
-      for (int j = 0; j < NT; ++j) b[j] = *reinterpret_cast<const uint2*>(ub + (j * 8 + gq) * g.Up);
+      for (int j = 0; j < NT; ++j) b[j] = lds64(ub + (uint32_t)j * up8_b);
+      uint32_t a[MTW][4];
 #pragma unroll
       for (int i = 0; i < MTW; ++i) {
-        const uint32_t a0 = xb[M0[i] + pp.x], a1 = xb[M1[i] + pp.x], a2 = xb[M0[i] + pp.y], a3 = xb[M1[i] + pp.y];
-#pragma unroll
-        for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a0, a1, a2, a3, b[j].x, b[j].y);
+        a[i][0] = lds32(xb + M0[i] + pp.x); a[i][1] = lds32(xb + M1[i] + pp.x);
+        a[i][2] = lds32(xb + M0[i] + pp.y); a[i][3] = lds32(xb + M1[i] + pp.y);
       }
+#pragma unroll
+      for (int i = 0; i < MTW; ++i)
+#pragma unroll
+        for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a[i][0], a[i][1], a[i][2], a[i][3], b[j].x, b[j].y);
     }
   }
 
@@ -521,7 +596,7 @@ static int launch_wgrad(const float* ug, const float* x, float* part, const Wgra
   conv_wgrad_mma_kernel<MTW, NT><<<(unsigned)grid, nwarps * 32, smem, st>>>(
       ug, x, part, g, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.Ho),
       FastDiv((uint32_t)g.KSI), FastDiv((uint32_t)(g.KH * g.KW)), FastDiv((uint32_t)g.KW), FastDiv((uint32_t)g.F),
-      FastDiv((uint32_t)g.CKK));
+      FastDiv((uint32_t)g.CKK), FastDiv((uint32_t)g.O));
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
@@ -537,6 +612,7 @@ int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int
   g.spitch = round_up_mod(W + 2 * pad, 8, 4);
   g.splane = (H + 2 * pad) * g.spitch;
   g.ximg = C * g.splane;               // multiple of 4 (spitch is)
+  g.xcontig = (pad == 0 && g.spitch == W) ? 1 : 0;
   g.F = Ho * Wo; g.F8 = (g.F + 7) & ~7; g.KSI = g.F8 / 8;
   g.Up = round_up_mod(g.F8, 32, 8);
   g.NP = (O + 7) & ~7;

@@ -10,8 +10,12 @@ static thread_local std::string t_last_error;
 std::atomic<int64_t> g_launches{0};
 
 static std::mutex g_mu;
-static float* g_scratch = nullptr;
+// One scratch arena per LANE.  A lane is a stream the host runs concurrently with others (ngb_set_lane): kernels of
+// different lanes may overlap on the GPU, so they must not share split-reduction partials or staged operand copies.
+// Lane 0 is allocated by ngb_init(); lanes 1..kLanes-1 on first use (outside graph capture: see ngb_set_lane).
+static float* g_scratch[kLanes] = {nullptr, nullptr, nullptr, nullptr};
 static int64_t g_scratch_bytes = 0;
+static thread_local int t_lane = 0;
 
 void set_error(const std::string& msg) { t_last_error = msg; }
 
@@ -25,11 +29,13 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 
-float* scratch_ptr() { return g_scratch; }
+float* scratch_ptr() { return g_scratch[t_lane]; }
 int64_t scratch_bytes() { return g_scratch_bytes; }
+int current_lane() { return t_lane; }
 
 int ensure_init() {
-  if (g_scratch) return NGB_OK;
+  if (g_scratch[t_lane]) return NGB_OK;
+  if (t_lane != 0) return fail(NGB_ERR_SCRATCH, "lane %d has no scratch arena (ngb_set_lane allocates it)", t_lane);
   return ngb_init(0);
 }
 
@@ -46,7 +52,7 @@ extern "C" int64_t ngb_launch_count(void) { return g_launches.load(); }
 extern "C" int ngb_init(int64_t scratch_bytes) {
   std::lock_guard<std::mutex> lk(g_mu);
   if (scratch_bytes <= 0) scratch_bytes = 64ll << 20;
-  if (g_scratch && g_scratch_bytes >= scratch_bytes) return NGB_OK;
+  if (g_scratch[0] && g_scratch_bytes >= scratch_bytes) return NGB_OK;
   int dev = 0;
   NGB_CUDA(cudaGetDevice(&dev));
   cudaDeviceProp prop;
@@ -55,13 +61,36 @@ extern "C" int ngb_init(int64_t scratch_bytes) {
     return fail(NGB_ERR_UNSUPPORTED, "libngb200 is built for sm_100a (B200) only; device %d is sm_%d%d", dev,
                 prop.major, prop.minor);
   }
-  if (g_scratch) {
-    NGB_CUDA(cudaFree(g_scratch));
-    g_scratch = nullptr;
+  for (int l = 0; l < kLanes; ++l) {
+    const bool had = g_scratch[l] != nullptr;
+    if (had) {
+      NGB_CUDA(cudaFree(g_scratch[l]));
+      g_scratch[l] = nullptr;
+    }
+    if (l == 0 || had) NGB_CUDA(cudaMalloc(&g_scratch[l], scratch_bytes));
   }
-  NGB_CUDA(cudaMalloc(&g_scratch, scratch_bytes));
   g_scratch_bytes = scratch_bytes;
   return NGB_OK;
+}
+
+// Selects the lane (0..3) whose scratch arena / conv workspace the calling thread's subsequent launches use; returns the
+// previous lane, or -1 on error.  The first selection of a lane allocates its arena (cudaMalloc: do it before capturing).
+extern "C" int ngb_set_lane(int lane) {
+  if (lane < 0 || lane >= kLanes) {
+    fail(NGB_ERR_INVALID, "ngb_set_lane: lane must be in [0, %d)", kLanes);
+    return -1;
+  }
+  const int prev = t_lane;
+  if (!g_scratch[lane]) {
+    if (!g_scratch[0] && ngb_init(0) != NGB_OK) return -1;
+    std::lock_guard<std::mutex> lk(g_mu);
+    if (!g_scratch[lane] && cudaMalloc(&g_scratch[lane], g_scratch_bytes) != cudaSuccess) {
+      fail(NGB_ERR_CUDA, "ngb_set_lane: cudaMalloc of the lane's scratch arena failed");
+      return -1;
+    }
+  }
+  t_lane = lane;
+  return prev;
 }
 
 namespace ngb {
@@ -85,10 +114,10 @@ extern "C" int ngb_debug_check_pipelines(void) {
 
 extern "C" int ngb_shutdown(void) {
   std::lock_guard<std::mutex> lk(g_mu);
-  if (g_scratch) {
-    cudaFree(g_scratch);
-    g_scratch = nullptr;
-    g_scratch_bytes = 0;
+  for (int l = 0; l < kLanes; ++l) {
+    if (g_scratch[l]) cudaFree(g_scratch[l]);
+    g_scratch[l] = nullptr;
   }
+  g_scratch_bytes = 0;
   return NGB_OK;
 }

@@ -3,7 +3,8 @@ compared with (a) trajectories recorded from the unmodified reference (tests/gol
 oracle/gen_golden.py) and (b) the CPU oracle on the same seeded inputs.
 
 Tolerances (dist = ||a-b||/(||a||+||b||)): first-step gradients 1e-5 on the fp32 SIMT path, 1e-3 where a Dot is large
-enough to go to the TF32 tensor cores (LeNet-B's 4096x256x120 Linear); loss trajectories 1e-4 / 2e-3; parameters after
+enough to go to the TF32 tensor cores, 2e-3 for LeNet-B (TF32 convolutions and Dots: five TF32 passes between the loss
+and the conv1 weight gradient; the fp32 mode of test_c3_lenet_vs_oracle_at_size holds 1e-4); loss trajectories 1e-4 / 2e-3; parameters after
 N Adam steps 1e-3 / 1e-2 (Adam's m/sqrt(v) normalisation amplifies the relative error of near-zero gradient entries)."""
 import numpy as np
 import pytest
@@ -85,7 +86,8 @@ def test_c3_lenet_grads_and_steps(ng, kind):
   loss.backward()
   for i, p in enumerate(model.parameters()):
     d = dist(p.grad.numpy(), g[f'grad0_{i}'])
-    assert d < 1e-3, (i, d)
+    # LeNet-B: every conv pass and the large Dots use TF32 operands; the conv1 weight gradient sits behind five of them
+    assert d < (2e-3 if kind == 'b' else 1e-3), (i, d)
   optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
   losses = [float(train_step(model, optim, loss_fn, X, Y).data) for _ in range(4)]
   assert dist(losses, g['losses']) < 2e-3, dist(losses, g['losses'])
@@ -211,3 +213,33 @@ def test_engine_semantics(ng):
   lin = ng.nn.Linear(3, 2)
   with pytest.raises(AttributeError):
     lin.weights = ng.nn.layers.Param(np.zeros((3, 2)))             # layers/__init__.py:187-188
+
+
+@pytest.mark.parametrize('captured', [False, True])
+def test_backward_lanes_change_nothing(ng, captured):
+  """Weight / bias gradients issued on side streams (set_backward_lanes, default 2) must give bit-identical parameters
+  to the single-stream order: every kernel is deterministic and each lane owns its scratch arena."""
+  from neograd_b200.capture import CapturedStep
+  from neograd_b200.configs import lenet_synthetic, train_step
+  results = []
+  for n_lanes in (0, 2):
+    prev = ng.set_backward_lanes(n_lanes)
+    try:
+      np.random.seed(0)
+      model, Xh, Yh = lenet_synthetic('b', 512)
+      X, Y = ng.tensor(Xh), ng.tensor(Yh)
+      optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
+      loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+      if captured:
+        step = CapturedStep(lambda: train_step(model, optim, loss_fn, X, Y), warmup=2)
+        for _ in range(3):
+          loss = step()
+      else:
+        for _ in range(5):
+          loss = train_step(model, optim, loss_fn, X, Y)
+      results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
+    finally:
+      ng.set_backward_lanes(prev)
+  assert results[0][0] == results[1][0]
+  for a, b in zip(results[0][1:], results[1][1:]):
+    assert np.array_equal(a, b)
