@@ -4,7 +4,7 @@ auto-removal rules as the reference (node.py:31-86)."""
 
 
 class Node:
-  __slots__ = ('tens', 'children', 'parents', 'parent_broadcast_shape', 'backward_fn', 'visited', 'lane_done')
+  __slots__ = ('tens', 'children', 'parents', 'parent_broadcast_shape', 'backward_fn', 'visited', 'lane_done', 'defer_leaves')
 
   def __init__(self, tens):
     self.tens = tens
@@ -13,6 +13,7 @@ class Node:
     self.parent_broadcast_shape = None
     self.backward_fn = None
     self.visited = False
+    self.defer_leaves = False          # leaf gradients of this op wait until its data gradient has been issued
     self.lane_done = None              # ids of leaf operands whose gradient from this node went to a backward lane
 
   def add_child(self, other):

@@ -29,7 +29,11 @@ class _Binary(Operation):
     def make(side):
       def into(ug, dst, accumulate):
         return D.binary_bwd(op, side, ug, _val(tens1), _val(tens2), dst, accumulate)
-      return GradFn(into)
+      alias = None
+      if op == B.ADD or (op == B.SUB and side == 0):     # gradient == ug when the operand was not broadcast
+        shape = (tens1, tens2)[side].shape
+        alias = lambda ug: ug if ug.shape == shape else None
+      return GradFn(into, alias)
     tens1.set_grad_fn(make(0))
     tens2.set_grad_fn(make(1))
 
@@ -182,7 +186,7 @@ class Flatten(Operation):
 
   def backward(self, tens):
     shape = tens.shape
-    tens.set_grad_fn(GradFn(lambda ug, dst, acc: _copy_into(ug.reshape(shape), dst, acc)))
+    tens.set_grad_fn(GradFn(lambda ug, dst, acc: _copy_into(ug.reshape(shape), dst, acc), lambda ug: ug.reshape(shape)))
 
 
 def flatten(tens): return Flatten().forward(tens)
@@ -197,7 +201,7 @@ class Reshape(Operation):
 
   def backward(self, tens):
     shape = tens.shape
-    tens.set_grad_fn(GradFn(lambda ug, dst, acc: _copy_into(ug.reshape(shape), dst, acc)))
+    tens.set_grad_fn(GradFn(lambda ug, dst, acc: _copy_into(ug.reshape(shape), dst, acc), lambda ug: ug.reshape(shape)))
 
 
 def reshape(tens, new_shape): return Reshape().forward(tens, new_shape)

@@ -21,10 +21,14 @@ class GradFn:
   """A grad_fn the engine can fuse.  `into(ug, dst, accumulate)` must write (accumulate=False) or add
   (accumulate=True) the operand-shaped gradient into `dst`; `dst=None` means allocate.  Calling the object like the
   reference's lambdas (`grad_fn(ug) -> array`) still works."""
-  __slots__ = ('into',)
+  __slots__ = ('into', 'alias')
 
-  def __init__(self, into):
+  def __init__(self, into, alias=None):
     self.into = into
+    # alias(ug) -> a view of ug that IS this operand's gradient (Add / reshape pass-through), or None.  The engine uses
+    # it instead of a copy kernel when the operand has a single consumer and no gradient yet (buffers then become
+    # copy-on-write, see Tensor._grad_shared).
+    self.alias = alias
 
   def __call__(self, ug):
     return self.into(ug, None, False)
@@ -38,6 +42,7 @@ class Tensor:
     self._grad = None           # gradient buffer (may be a pinned arena view)
     self._grad_live = False     # whether _grad currently holds the gradient (False <=> reference's `0.`)
     self._grad_pinned = False
+    self._grad_shared = False   # _grad aliases another tensor's gradient buffer: copy before accumulating in place
     self.data = data
     self.requires_grad = requires_grad
     self.requires_broadcasting = requires_broadcasting
@@ -97,12 +102,14 @@ class Tensor:
   def zero_grad(self):
     """tensor.py:39-42."""
     self._grad_live = False
+    self._grad_shared = False
     if not self._grad_pinned:
       self._grad = None
 
   def accumulate_grad(self, grad):
     """tensor.py:291-301: `self.grad += grad` (the first accumulation replaces the Python 0.)."""
     if self._grad_live:
+      self._unshare_grad()
       self._grad.add_(grad)
     elif self._grad_pinned:
       self._grad.assign(grad)
@@ -152,17 +159,33 @@ class Tensor:
     graph = get_graph()
     for child in node.children:
       if self.requires_grad and calculate_grads:
-        if child.lane_done is not None and id(self) in child.lane_done:
-          child.lane_done.discard(id(self))          # accumulated when the child's gradient became final
+        if child.lane_done is not None and child.lane_done.get(id(self)) == 'lane':
+          del child.lane_done[id(self)]              # accumulated on a backward lane when the child's gradient became final
         else:
+          if child.defer_leaves and not node.parents:
+            if child.lane_done is None:
+              child.lane_done = {}
+            child.lane_done[id(self)] = 'main'       # visited before the deferred issue: that one must skip this leaf
           child.backward_fn(*[n.tens for n in child.parents])
           ct = child.tens
           upper_grad = ct._grad if ct._grad_live else DeviceArray.zeros(ct.shape)
           gf = self.grad_fn
           if isinstance(gf, GradFn):
-            self._ensure_grad_buffer()
-            gf.into(upper_grad, self._grad, self._grad_live)
-            self._grad_live = True
+            view = None
+            if gf.alias is not None and not self._grad_live and not self._grad_pinned and len(node.children) == 1:
+              view = gf.alias(upper_grad)
+            if view is not None:                     # pass-through gradient: share the buffer, no copy kernel
+              self._grad, self._grad_live, self._grad_shared = view, True, True
+              ct._grad_shared = True
+            else:
+              self._ensure_grad_buffer()
+              if self._grad_live:
+                self._unshare_grad()
+              gf.into(upper_grad, self._grad, self._grad_live)
+              self._grad_live = True
+            if child.defer_leaves:                   # the op's data gradient is on its way: now its weight / bias gradients
+              child.defer_leaves = False
+              ct._issue_leaf_grads(child)
           else:
             grad = gf(upper_grad)
             grad = unbroadcast_data(grad, self.shape, child.parent_broadcast_shape)
@@ -171,7 +194,13 @@ class Tensor:
       if not retain_graph and child.are_parents_visited():
         graph.remove_tensor(child.tens)
     if node.parents and self.requires_grad and _lanes.active():
-      self._issue_leaf_grads(node)
+      # If the op also has a data operand that needs a gradient, that kernel is the one the rest of the pass waits on:
+      # it is issued first (at the operand's visit) and the leaf gradients follow it, so they overlap the NEXT kernels
+      # of the chain instead of competing with this one for the SMs.
+      if any(p.parents and p.tens.requires_grad for p in node.parents):
+        node.defer_leaves = True
+      else:
+        self._issue_leaf_grads(node)
     if not retain_graph and node.are_parents_visited():
       graph.remove_tensor(node.tens)
 
@@ -185,22 +214,33 @@ class Tensor:
     for p in leaves:
       t = p.tens
       gf = t.grad_fn
+      if node.lane_done is not None and node.lane_done.get(id(t)) == 'main':
+        del node.lane_done[id(t)]                    # already accumulated at the leaf's own visit
+        continue
       if not isinstance(gf, GradFn) or (node.lane_done is not None and id(t) in node.lane_done):
         continue                                     # user-defined grad_fn: the reference's path at the leaf's own visit
       if ready is None:
         ready = _lanes.mark_ready()                  # main stream: this tensor's gradient is complete
       t._ensure_grad_buffer()
+      if t._grad_live:
+        t._unshare_grad()
       dst, live = t._grad, t._grad_live
       _lanes.run(t, lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live), (upper_grad, gf, node), ready)
       t._grad_live = True
       if node.lane_done is None:
-        node.lane_done = set()
-      node.lane_done.add(id(t))
+        node.lane_done = {}
+      node.lane_done[id(t)] = 'lane'
 
   def _ensure_grad_buffer(self):
     if self._grad is None:
       self._grad = DeviceArray.empty(self.shape)
       self._grad_live = False
+      self._grad_shared = False
+
+  def _unshare_grad(self):
+    if self._grad_shared:
+      self._grad = self._grad.copy()
+      self._grad_shared = False
 
   # ------------------------------------------------------------------ operators (tensor.py:116-289)
   def __add__(self, other):

@@ -28,7 +28,10 @@ class CapturedStep:
     from . import _backend as B
     n0 = B.lib.ngb_launch_count()
     self.graph = t.cuda.CUDAGraph()
-    with t.cuda.graph(self.graph):
+    # Captured on a HIGH-priority stream: the backward lanes (default priority) carry the weight / bias gradients, and
+    # when one of those and the next data-gradient kernel become ready together the chain that everything waits on
+    # must get the SMs first (kernel nodes inherit the priority of the stream they were captured on).
+    with t.cuda.graph(self.graph, stream=t.cuda.Stream(priority=-1)):
       self.result = fn()
     self.launches = int(B.lib.ngb_launch_count() - n0)   # kernels of libngb200 recorded in the graph
 
