@@ -65,6 +65,9 @@ int ngb_workspace_reserve(int64_t bytes);
  * ngb_set_lane selects the lane of the CALLING THREAD's subsequent launches and returns the previous one (-1 on error);
  * the first selection of a lane allocates its arena, so select every lane once before a CUDA-graph capture. */
 int ngb_set_lane(int lane);
+/* Hint for the persistent kernels: corun = 1 -> the calling thread's next launches are expected to overlap another
+ * lane's kernels (they then leave part of every SM free); 0 (default) -> full occupancy.  Returns the previous value. */
+int ngb_set_corun(int corun);
 /* Process-wide precision mode: what NGB_GEMM_AUTO (and the conv dispatcher) resolve to.  NGB_GEMM_AUTO (default) = TF32
  * tensor cores whenever the shape qualifies; NGB_GEMM_SIMT = exact-fp32 CUDA-core kernels everywhere (parity runs,
  * grad_check); NGB_GEMM_TCGEN05 is not a valid default.  Returns the previous value. */

@@ -54,6 +54,7 @@ SIGNATURES = {
   'ngb_workspace_reserve': ([c_int64], c_int),
   'ngb_set_default_engine': ([c_int], c_int),
   'ngb_set_lane': ([c_int], c_int),
+  'ngb_set_corun': ([c_int], c_int),
   'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
   'ngb_launch_count': ([], c_int64),
   'ngb_gemm': ([c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _S], c_int),
@@ -169,7 +170,7 @@ class _Lanes:
     ev.record()
     return ev
 
-  def run(self, key, fn, keep, ready=None):
+  def run(self, key, fn, keep, ready=None, corun=True):
     import torch
     if self.streams is None or len(self.streams) != self.n:
       self._init()
@@ -184,11 +185,13 @@ class _Lanes:
     else:
       side.wait_stream(torch.cuda.current_stream())
     prev = lib.ngb_set_lane(lane)
+    prev_corun = lib.ngb_set_corun(1 if corun else 0)
     try:
       with torch.cuda.stream(side):
         fn()
     finally:
       lib.ngb_set_lane(prev)
+      lib.ngb_set_corun(prev_corun)
     self.used.add(lane)
     self.keep.append(keep)
 
@@ -231,7 +234,7 @@ class profile_calls:
   `records` is a list of (name, args, start_event, end_event); call `summary()` after the block (it synchronises).
   Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
   SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
-          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane')
+          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane', 'ngb_set_corun')
 
   def __enter__(self):
     import torch

@@ -200,11 +200,11 @@ class Tensor:
       if any(p.parents and p.tens.requires_grad for p in node.parents):
         node.defer_leaves = True
       else:
-        self._issue_leaf_grads(node)
+        self._issue_leaf_grads(node, corun=False)   # end of a chain: nothing of this op runs on the main stream
     if not retain_graph and node.are_parents_visited():
       graph.remove_tensor(node.tens)
 
-  def _issue_leaf_grads(self, node):
+  def _issue_leaf_grads(self, node, corun=True):
     leaves = [p for p in node.parents if not p.parents and p.tens.requires_grad and p.tens is not self]
     if not leaves:
       return
@@ -225,7 +225,7 @@ class Tensor:
       if t._grad_live:
         t._unshare_grad()
       dst, live = t._grad, t._grad_live
-      _lanes.run(t, lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live), (upper_grad, gf, node), ready)
+      _lanes.run(t, lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live), (upper_grad, gf, node), ready, corun)
       t._grad_live = True
       if node.lane_done is None:
         node.lane_done = {}

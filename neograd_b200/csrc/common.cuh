@@ -20,6 +20,7 @@ constexpr int kLanes = 4;     // concurrent host-driven streams with private scr
 float* scratch_ptr();          // arena of the calling thread's current lane
 int64_t scratch_bytes();
 int current_lane();
+int corun_hint();               // ngb_set_corun: leave room on the SMs for another lane's kernels
 int ensure_init();
 
 extern std::atomic<int64_t> g_launches;

@@ -27,6 +27,9 @@ int conv_mma_gather(const float* in, const float* w, const float* bias, float* o
 int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int H, int W, int O, int KH, int KW, int pad,
                    int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done);
 
+int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C, int H, int W, int O, int KH, int KW, int pad,
+                        int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done);
+
 constexpr int OT = 8;  // output channels per thread (register tile)
 
 struct ConvGeo {
@@ -809,6 +812,8 @@ extern "C" int ngb_conv_dgrad(const float* ug, const float* w, float* dx, int64_
   //  full-correlation zero halo makes it do 2.25x the useful work -- so small layers use conv_dgrad_small instead.)
   {
     bool done = false;
+    rc = conv_mma_dgrad_rows(ug, w, dx, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, accumulate, st, &done);
+    if (rc || done) return rc;
     rc = conv_mma_gather(ug, w, nullptr, dx, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, 1, accumulate, st, &done);
     if (rc || done) return rc;
     rc = conv_dgrad_small(ug, w, dx, g, accumulate, st, &done);

@@ -380,6 +380,243 @@ int conv_mma_gather(const float* in, const float* w, const float* bias, float* o
   return NGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ dgrad, row-decomposed
+// dx[n][c][h][w] = sum_{o,kh,kw} ug[n][o][p = h+pad-kh][q = w+pad-kw] * W[o][c][kh][kw]        (conv.py:299-309, stride 1)
+//
+// The gather kernel above needs 4 shared-memory loads per MMA for this pass: its N dimension is C (6 -> 8), so a gathered
+// A fragment is used once, and the full-correlation zero halo makes it multiply 2.25x the useful taps.  Here the sum is
+// split as   T[(c,kh)][(p,w)] = sum_{o,kw} W[o][c][kh][kw] * ug[o][p][w+pad-kw]      (one GEMM per image)
+//            dx[c][h][w]      = sum_kh T[(c,kh)][(h+pad-kh, w)]                        (shift-add over kh)
+// so that M = (c, kh) is FULL (two channels x 8 kh slots per 16-row tile), the A operand is the filter bank --
+// K = KW*O (80) values per row, held in registers for the whole kernel -- and the only gathered operand is B:
+// 2 loads per MMA, no vertical halo, no table lookups inside the k loop (all k offsets are warp-uniform).
+// A warp owns (channel pair j, image slot): it walks the image's position tiles, and adds every finished 16x8 tile into
+// the image's dx accumulator in shared memory at row offset kh (only this warp touches channels 2j, 2j+1 of the slot:
+// plain read-modify-write, deterministic).  The accumulators are then written to HBM with coalesced 128-bit stores.
+struct RowsGeo {
+  int N, C, O, H, W, Ho, Wo, KH, pad;
+  int hl, P, plane, uimg;      // staged ug: left halo, row pitch, plane pitch, image pitch (floats)
+  int NPOS, NT8;               // Ho*W positions per image, tiles of 8
+  int HWp, dimg;               // dx accumulator plane pitch (even) and image pitch
+  int MTC, IP;                 // channel-pair tiles, images in flight per CTA
+  int pair_ok;                 // 64-bit read-modify-write possible (W and HWp even)
+};
+
+template <int KW, int OB>
+__global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* __restrict__ ug, const float* __restrict__ w,
+                                                                  float* __restrict__ dx, RowsGeo g, int accumulate,
+                                                                  FastDiv d_w, FastDiv d_howo, FastDiv d_ho, FastDiv d_hw,
+                                                                  FastDiv d_o) {
+  extern __shared__ __align__(16) uint32_t smem_u[];
+  constexpr int KS = KW * OB;
+  int* boff = reinterpret_cast<int*>(smem_u);               // [NT8*8] byte offset of position n in a staged plane
+  int* prow = boff + g.NT8 * 8;                             // [NT8*8] p of position n (for the h range check)
+  uint32_t* us = reinterpret_cast<uint32_t*>(prow + g.NT8 * 8);   // [IP][O8][plane]
+  float* dxs = reinterpret_cast<float*>(us + g.IP * g.uimg);      // [IP][C][HWp]
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int lane = tid & 31, warp = tid >> 5;
+  const int gq = lane >> 2, t = lane & 3;
+  const int j = warp % g.MTC, slot = warp / g.MTC;
+  const int KK = g.KH * KW;
+
+  // ---- stationary A fragments: rows r -> (c = 2j + r/8, kh = r%8), k-step ks = kw*OB + ob, labels t / t+4 -> o = 8ob + t (+4)
+  uint32_t a[KS][4];
+#pragma unroll
+  for (int kw = 0; kw < KW; ++kw)
+#pragma unroll
+    for (int ob = 0; ob < OB; ++ob) {
+      const int ks = kw * OB + ob;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int c = 2 * j + (e & 1);
+        const int o = ob * 8 + t + ((e & 2) ? 4 : 0);
+        float v = 0.f;
+        if (gq < g.KH && c < g.C && o < g.O) v = __ldg(w + ((int64_t)o * g.C + c) * KK + gq * KW + kw);
+        a[ks][e] = to_tf32(v);
+      }
+    }
+  for (int n = tid; n < g.NT8 * 8; n += nthr) {
+    int off = 0, p = 0;
+    if (n < g.NPOS) {
+      uint32_t pp, ww;
+      d_w.divmod((uint32_t)n, pp, ww);
+      p = (int)pp;
+      off = ((int)pp * g.P + (int)ww) * 4;
+    }
+    boff[n] = off;
+    prow[n] = p;
+  }
+  // zero once: halo columns, padded channel planes (never rewritten) and the dx accumulators
+  for (int e = tid; e < g.IP * (g.uimg + g.dimg); e += nthr) us[e] = 0u;
+  __syncthreads();
+
+  const uint32_t us_sa = smem_u32(us) + (uint32_t)(slot * g.uimg + t * g.plane) * 4u;
+  const uint32_t bo_sa = smem_u32(boff) + (uint32_t)gq * 4u;
+  const uint32_t dx_sa = smem_u32(dxs) + (uint32_t)(slot * g.dimg) * 4u;
+  const uint32_t plane_b = (uint32_t)g.plane * 4u;
+  const int HoWo = g.Ho * g.Wo;
+  const int64_t passes = ceil_div<int64_t>(g.N, g.IP);
+  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
+    const int n0 = (int)(pass * g.IP);
+    const int ng = min(g.IP, g.N - n0);
+    // ---- stage: global [o][q][p] (p contiguous) -> smem [o][p][hl + q]
+    {
+      const float* src = ug + (int64_t)n0 * g.O * HoWo;
+      const int raw = ng * g.O * HoWo;
+#pragma unroll 4
+      for (int e = tid; e < raw; e += nthr) {
+        uint32_t pl, f, q, p;
+        d_howo.divmod((uint32_t)e, pl, f);                 // pl = img*O + o
+        d_ho.divmod(f, q, p);
+        uint32_t img, o;
+        d_o.divmod(pl, img, o);
+        us[img * g.uimg + o * g.plane + p * g.P + g.hl + q] = to_tf32(__ldg(src + e));
+      }
+    }
+    __syncthreads();
+
+    if (slot < ng) {
+      const int c0 = 2 * j;
+      // accumulator addresses of this lane's two rows: (c0, kh = gq) and (c0 + 1, kh = gq)
+      const bool row_ok = gq < g.KH;
+      const bool c_ok0 = c0 < g.C, c_ok1 = c0 + 1 < g.C;
+      const int rbase = (gq - g.pad) * g.W + 2 * t;          // element offset inside a channel plane, before + n0
+      for (int nt = 0; nt < g.NT8; ++nt) {
+        const uint32_t addr0 = us_sa + lds32(bo_sa + (uint32_t)nt * 32u);
+        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kw = 0; kw < KW; ++kw)
+#pragma unroll
+          for (int ob = 0; ob < OB; ++ob) {
+            const uint32_t off = (uint32_t)(ob * 8) * plane_b + (uint32_t)(KW - 1 - kw) * 4u;
+            const uint32_t b0 = lds32(addr0 + off), b1 = lds32(addr0 + off + 4u * plane_b);
+            mma_tf32(acc, a[kw * OB + ob][0], a[kw * OB + ob][1], a[kw * OB + ob][2], a[kw * OB + ob][3], b0, b1);
+          }
+        // ---- shift-add: T[(c,kh)][n] -> dxs[c][(p + kh - pad)*W + w] = dxs[c][(kh - pad)*W + n]
+        const int nb = nt * 8 + 2 * t;
+        if (row_ok) {
+          const int p0 = prow[nb], p1 = prow[nb + 1];
+          const int h0 = p0 + gq - g.pad, h1 = p1 + gq - g.pad;
+          const bool v0 = nb < g.NPOS && h0 >= 0 && h0 < g.H, v1 = nb + 1 < g.NPOS && h1 >= 0 && h1 < g.H;
+          const int e0 = rbase + nt * 8;
+          if (g.pair_ok && v0 && v1) {
+            if (c_ok0) {
+              float2* q2 = reinterpret_cast<float2*>(dxs + slot * g.dimg + c0 * g.HWp + e0);
+              float2 o2 = *q2; o2.x += acc[0]; o2.y += acc[1]; *q2 = o2;
+            }
+            if (c_ok1) {
+              float2* q2 = reinterpret_cast<float2*>(dxs + slot * g.dimg + (c0 + 1) * g.HWp + e0);
+              float2 o2 = *q2; o2.x += acc[2]; o2.y += acc[3]; *q2 = o2;
+            }
+          } else {
+            float* q0 = dxs + slot * g.dimg + c0 * g.HWp + e0;
+            float* q1 = q0 + g.HWp;
+            if (c_ok0 && v0) q0[0] += acc[0];
+            if (c_ok0 && v1) q0[1] += acc[1];
+            if (c_ok1 && v0) q1[0] += acc[2];
+            if (c_ok1 && v1) q1[1] += acc[3];
+          }
+        }
+        __syncwarp();   // the next tile's read-modify-write may hit addresses other lanes just wrote
+      }
+    }
+    __syncthreads();
+    // ---- write the accumulators out (coalesced) and clear them for the next pass
+    {
+      const int HW = g.H * g.W;
+      float* dst = dx + (int64_t)n0 * g.C * HW;
+      const int total = ng * g.C * HW;
+      if ((HW & 3) == 0 && (g.HWp & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+        for (int e4 = tid; e4 < (total >> 2); e4 += nthr) {
+          uint32_t pl, f;
+          d_hw.divmod((uint32_t)e4 * 4u, pl, f);            // pl = img*C + c
+          float4* sp = reinterpret_cast<float4*>(dxs + pl * g.HWp + f);
+          float4 v = *sp;
+          *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+          float4* gp = reinterpret_cast<float4*>(dst + 4 * (int64_t)e4);
+          if (accumulate) { const float4 o4 = *gp; v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w; }
+          *gp = v;
+        }
+      } else {
+        for (int e = tid; e < total; e += nthr) {
+          uint32_t pl, f;
+          d_hw.divmod((uint32_t)e, pl, f);
+          float* sp = dxs + pl * g.HWp + f;
+          const float v = *sp;
+          *sp = 0.f;
+          dst[e] = accumulate ? dst[e] + v : v;
+        }
+      }
+    }
+    // (the next pass's staging writes `us`, which nobody reads any more; the __syncthreads after it orders dxs too)
+  }
+}
+
+template <int KW, int OB>
+static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const RowsGeo& g, int accumulate, size_t smem,
+                             cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    NGB_CUDA(cudaFuncSetAttribute(conv_dgrad_rows_mma_kernel<KW, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    attr = true;
+  }
+  const int threads = g.MTC * g.IP * 32;
+  int occ = 1;
+  NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_dgrad_rows_mma_kernel<KW, OB>, threads, smem));
+  if (occ < 1) occ = 1;
+  const int64_t passes = ceil_div<int64_t>(g.N, g.IP);
+  const int grid = (int)(passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ);
+  conv_dgrad_rows_mma_kernel<KW, OB><<<grid, threads, smem, st>>>(ug, w, dx, g, accumulate, FastDiv((uint32_t)g.W),
+                                                                   FastDiv((uint32_t)(g.Ho * g.Wo)), FastDiv((uint32_t)g.Ho),
+                                                                   FastDiv((uint32_t)(g.H * g.W)), FastDiv((uint32_t)g.O));
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C, int H, int W, int O, int KH, int KW, int pad,
+                        int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done) {
+  *done = false;
+  if (g_default_engine.load() == NGB_GEMM_SIMT) return NGB_OK;
+  if (stride != 1 || pad > KW - 1 || pad > KH - 1 || KH > 8 || C < 3 || C > 8 || W < 8) return NGB_OK;
+  const int OB = (O + 7) / 8;
+  if (!((KW == 5 || KW == 3) && (OB == 1 || OB == 2)) && !(KW == 3 && OB == 4)) return NGB_OK;
+  RowsGeo g;
+  g.N = N; g.C = C; g.O = O; g.H = H; g.W = W; g.Ho = Ho; g.Wo = Wo; g.KH = KH; g.pad = pad;
+  g.hl = KW - 1 - pad;
+  g.P = round_up_mod(Wo + 2 * g.hl, 8, 4);
+  g.plane = round_up_mod(Ho * g.P, 32, 8);
+  g.uimg = OB * 8 * g.plane;
+  g.NPOS = Ho * W;
+  g.NT8 = ceil_div(g.NPOS, 8);
+  g.HWp = (H * W + 3) & ~3;
+  g.dimg = C * g.HWp;
+  g.MTC = ceil_div(C, 2);
+  g.pair_ok = (W % 2 == 0) ? 1 : 0;
+  // the last position tile reads up to 7 positions past NPOS at offset 0 (valid); every real read stays inside the plane:
+  // max col = W - 1 + KW - 1 = Wo + 2*hl - 1 < P
+  const size_t fixed = (size_t)g.NT8 * 8 * 2 * 4;
+  const size_t per_img = ((size_t)g.uimg + g.dimg) * 4;
+  int IP = 12 / g.MTC;                                   // up to 12 warps
+  while (IP > 1 && fixed + IP * per_img > 64 * 1024) --IP;
+  if (IP > N) IP = N;
+  if (fixed + IP * per_img > 96 * 1024) return NGB_OK;
+  if (IP >= 3 && fixed + 3 * per_img <= 40 * 1024) IP = 3;   // smaller CTAs, more of them per SM
+  g.IP = IP;
+  const size_t smem = fixed + (size_t)IP * per_img;
+  int rc = ensure_init();
+  if (rc) return rc;
+#define NGB_ROWS(KW_, OB_) rc = launch_dgrad_rows<KW_, OB_>(ug, w, dx, g, accumulate, smem, st)
+  if (KW == 5 && OB == 1) NGB_ROWS(5, 1);
+  else if (KW == 5 && OB == 2) NGB_ROWS(5, 2);
+  else if (KW == 3 && OB == 1) NGB_ROWS(3, 1);
+  else if (KW == 3 && OB == 2) NGB_ROWS(3, 2);
+  else NGB_ROWS(3, 4);
+#undef NGB_ROWS
+  if (rc) return rc;
+  *done = true;
+  return NGB_OK;
+}
+
 // ------------------------------------------------------------------------------------------------ wgrad
 // dw[o][m] = sum_n sum_f ug[n][o][f] * xs[n][moff[m] + poff[f]],   m = (c,kh,kw) (dw's own inner layout), f = q*Ho + p.
 // GEMM view: D[m][o], reduction over the output positions of every image.  The 8 positions of a k-step are consecutive
@@ -587,6 +824,9 @@ static int launch_wgrad(const float* ug, const float* x, float* part, const Wgra
   int occ = 1;
   NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_wgrad_mma_kernel<MTW, NT>, nwarps * 32, smem));
   if (occ < 1) occ = 1;
+  // Beside the data-gradient chain (ngb_set_corun) a persistent grid at full occupancy would hold every register of
+  // every SM until it ends and stall the chain's next kernel: leave half of each SM free.
+  if (corun_hint() && occ > 1) occ = (occ + 1) / 2;
   const int64_t passes = ceil_div<int64_t>(g.N, g.G);
   const int64_t nwts = (int64_t)g.O * g.CKK;
   int64_t grid = passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ;

@@ -16,6 +16,7 @@ static std::mutex g_mu;
 static float* g_scratch[kLanes] = {nullptr, nullptr, nullptr, nullptr};
 static int64_t g_scratch_bytes = 0;
 static thread_local int t_lane = 0;
+static thread_local int t_corun = 0;
 
 void set_error(const std::string& msg) { t_last_error = msg; }
 
@@ -32,6 +33,7 @@ int fail(int code, const char* fmt, ...) {
 float* scratch_ptr() { return g_scratch[t_lane]; }
 int64_t scratch_bytes() { return g_scratch_bytes; }
 int current_lane() { return t_lane; }
+int corun_hint() { return t_corun; }
 
 int ensure_init() {
   if (g_scratch[t_lane]) return NGB_OK;
@@ -96,6 +98,15 @@ extern "C" int ngb_set_lane(int lane) {
 namespace ngb {
 unsigned long long gemm_take_timeout();
 unsigned long long conv_take_timeout();
+}
+
+// Hint for persistent kernels: 1 = the calling thread's next launches are expected to run BESIDE another lane's kernels
+// (leave part of every SM free so the other lane's kernels can become resident), 0 (default) = they have the GPU to
+// themselves.  Returns the previous value.
+extern "C" int ngb_set_corun(int corun) {
+  const int prev = t_corun;
+  t_corun = corun ? 1 : 0;
+  return prev;
 }
 
 // A producer / MMA / epilogue warp that waits on an mbarrier for more than a second records where and leaves the kernel

@@ -263,6 +263,8 @@ SMALL_MMA_CASES = [   # N, C, H, W, O, KH, KW, pad, stride: small-channel layers
   (5, 8, 10, 10, 8, 3, 3, 2, 1),       # "full" padding = K-1: no halo in the data gradient
   (3, 4, 16, 16, 32, 3, 3, 1, 1),      # O = 32: four channel tiles
   (130, 16, 8, 8, 4, 3, 3, 0, 1),      # C = 16: two channel tiles in the data gradient, 9 filter m-tiles in wgrad
+  (7, 4, 9, 11, 12, 5, 5, 1, 1),       # odd W (32-bit shift-add in the row-decomposed dgrad), padding clips rows
+  (10, 7, 8, 8, 20, 3, 3, 0, 1),       # odd C (half-empty channel pair), O = 20 -> three k-blocks of output channels
 ]
 
 
