@@ -140,7 +140,7 @@ class _Lanes:
   join, so the stream-ordered allocator cannot hand them to a later main-stream allocation."""
 
   def __init__(self):
-    self.n = 2
+    self.n = 3
     self.streams = None
     self.used = set()
     self.keep = []
@@ -213,7 +213,7 @@ lanes = _Lanes()
 
 def set_backward_lanes(n):
   """Number of side streams Tensor.backward() may use for weight / bias gradients (0 = everything on one stream, the
-  reference's order of execution; default 2).  Returns the previous setting."""
+  reference's order of execution; default 3).  Returns the previous setting."""
   n = int(n)
   if not 0 <= n <= 3:
     raise ValueError('set_backward_lanes: n must be 0..3')

@@ -35,6 +35,15 @@ __device__ __forceinline__ uint2 lds64(uint32_t addr) {
   return v;
 }
 
+// Persistent CTAs own a CONTIGUOUS range of images (balanced to +-1 image over the grid) and walk it G images at a time:
+// with pass-granular round robin, 512 passes over 444 resident CTAs meant two waves at 58 % efficiency.
+__device__ __forceinline__ void cta_image_range(int N, int& lo, int& cnt) {
+  const int per = N / (int)gridDim.x, rem = N % (int)gridDim.x;
+  const int b = (int)blockIdx.x;
+  lo = b * per + (b < rem ? b : rem);
+  cnt = per + (b < rem ? 1 : 0);
+}
+
 // D(16x8) += A(16x8, row) * B(8x8, col); lane = 4*g + t:
 //   a0 (g, t) a1 (g+8, t) a2 (g, t+4) a3 (g+8, t+4);  b0 (k=t, n=g) b1 (k=t+4, n=g);  d0 (g, 2t) d1 (g, 2t+1) d2 (g+8, 2t) d3 (g+8, 2t+1)
 // The k labels are only names: both operands use the same permutation of the reduction index.
@@ -147,11 +156,11 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
       bv[j][b2] = (bias != nullptr && co < g.Cout) ? __ldg(bias + co) : 0.f;
     }
 
-  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
   const int raw_img = g.Cin * g.raw_plane;
-  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
-    const int n0 = (int)(pass * g.G);
-    const int ng = min(g.G, g.N - n0);
+  int img_lo, img_cnt;
+  cta_image_range(g.N, img_lo, img_cnt);
+  for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.G) {
+    const int ng = min(g.G, img_lo + img_cnt - n0);
     __syncthreads();   // previous pass's fragments are consumed (first pass: the prologue's zero fill is complete)
     // ---- stage ng images, rounded to TF32
     const float* src = in + (int64_t)n0 * raw_img;
@@ -284,19 +293,59 @@ static inline int round_up_mod(int v, int m, int r) {   // smallest v' >= v with
   return v + d;
 }
 
+// Images per pass and grid size of a persistent kernel.  Every CTA owns ceil(N/grid) or floor(N/grid) images; that range
+// is walked in ceil(range/gmax) passes of (nearly) equal size G, so no CTA ends with a one-image straggler pass.  A
+// smaller G shrinks the shared-memory footprint, which can raise occupancy and hence the grid: iterate to a fixed point.
+template <typename Kernel>
+static int balance_images(Kernel kernel, int threads, size_t fixed, size_t per_img, int N, int gmin, int gmax, bool corun, int* G_out,
+                          int* grid_out) {
+  int G = gmax < 1 ? 1 : gmax, grid = 1;
+  for (int it = 0; it < 4; ++it) {
+    int occ = 1;
+    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, threads, fixed + (size_t)G * per_img));
+    if (occ < 1) occ = 1;
+    if (corun && occ > 1) occ = (occ + 1) / 2;   // ngb_set_corun: leave half of every SM to the other lane's kernels
+    grid = N < kNumSMs * occ ? N : kNumSMs * occ;
+    const int ipc = ceil_div(N, grid);
+    int Gn = ceil_div(ipc, ceil_div(ipc, gmax));
+    if (Gn < gmin) Gn = gmin;
+    if (Gn >= G) break;
+    G = Gn;
+  }
+  *G_out = G;
+  *grid_out = grid;
+  return NGB_OK;
+}
+
 template <int MT, int NT>
-static int launch_gather(const float* in, const float* w, const float* bias, float* out, const GatherGeo& g, int accumulate,
-                         int nwarps, size_t smem, cudaStream_t st) {
+static int launch_gather(const float* in, const float* w, const float* bias, float* out, GatherGeo g, int accumulate, int gmax,
+                         size_t fixed, size_t per_img, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  int occ = 1;   // persistent grid: exactly the CTAs that are resident at once
-  NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gather_mma_kernel<MT, NT>, nwarps * 32, smem));
-  if (occ < 1) occ = 1;
-  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
-  const int grid = (int)(passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ);
+  int grid = 1;
+  int rc = balance_images(conv_gather_mma_kernel<MT, NT>, 256, fixed, per_img, g.N, 1, gmax, corun_hint() != 0, &g.G, &grid);
+  if (rc) return rc;
+  // warps: cover the G*MTI tiles of a pass (MT per warp) with as little idle tail as possible
+  const int units = g.G * g.MTI;
+  int nwarps = 8;
+  double best_eff = -1.0;
+  const int cand[] = {8, 9, 10, 12, 7, 6, 11};
+  for (int nw : cand) {
+    const int rounds = ceil_div(units, nw * MT);
+    const double eff = (double)units / ((double)rounds * nw * MT);
+    if (eff > best_eff + 1e-9) { best_eff = eff; nwarps = nw; }
+  }
+  const size_t smem = fixed + (size_t)g.G * per_img;
+  if (nwarps != 8) {   // occupancy of the final block size (G stays)
+    int occ = 1;
+    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gather_mma_kernel<MT, NT>, nwarps * 32, smem));
+    if (occ < 1) occ = 1;
+    if (corun_hint() && occ > 1) occ = (occ + 1) / 2;
+    grid = g.N < kNumSMs * occ ? g.N : kNumSMs * occ;
+  }
   conv_gather_mma_kernel<MT, NT><<<grid, nwarps * 32, smem, st>>>(
       in, w, bias, out, g, accumulate, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.fdiv),
       FastDiv((uint32_t)g.MTI), FastDiv((uint32_t)g.NPp), FastDiv((uint32_t)g.Op8), FastDiv((uint32_t)g.KW),
@@ -353,24 +402,12 @@ int conv_mma_gather(const float* in, const float* w, const float* bias, float* o
   int G = 8;
   while (G > 1 && fixed + G * per_img > budget) --G;
   if (G > N) G = N;
-  g.G = G;
-  const size_t smem = fixed + (size_t)G * per_img;
-  // warps x m-tiles per warp: cover the G*MTI tiles of a pass with as little idle tail as possible
+  // m-tiles per warp: 4 (2 when there are four channel tiles), unless an image has too few tiles to feed 8 warps
   const int MTmax = NT == 4 ? 2 : 4;
-  const int units = G * g.MTI;
-  int best_mt = 2, best_nw = 8;
-  double best_eff = -1.0;
-  for (int mt = MTmax; mt >= 2; mt >>= 1) {
-    const int cand[] = {8, 9, 10, 12, 7, 6, 11};
-    for (int nw : cand) {
-      const int rounds = ceil_div(units, nw * mt);
-      const double eff = (double)units / ((double)rounds * nw * mt);
-      if (eff > best_eff + 1e-9) { best_eff = eff; best_mt = mt; best_nw = nw; }
-    }
-  }
+  const int best_mt = (MTmax == 4 && G * g.MTI < 32) ? 2 : MTmax;
   int rc = ensure_init();
   if (rc) return rc;
-#define NGB_GATHER(MT_, NT_) rc = launch_gather<MT_, NT_>(in, w, bias, out, g, accumulate, best_nw, smem, st)
+#define NGB_GATHER(MT_, NT_) rc = launch_gather<MT_, NT_>(in, w, bias, out, g, accumulate, G, fixed, per_img, st)
   if (NT == 1) { if (best_mt == 4) NGB_GATHER(4, 1); else NGB_GATHER(2, 1); }
   else if (NT == 2) { if (best_mt == 4) NGB_GATHER(4, 2); else NGB_GATHER(2, 2); }
   else NGB_GATHER(2, 4);
@@ -455,10 +492,10 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
   const uint32_t dx_sa = smem_u32(dxs) + (uint32_t)(slot * g.dimg) * 4u;
   const uint32_t plane_b = (uint32_t)g.plane * 4u;
   const int HoWo = g.Ho * g.Wo;
-  const int64_t passes = ceil_div<int64_t>(g.N, g.IP);
-  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
-    const int n0 = (int)(pass * g.IP);
-    const int ng = min(g.IP, g.N - n0);
+  int img_lo, img_cnt;
+  cta_image_range(g.N, img_lo, img_cnt);
+  for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.IP) {
+    const int ng = min(g.IP, img_lo + img_cnt - n0);
     // ---- stage: global [o][q][p] (p contiguous) -> smem [o][p][hl + q]
     {
       const float* src = ug + (int64_t)n0 * g.O * HoWo;
@@ -555,6 +592,7 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
 template <int KW, int OB>
 static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const RowsGeo& g, int accumulate, size_t smem,
                              cudaStream_t st) {
+  // (images per pass = image slots of the block, fixed by its warp count: only the grid is balanced here)
   static bool attr = false;
   if (!attr) {
     NGB_CUDA(cudaFuncSetAttribute(conv_dgrad_rows_mma_kernel<KW, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -564,6 +602,7 @@ static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const R
   int occ = 1;
   NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_dgrad_rows_mma_kernel<KW, OB>, threads, smem));
   if (occ < 1) occ = 1;
+  if (corun_hint() && occ > 1) occ = (occ + 1) / 2;
   const int64_t passes = ceil_div<int64_t>(g.N, g.IP);
   const int grid = (int)(passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ);
   conv_dgrad_rows_mma_kernel<KW, OB><<<grid, threads, smem, st>>>(ug, w, dx, g, accumulate, FastDiv((uint32_t)g.W),
@@ -690,11 +729,11 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
   const uint32_t xs_sa = smem_u32(xs), po_sa = smem_u32(poff);
   const uint32_t us_sa = smem_u32(us) + (uint32_t)(gq * g.Up) * 4u;       // this lane's channel row of the ug fragment
   const uint32_t ximg_b = (uint32_t)g.ximg * 4u, uimg_b = (uint32_t)g.uimg * 4u, up8_b = (uint32_t)g.Up * 32u;
-  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
   const int xraw_img = g.C * g.raw_plane, uraw_img = g.O * g.F;
-  for (int64_t pass = blockIdx.x; pass < passes; pass += gridDim.x) {
-    const int n0 = (int)(pass * g.G);
-    const int ng = min(g.G, g.N - n0);
+  int img_lo, img_cnt;
+  cta_image_range(g.N, img_lo, img_cnt);
+  for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.G) {
+    const int ng = min(g.G, img_lo + img_cnt - n0);
     __syncthreads();
     if (g.xcontig) {  // ---- x: staged image == raw image
       const float* src = x + (int64_t)n0 * xraw_img;
@@ -814,22 +853,22 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
 }
 
 template <int MTW, int NT>
-static int launch_wgrad(const float* ug, const float* x, float* part, const WgradGeo& g, int nwarps, size_t smem, int* grid_out,
-                        cudaStream_t st) {
+static int launch_wgrad(const float* ug, const float* x, float* part, WgradGeo g, int nwarps, int gmin, int gmax, size_t fixed,
+                        size_t per_img, int* grid_out, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
-  int occ = 1;
-  NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_wgrad_mma_kernel<MTW, NT>, nwarps * 32, smem));
-  if (occ < 1) occ = 1;
   // Beside the data-gradient chain (ngb_set_corun) a persistent grid at full occupancy would hold every register of
-  // every SM until it ends and stall the chain's next kernel: leave half of each SM free.
-  if (corun_hint() && occ > 1) occ = (occ + 1) / 2;
-  const int64_t passes = ceil_div<int64_t>(g.N, g.G);
+  // every SM until it ends and stall the chain's next kernel: balance_images then leaves half of each SM free.
+  int grid_i = 1;
+  int rc = balance_images(conv_wgrad_mma_kernel<MTW, NT>, nwarps * 32, fixed, per_img, g.N, gmin, gmax, corun_hint() != 0, &g.G,
+                          &grid_i);
+  if (rc) return rc;
+  const size_t smem = fixed + (size_t)g.G * per_img;
   const int64_t nwts = (int64_t)g.O * g.CKK;
-  int64_t grid = passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ;
+  int64_t grid = grid_i;
   if (grid * nwts * 4 > scratch_bytes()) grid = scratch_bytes() / (nwts * 4);
   if (grid < 1) return fail(NGB_ERR_SCRATCH, "conv wgrad: scratch arena too small for %lld filter elements", (long long)nwts);
   *grid_out = (int)grid;
@@ -874,16 +913,15 @@ int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int
   int G = 8;
   while (G > 1 && fixed + G * per_img > 48 * 1024) --G;
   if (G > N) G = N;
-  if ((size_t)G * per_img < red_bytes) return NGB_OK;       // the reduction tile reuses the staging area
-  g.G = G;
-  const size_t smem = fixed + (size_t)G * per_img;
+  const int gmin = (int)ceil_div<size_t>(red_bytes, per_img);   // the reduction tile reuses the staging area
+  if (G < gmin) return NGB_OK;
   int rc = ensure_init();
   if (rc) return rc;
   const int64_t nw = (int64_t)O * g.CKK;
   if (nw * 4 * kNumSMs * 4 > scratch_bytes()) return NGB_OK;
   int grid = 0;
   float* part = scratch_ptr();
-#define NGB_WGRAD(M_, N_) rc = launch_wgrad<M_, N_>(ug, x, part, g, nwarps, smem, &grid, st)
+#define NGB_WGRAD(M_, N_) rc = launch_wgrad<M_, N_>(ug, x, part, g, nwarps, gmin, G, fixed, per_img, &grid, st)
   if (NT == 1) {
     switch (MTW) { case 1: NGB_WGRAD(1, 1); break; case 2: NGB_WGRAD(2, 1); break; case 3: NGB_WGRAD(3, 1); break;
                    case 4: NGB_WGRAD(4, 1); break; default: NGB_WGRAD(5, 1); break; }

@@ -217,12 +217,14 @@ def test_engine_semantics(ng):
 
 @pytest.mark.parametrize('captured', [False, True])
 def test_backward_lanes_change_nothing(ng, captured):
-  """Weight / bias gradients issued on side streams (set_backward_lanes, default 2) must give bit-identical parameters
-  to the single-stream order: every kernel is deterministic and each lane owns its scratch arena."""
+  """Weight / bias gradients issued on side streams (set_backward_lanes, default 3) must give the same parameters as the
+  single-stream order.  Every kernel is deterministic and each lane owns its scratch arena, so a configuration is
+  bit-reproducible run to run; between configurations only the number of per-CTA partials of a split reduction differs
+  (kernels that co-run with the data-gradient chain use half of each SM), i.e. fp32 re-association."""
   from neograd_b200.capture import CapturedStep
   from neograd_b200.configs import lenet_synthetic, train_step
   results = []
-  for n_lanes in (0, 2):
+  for n_lanes in (0, 3, 3):
     prev = ng.set_backward_lanes(n_lanes)
     try:
       np.random.seed(0)
@@ -240,6 +242,9 @@ def test_backward_lanes_change_nothing(ng, captured):
       results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
     finally:
       ng.set_backward_lanes(prev)
-  assert results[0][0] == results[1][0]
+  assert abs(results[0][0] - results[1][0]) <= 1e-6 * abs(results[0][0])
   for a, b in zip(results[0][1:], results[1][1:]):
+    assert dist(a, b) < 1e-6, dist(a, b)
+  assert results[1][0] == results[2][0]                     # same configuration twice: bit-identical
+  for a, b in zip(results[1][1:], results[2][1:]):
     assert np.array_equal(a, b)

@@ -12,7 +12,7 @@ def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--workload', default='lenet_b')
   ap.add_argument('--batch', type=int, default=4096)
-  ap.add_argument('--lanes', type=int, default=2)
+  ap.add_argument('--lanes', type=int, default=3)
   ap.add_argument('--flush', type=int, default=1)
   args = ap.parse_args()
   import torch
