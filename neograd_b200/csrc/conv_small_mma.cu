@@ -15,6 +15,8 @@
 // its share of the batch.  Exact-fp32 mode (ngb_set_default_engine(NGB_GEMM_SIMT)) never comes here.
 #include "common.cuh"
 
+#include <type_traits>
+
 namespace ngb {
 
 __device__ __forceinline__ uint32_t to_tf32(float x) {
@@ -27,6 +29,19 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   uint32_t v;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
+  return v;
+}
+template <int I, int N, class F>
+__device__ __forceinline__ void static_for(F&& f) {     // compile-time loop: the index can be a template argument
+  if constexpr (I < N) {
+    f(std::integral_constant<int, I>{});
+    static_for<I + 1, N>(f);
+  }
+}
+template <int IMM>
+__device__ __forceinline__ uint32_t lds32_imm(uint32_t addr) {   // [reg + compile-time byte offset]: no address arithmetic
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1+%2];" : "=r"(v) : "r"(addr), "n"(IMM));
   return v;
 }
 __device__ __forceinline__ uint2 lds64(uint32_t addr) {
@@ -75,10 +90,10 @@ struct GatherGeo {
   int G;                               // images per pass
 };
 
-template <int MT, int NT>
+template <int MT, int NT, bool ACC>
 __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ out,
-                                                              GatherGeo g, int accumulate, FastDiv d_plane, FastDiv d_cols,
+                                                              GatherGeo g, FastDiv d_plane, FastDiv d_cols,
                                                               FastDiv d_fdiv, FastDiv d_mti, FastDiv d_npp, FastDiv d_op8,
                                                               FastDiv d_kw, FastDiv d_kk) {
   extern __shared__ __align__(16) uint32_t smem_u[];
@@ -278,7 +293,7 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
               if (cvalid[j][b2]) {
                 float* o = obase + (eo[i] + coff[j][b2] + 8 * h);
                 const float v = acc[i][j][2 * h + b2] + bv[j][b2];
-                *o = accumulate ? *o + v : v;
+                if (ACC) *o += v; else *o = v;
               }
             }
           }
@@ -317,16 +332,16 @@ static int balance_images(Kernel kernel, int threads, size_t fixed, size_t per_i
   return NGB_OK;
 }
 
-template <int MT, int NT>
-static int launch_gather(const float* in, const float* w, const float* bias, float* out, GatherGeo g, int accumulate, int gmax,
-                         size_t fixed, size_t per_img, cudaStream_t st) {
+template <int MT, int NT, bool ACC>
+static int launch_gather(const float* in, const float* w, const float* bias, float* out, GatherGeo g, int gmax, size_t fixed,
+                         size_t per_img, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     attr = true;
   }
   int grid = 1;
-  int rc = balance_images(conv_gather_mma_kernel<MT, NT>, 256, fixed, per_img, g.N, 1, gmax, corun_hint() != 0, &g.G, &grid);
+  int rc = balance_images(conv_gather_mma_kernel<MT, NT, ACC>, 256, fixed, per_img, g.N, 1, gmax, corun_hint() != 0, &g.G, &grid);
   if (rc) return rc;
   // warps: cover the G*MTI tiles of a pass (MT per warp) with as little idle tail as possible
   const int units = g.G * g.MTI;
@@ -341,13 +356,13 @@ static int launch_gather(const float* in, const float* w, const float* bias, flo
   const size_t smem = fixed + (size_t)g.G * per_img;
   if (nwarps != 8) {   // occupancy of the final block size (G stays)
     int occ = 1;
-    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gather_mma_kernel<MT, NT>, nwarps * 32, smem));
+    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gather_mma_kernel<MT, NT, ACC>, nwarps * 32, smem));
     if (occ < 1) occ = 1;
     if (corun_hint() && occ > 1) occ = (occ + 1) / 2;
     grid = g.N < kNumSMs * occ ? g.N : kNumSMs * occ;
   }
-  conv_gather_mma_kernel<MT, NT><<<grid, nwarps * 32, smem, st>>>(
-      in, w, bias, out, g, accumulate, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.fdiv),
+  conv_gather_mma_kernel<MT, NT, ACC><<<grid, nwarps * 32, smem, st>>>(
+      in, w, bias, out, g, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.fdiv),
       FastDiv((uint32_t)g.MTI), FastDiv((uint32_t)g.NPp), FastDiv((uint32_t)g.Op8), FastDiv((uint32_t)g.KW),
       FastDiv((uint32_t)(g.KH * g.KW)));
   NGB_LAUNCH_CHECK();
@@ -407,7 +422,9 @@ int conv_mma_gather(const float* in, const float* w, const float* bias, float* o
   const int best_mt = (MTmax == 4 && G * g.MTI < 32) ? 2 : MTmax;
   int rc = ensure_init();
   if (rc) return rc;
-#define NGB_GATHER(MT_, NT_) rc = launch_gather<MT_, NT_>(in, w, bias, out, g, accumulate, G, fixed, per_img, st)
+#define NGB_GATHER(MT_, NT_)                                                                              \
+  rc = accumulate ? launch_gather<MT_, NT_, true>(in, w, bias, out, g, G, fixed, per_img, st)             \
+                  : launch_gather<MT_, NT_, false>(in, w, bias, out, g, G, fixed, per_img, st)
   if (NT == 1) { if (best_mt == 4) NGB_GATHER(4, 1); else NGB_GATHER(2, 1); }
   else if (NT == 2) { if (best_mt == 4) NGB_GATHER(4, 2); else NGB_GATHER(2, 2); }
   else NGB_GATHER(2, 4);
@@ -514,39 +531,31 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
 
     if (slot < ng) {
       const int c0 = 2 * j;
-      // accumulator addresses of this lane's two rows: (c0, kh = gq) and (c0 + 1, kh = gq)
+      // this lane's two accumulator rows: (c0, kh = gq) and (c0 + 1, kh = gq)
       const bool row_ok = gq < g.KH;
       const bool c_ok0 = c0 < g.C, c_ok1 = c0 + 1 < g.C;
       const int rbase = (gq - g.pad) * g.W + 2 * t;          // element offset inside a channel plane, before + n0
-      for (int nt = 0; nt < g.NT8; ++nt) {
-        const uint32_t addr0 = us_sa + lds32(bo_sa + (uint32_t)nt * 32u);
-        float acc[4] = {0.f, 0.f, 0.f, 0.f};
+      float* const dx_c0 = dxs + slot * g.dimg + c0 * g.HWp;
+      // no padding, whole tiles, even W: every (row, position) of a tile lands inside the plane, 8-byte aligned
+      const bool fast = g.pad == 0 && (g.NPOS & 7) == 0 && g.pair_ok;
+      uint32_t base[OB][2];                                  // planes of o = 8ob + t and o + 4 (byte addresses)
 #pragma unroll
-        for (int kw = 0; kw < KW; ++kw)
-#pragma unroll
-          for (int ob = 0; ob < OB; ++ob) {
-            const uint32_t off = (uint32_t)(ob * 8) * plane_b + (uint32_t)(KW - 1 - kw) * 4u;
-            const uint32_t b0 = lds32(addr0 + off), b1 = lds32(addr0 + off + 4u * plane_b);
-            mma_tf32(acc, a[kw * OB + ob][0], a[kw * OB + ob][1], a[kw * OB + ob][2], a[kw * OB + ob][3], b0, b1);
-          }
-        // ---- shift-add: T[(c,kh)][n] -> dxs[c][(p + kh - pad)*W + w] = dxs[c][(kh - pad)*W + n]
-        const int nb = nt * 8 + 2 * t;
+      for (int ob = 0; ob < OB; ++ob) {
+        base[ob][0] = us_sa + (uint32_t)(ob * 8) * plane_b;
+        base[ob][1] = base[ob][0] + 4u * plane_b;
+      }
+      auto shift_add = [&](const float (&acc)[4], int nt) {
+        // T[(c,kh)][n] -> dxs[c][(p + kh - pad)*W + w] = dxs[c][(kh - pad)*W + n]
         if (row_ok) {
-          const int p0 = prow[nb], p1 = prow[nb + 1];
-          const int h0 = p0 + gq - g.pad, h1 = p1 + gq - g.pad;
-          const bool v0 = nb < g.NPOS && h0 >= 0 && h0 < g.H, v1 = nb + 1 < g.NPOS && h1 >= 0 && h1 < g.H;
           const int e0 = rbase + nt * 8;
-          if (g.pair_ok && v0 && v1) {
-            if (c_ok0) {
-              float2* q2 = reinterpret_cast<float2*>(dxs + slot * g.dimg + c0 * g.HWp + e0);
-              float2 o2 = *q2; o2.x += acc[0]; o2.y += acc[1]; *q2 = o2;
-            }
-            if (c_ok1) {
-              float2* q2 = reinterpret_cast<float2*>(dxs + slot * g.dimg + (c0 + 1) * g.HWp + e0);
-              float2 o2 = *q2; o2.x += acc[2]; o2.y += acc[3]; *q2 = o2;
-            }
+          if (fast) {
+            if (c_ok0) { float2* q2 = reinterpret_cast<float2*>(dx_c0 + e0); float2 o2 = *q2; o2.x += acc[0]; o2.y += acc[1]; *q2 = o2; }
+            if (c_ok1) { float2* q2 = reinterpret_cast<float2*>(dx_c0 + g.HWp + e0); float2 o2 = *q2; o2.x += acc[2]; o2.y += acc[3]; *q2 = o2; }
           } else {
-            float* q0 = dxs + slot * g.dimg + c0 * g.HWp + e0;
+            const int nb = nt * 8 + 2 * t;
+            const int h0 = prow[nb] + gq - g.pad, h1 = prow[nb + 1] + gq - g.pad;
+            const bool v0 = nb < g.NPOS && h0 >= 0 && h0 < g.H, v1 = nb + 1 < g.NPOS && h1 >= 0 && h1 < g.H;
+            float* q0 = dx_c0 + e0;
             float* q1 = q0 + g.HWp;
             if (c_ok0 && v0) q0[0] += acc[0];
             if (c_ok0 && v1) q0[1] += acc[1];
@@ -555,6 +564,33 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
           }
         }
         __syncwarp();   // the next tile's read-modify-write may hit addresses other lanes just wrote
+      };
+      // two position tiles in flight: independent accumulator chains hide the MMA latency
+      for (int nt = 0; nt < g.NT8; nt += 2) {
+        const bool two = nt + 1 < g.NT8;
+        const uint32_t bo0 = lds32(bo_sa + (uint32_t)nt * 32u);
+        const uint32_t bo1 = two ? lds32(bo_sa + (uint32_t)(nt + 1) * 32u) : bo0;
+        uint32_t p0[OB][2], p1[OB][2];
+#pragma unroll
+        for (int ob = 0; ob < OB; ++ob) {
+          p0[ob][0] = base[ob][0] + bo0; p0[ob][1] = base[ob][1] + bo0;
+          p1[ob][0] = base[ob][0] + bo1; p1[ob][1] = base[ob][1] + bo1;
+        }
+        float acc0[4] = {0.f, 0.f, 0.f, 0.f}, acc1[4] = {0.f, 0.f, 0.f, 0.f};
+        static_for<0, KW>([&](auto kwc) {
+          constexpr int kw = decltype(kwc)::value;
+          constexpr int IMM = (KW - 1 - kw) * 4;               // column shift of this tap: an immediate of the load
+#pragma unroll
+          for (int ob = 0; ob < OB; ++ob) {
+            const uint32_t b00 = lds32_imm<IMM>(p0[ob][0]), b01 = lds32_imm<IMM>(p0[ob][1]);
+            const uint32_t b10 = lds32_imm<IMM>(p1[ob][0]), b11 = lds32_imm<IMM>(p1[ob][1]);
+            const uint32_t(&ak)[4] = a[kw * OB + ob];
+            mma_tf32(acc0, ak[0], ak[1], ak[2], ak[3], b00, b01);
+            mma_tf32(acc1, ak[0], ak[1], ak[2], ak[3], b10, b11);
+          }
+        });
+        shift_add(acc0, nt);
+        if (two) shift_add(acc1, nt + 1);
       }
     }
     __syncthreads();
