@@ -42,14 +42,20 @@ constexpr int UMMA_K = 8;
 constexpr int TILE_J0 = 32;       // output extent along its contiguous axis (= i1 direction): one 128-byte line per warp store
 constexpr int TILE_J1 = 4;        // output extent along j1 (= i0 direction): one TMEM lane quadrant each
 
-template <int BLOCK_N>
+// TG = taps along i0 that share ONE A box per stage.  The box covers TILE_J1 + TG - 1 rows of i0; tap t0 of the group is
+// the 128-row window starting t0 * 32 rows (= t0 * 4 KB, a multiple of the 1 KB swizzle atom) into it, so the A operand
+// is fetched once per (t1, channel block) instead of once per tap.  The kernel is bound by the L2 -> SMEM fill rate
+// (~60 B/clk/SM against 128-190 B/clk the MMAs of a 64/128-column tile could consume), so bytes per MMA are what counts.
+template <int BLOCK_N, int TG>
 struct Cfg {
-  static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;   // 16 KB
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kABytes = (TILE_J1 + TG - 1) * TILE_J0 * BLOCK_K * 4;   // 16 KB for TG = 1, 24 KB for TG = 3
+  static constexpr int kBTap = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kBBytes = TG * kBTap;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (200 * 1024) / kStageBytes > 8 ? 8 : (200 * 1024) / kStageBytes;
+  static constexpr int kStages = (218 * 1024) / kStageBytes > 8 ? 8 : (218 * 1024) / kStageBytes;
   static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 + 256;
+  static_assert(kStages >= 2, "pipeline needs two stages");
 };
 
 struct IgemmArgs {
@@ -140,10 +146,13 @@ __global__ void __launch_bounds__(256) stage_channels_last_v4_kernel(const float
 }
 
 // ---------------------------------------------------------------------------------------------- fprop / dgrad kernel
-template <int BLOCK_N>
+// CL = 2: the two CTAs of a cluster work on two position tiles of the SAME channel tile in lock step; each fetches half
+// of every weight box and multicasts it to both, which halves the B bytes each SM pulls from L2.
+template <int BLOCK_N, int TG, int CL>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_constant__ CUtensorMap tmap_w, const IgemmArgs g) {
-  using C_ = Cfg<BLOCK_N>;
+  using C_ = Cfg<BLOCK_N, TG>;
+  const uint32_t crank = CL > 1 ? cluster_ctarank() : 0u;
   constexpr int kStages = C_::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -160,50 +169,70 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tmap_in);
     prefetch_tmap(&tmap_w);
-    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], CL); }
     for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C_::kTmemCols);
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // the peer's barriers exist before anything is multicast at them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int taps = g.T0 * g.T1;
-  const int kblocks = taps * g.cblocks;
+  const int kblocks = g.T1 * (g.T0 / TG) * g.cblocks;      // stages per tile (host guarantees T0 % TG == 0)
   const int tiles_sp = g.tiles_j0 * g.tiles_j1;
-  const int64_t num_work = (int64_t)g.N * tiles_sp * g.tiles_co;
-
-  // work item -> (n, tile_j1, tile_j0, co tile); co fastest so CTAs that run together share the A tile in L2
-  auto decode = [&](int64_t w, int& n, int& j0b, int& j1b, int& co0) {
+  const int64_t m_tiles = (int64_t)g.N * tiles_sp;
+  // One loop index for every role.  CL = 1: w = work item (co fastest so CTAs that run together share the A tile in L2).
+  // CL = 2: w = (pair of position tiles, co tile); this CTA takes tile 2*pair + rank.  A cluster whose second tile does
+  // not exist still runs the pipeline on a clamped tile (barriers stay in lock step) and skips the stores.
+  const int64_t num_work = (CL > 1 ? (m_tiles + 1) / 2 : m_tiles) * g.tiles_co;
+  const int64_t w_first = CL > 1 ? (int64_t)(blockIdx.x / CL) : (int64_t)blockIdx.x;
+  const int64_t w_step = CL > 1 ? (int64_t)(gridDim.x / CL) : (int64_t)gridDim.x;
+  auto decode = [&](int64_t w, int& n, int& j0b, int& j1b, int& co0) -> bool {
     const int ct = (int)(w % g.tiles_co);
     int64_t r = w / g.tiles_co;
+    bool valid = true;
+    if (CL > 1) {
+      r = 2 * r + crank;
+      if (r >= m_tiles) { r = m_tiles - 1; valid = false; }
+    }
     const int sp = (int)(r % tiles_sp);
     n = (int)(r / tiles_sp);
     j0b = (sp % g.tiles_j0) * TILE_J0;
     j1b = (sp / g.tiles_j0) * TILE_J1;
     co0 = ct * BLOCK_N;
+    return valid;
   };
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int64_t w = w_first; w < num_work; w += w_step) {
         int n, j0b, j1b, co0;
         decode(w, n, j0b, j1b, co0);
         for (int t1 = 0; t1 < g.T1; ++t1) {
-          for (int t0 = 0; t0 < g.T0; ++t0) {
-            const int tap = t1 * g.T0 + t0;
+          for (int t0 = 0; t0 < g.T0; t0 += TG) {
             for (int cb = 0; cb < g.cblocks; ++cb, ++it) {
               const int s = it % kStages;
               const uint32_t ph = (it / kStages) & 1;
               mbar_wait(&empty[s], ph ^ 1, 1);
               mbar_arrive_expect_tx(&full[s], C_::kStageBytes);
-              // staged input dims {c, i1, i0, n}: the tap is a shift of the two spatial (outer) coordinates
+              // staged input dims {c, i1, i0, n}: the tap is a shift of the two spatial (outer) coordinates; the box
+              // spans the i0 rows of all TG taps of the group
               tma_load_4d(smem_a + s * C_::kABytes, &tmap_in, &full[s], cb * BLOCK_K, j0b + t1 - g.pad1, j1b + t0 - g.pad0, n);
-              tma_load_2d(smem_b + s * C_::kBBytes, &tmap_w, &full[s], cb * BLOCK_K, tap * g.Cout + co0);
+#pragma unroll
+              for (int u = 0; u < TG; ++u) {
+                if (CL > 1) {   // this CTA's half of the weight box goes to both CTAs
+                  constexpr int kHalfRows = BLOCK_N / 2;
+                  tma_load_2d_mc(smem_b + s * C_::kBBytes + u * C_::kBTap + crank * (kHalfRows * BLOCK_K * 4), &tmap_w, &full[s],
+                                 cb * BLOCK_K, (t1 * g.T0 + t0 + u) * g.Cout + co0 + (int)crank * kHalfRows, (uint16_t)0x3);
+                } else {
+                  tma_load_2d(smem_b + s * C_::kBBytes + u * C_::kBTap, &tmap_w, &full[s], cb * BLOCK_K,
+                              (t1 * g.T0 + t0 + u) * g.Cout + co0);
+                }
+              }
             }
           }
         }
@@ -215,7 +244,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
       constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, 0, 0);
       constexpr uint64_t desc_base = make_smem_desc_base(16, 1024);   // K-major, 128B swizzle (both operands)
       uint32_t it = 0, tile_it = 0;
-      for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+      for (int64_t w = w_first; w < num_work; w += w_step, ++tile_it) {
         const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1, 2);
         tc_fence_after();
@@ -228,11 +257,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           const uint32_t a_addr = smem_u32(smem_a + s * C_::kABytes);
           const uint32_t b_addr = smem_u32(smem_b + s * C_::kBBytes);
 #pragma unroll
-          for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_tf32(d_tmem, smem_desc(desc_base, a_addr + k * UMMA_K * 4), smem_desc(desc_base, b_addr + k * UMMA_K * 4), idesc,
-                      (kb > 0 || k > 0) ? 1u : 0u);
+          for (int u = 0; u < TG; ++u) {
+#pragma unroll
+            for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+              umma_tf32(d_tmem, smem_desc(desc_base, a_addr + u * (TILE_J0 * BLOCK_K * 4) + k * UMMA_K * 4),
+                        smem_desc(desc_base, b_addr + u * C_::kBTap + k * UMMA_K * 4), idesc, (kb > 0 || u > 0 || k > 0) ? 1u : 0u);
+            }
           }
-          umma_commit(&empty[s]);
+          if (CL > 1) umma_commit_mc(&empty[s], (uint16_t)0x3);   // the stage is free once BOTH CTAs have consumed it
+          else umma_commit(&empty[s]);
         }
         umma_commit(&tmem_full[acc]);
       }
@@ -243,14 +276,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
     const int quad = warp & 3;                // TMEM lane quadrant == offset along j1; lane == offset along j0
     uint32_t tile_it = 0;
     const int64_t plane = (int64_t)g.J0 * g.J1;
-    for (int64_t w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+    for (int64_t w = w_first; w < num_work; w += w_step, ++tile_it) {
       int n, j0b, j1b, co0;
-      decode(w, n, j0b, j1b, co0);
+      const bool tile_valid = decode(w, n, j0b, j1b, co0);
       const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_ph, 4);
       tc_fence_after();
       const int j0 = j0b + lane, j1 = j1b + quad;
-      const bool ok = j0 < g.J0 && j1 < g.J1;
+      const bool ok = tile_valid && j0 < g.J0 && j1 < g.J1;
       float* obase = g.out + ((int64_t)n * g.Cout + co0) * plane + (int64_t)j1 * g.J0 + j0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
@@ -262,15 +295,21 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (ok) {
+        // bias of the chunk's 32 channels: one coalesced load, broadcast by shuffle (was 32 loads per thread)
+        float bv = 0.f;
+        if (g.bias && co0 + c0 + lane < g.Cout) bv = __ldg(g.bias + co0 + c0 + lane);
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int co = co0 + c0 + j;
-            if (co < g.Cout) {
-              float r = v[j];
-              if (g.bias) r += __ldg(g.bias + co);
-              float* o = obase + (int64_t)(c0 + j) * plane;
-              *o = g.accumulate ? *o + r : r;
+        for (int j = 0; j < 32; ++j) v[j] += __shfl_sync(0xffffffffu, bv, j);
+        if (ok) {
+          if (g.accumulate) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (co0 + c0 + j < g.Cout) { float* o = obase + (int64_t)(c0 + j) * plane; *o += v[j]; }
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              if (co0 + c0 + j < g.Cout) obase[(int64_t)(c0 + j) * plane] = v[j];
             }
           }
         }
@@ -280,6 +319,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap tmap_in, const __grid_cons
 
   tc_fence_before();
   __syncthreads();
+  if (CL > 1) cluster_sync_all();      // no CTA leaves while its peer can still multicast into it
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, C_::kTmemCols);
@@ -364,17 +404,41 @@ int stage(const float* in, float* S, int64_t N, int64_t C, int64_t I1, int64_t I
   return NGB_OK;
 }
 
-template <int BN>
-int launch_igemm(const CUtensorMap& tin, const CUtensorMap& tw, const IgemmArgs& g, int grid, cudaStream_t st) {
-  using C_ = Cfg<BN>;
-  auto kern = conv_igemm_kernel<BN>;
+template <int BN, int TG, int CL>
+int launch_igemm(const CUtensorMap& tin, const CUtensorMap& tw, const IgemmArgs& g, int64_t work, cudaStream_t st) {
+  using C_ = Cfg<BN, TG>;
+  auto kern = conv_igemm_kernel<BN, TG, CL>;
   static bool attr_set = false;
+  static int max_clusters = 0;
   if (!attr_set) {
     NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(tin, tw, g);
-  NGB_LAUNCH_CHECK();
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = C_::kSmemBytes;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  int grid;
+  if (CL > 1) {
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_clusters == 0) {   // clusters that can be resident at once (GPC boundaries can leave an SM unpaired)
+      cfg.gridDim = dim3(kNumSMs / CL * CL);
+      NGB_CUDA(cudaOccupancyMaxActiveClusters(&max_clusters, kern, &cfg));
+      if (max_clusters < 1) max_clusters = 1;
+    }
+    const int64_t pairs = (work + CL - 1) / CL;   // upper bound on cluster work items per channel tile set
+    const int64_t clusters = pairs < max_clusters ? pairs : max_clusters;
+    grid = (int)clusters * CL;
+  } else {
+    grid = (int)(work < kNumSMs ? work : kNumSMs);
+  }
+  cfg.gridDim = dim3(grid);
+  NGB_CUDA(cudaLaunchKernelEx(&cfg, kern, tin, tw, g));
+  count_launch();
   return NGB_OK;
 }
 
@@ -409,24 +473,29 @@ int run_igemm(const float* in, const float* w, const float* bias, float* out, in
   g.cblocks = (int)(Cin / BLOCK_K);
   g.out = out; g.bias = bias; g.accumulate = accumulate;
 
+  // taps along i0 sharing one A box: 3 for 3-tap filters on the narrow tiles (their stage still fits 3-4 times)
+  // taps along i0 sharing one A box: 3 for 3-tap filters on the narrow tiles (a 256-column stage would not fit twice)
+  const int TG = (T0 == 3 && BN <= 128) ? 3 : 1;
+  // CL = 2 (weight boxes multicast over a 2-CTA cluster) is implemented and parity-tested, but measured no faster on
+  // B200: the L2 -> SM fabric delivers a copy per destination SM, so the bytes each SM receives are unchanged.
+  constexpr int CL = 1;
   CUtensorMap tin, tw;
   {
     const uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)I1, (uint64_t)I0, (uint64_t)N};
     const uint64_t str[3] = {(uint64_t)Cin * 4, (uint64_t)Cin * I1 * 4, (uint64_t)Cin * I1 * I0 * 4};
-    const uint32_t box[4] = {BLOCK_K, TILE_J0, TILE_J1, 1};
+    const uint32_t box[4] = {BLOCK_K, TILE_J0, (uint32_t)(TILE_J1 + TG - 1), 1};
     rc = make_tmap_f32(&tin, S, 4, dims, str, box, false);
     if (rc) return rc;
     const uint64_t wdims[2] = {(uint64_t)Cin, (uint64_t)(T0 * T1 * Cout)};
     const uint64_t wstr[1] = {(uint64_t)Cin * 4};
-    const uint32_t wbox[2] = {BLOCK_K, (uint32_t)BN};
+    const uint32_t wbox[2] = {BLOCK_K, (uint32_t)(BN / CL)};     // CL = 2: each CTA of the pair fetches half of the rows
     rc = make_tmap_f32(&tw, wp, 2, wdims, wstr, wbox, false);
     if (rc) return rc;
   }
   const int64_t work = (int64_t)N * g.tiles_j0 * g.tiles_j1 * g.tiles_co;
-  const int grid = (int)(work < kNumSMs ? work : kNumSMs);
-  if (BN == 64) rc = launch_igemm<64>(tin, tw, g, grid, st);
-  else if (BN == 128) rc = launch_igemm<128>(tin, tw, g, grid, st);
-  else rc = launch_igemm<256>(tin, tw, g, grid, st);
+  if (BN == 64) rc = TG == 3 ? launch_igemm<64, 3, CL>(tin, tw, g, work, st) : launch_igemm<64, 1, CL>(tin, tw, g, work, st);
+  else if (BN == 128) rc = TG == 3 ? launch_igemm<128, 3, CL>(tin, tw, g, work, st) : launch_igemm<128, 1, CL>(tin, tw, g, work, st);
+  else rc = launch_igemm<256, 1, CL>(tin, tw, g, work, st);
   return rc;
 }
 
