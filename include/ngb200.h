@@ -110,6 +110,15 @@ int ngb_maxpool_fwd(const float* x, float* y, uint8_t* idx, int64_t outer, int64
 int ngb_maxpool_bwd(const float* ug, const uint8_t* idx, float* dx, int64_t outer, int64_t H, int64_t W,
                     int64_t KH, int64_t KW, int64_t pad, int64_t stride, int accumulate,
                     ngb_stream_t stream);                                                   /* conv.py:404-431 */
+/* ReLU -> MaxPool pairs (activations.py:20 followed by conv.py:384-402) without the ReLU's output ever touching HBM:
+ *   fwd: y / idx = maxpool(max(0, x));    bwd: dx (+)= (xm >= 0) * maxpool_bwd(ug, idx)   (xm = the ReLU's input).
+ * Only 2x2 / stride 2 / pad 0 on 16-byte aligned rows (even H for bwd); other geometries return NGB_ERR_UNSUPPORTED
+ * and the caller runs the two ops separately.  Results are bit-identical to the separate kernels. */
+int ngb_maxpool_relu_fwd(const float* x, float* y, uint8_t* idx, int64_t outer, int64_t H, int64_t W,
+                         int64_t KH, int64_t KW, int64_t pad, int64_t stride, ngb_stream_t stream);
+int ngb_maxpool_relu_bwd(const float* ug, const uint8_t* idx, const float* xm, float* dx, int64_t outer, int64_t H,
+                         int64_t W, int64_t KH, int64_t KW, int64_t pad, int64_t stride, int accumulate,
+                         ngb_stream_t stream);
 
 /* ---- broadcasting elementwise ops + unbroadcast: basics.py:6-339, utils.py:34-78, tensor.py:93-100 -------- */
 /* out = a (op) b with NumPy broadcasting.  A NULL operand pointer means "use the scalar immediate". */

@@ -3,6 +3,8 @@
 Forward bodies call one kernel of libngb200.so; every grad_fn is a `GradFn` whose `into` issues ONE kernel that
 computes local-gradient x upstream-gradient, reduces over the broadcast axes of that operand (utils.py:34-78) and
 writes / accumulates into the operand's gradient buffer."""
+import ctypes
+
 import numpy as np
 
 from ... import _backend as B
@@ -96,12 +98,29 @@ class _Unary(Operation):
 
   def forward(self, tens):
     tens = self.get_tensors(tens)
-    return self.get_result_tensor(D.unary(self.OP, tens.data, self.alpha), tens)
+    x, op, alpha = tens.data, self.OP, self.alpha
+    if op == B.RELU and D.LAZY_FUSION:
+      # produced on first use: a MaxPool that follows reads x itself (maxpool(relu(x)) in one kernel, conv.py here)
+      out = D.LazyArray(x.shape, lambda: D.unary(op, x, alpha), 'relu', x)
+    else:
+      out = D.unary(op, x, alpha)
+    return self.get_result_tensor(out, tens)
 
   def backward(self, tens):
     op, alpha, x = self.OP, self.alpha, tens.data
 
     def into(ug, dst, accumulate):
+      if op == B.RELU and isinstance(ug, D.LazyArray) and ug.pending and ug.tag == 'maxpool_bwd':
+        # upstream gradient = input gradient of a MaxPool that has not been written yet: route + mask in one kernel
+        pug, idx, outer, H, W, KH, KW, pad, stride = ug.args
+        if dst is None:
+          dst, accumulate = D.DeviceArray.empty(x.shape), False
+        rc = B.lib.ngb_maxpool_relu_bwd(pug.ptr, ctypes.c_void_p(idx.data_ptr()), x.ptr, dst.ptr, outer, H, W, KH, KW, pad, stride,
+                                        int(accumulate), D._st())
+        if rc == 0:
+          return dst
+        if rc != B.ERR_UNSUPPORTED:
+          B.check(rc)
       if dst is None:
         return D.unary_bwd(op, x, ug, alpha)
       B.check(B.lib.ngb_ew_unary_bwd(op, float(alpha), x.ptr, ug.ptr, dst.ptr, x.size, int(accumulate), D._st()))

@@ -149,8 +149,16 @@ class _MaxPool(Operation, Conv):
     outer = int(np.prod(lead))
     y = D.DeviceArray.empty(lead + (ho, wo))
     idx = D.torch().empty(lead + (ho, wo), device='cuda', dtype=D.torch().uint8)
-    B.check(B.lib.ngb_maxpool_fwd(inputs.data.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), outer, H, W,
-                                  self.kernel_shape[0], self.kernel_shape[1], self.padding, self.stride, D._st()))
+    xin, rc = inputs.data, -1
+    if isinstance(xin, D.LazyArray) and xin.pending and xin.tag == 'relu':
+      # the input is a ReLU output nobody has read yet: pool max(0, x) of the ReLU's own input, relu(x) is never written
+      rc = B.lib.ngb_maxpool_relu_fwd(xin.args.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), outer, H, W,
+                                      self.kernel_shape[0], self.kernel_shape[1], self.padding, self.stride, D._st())
+      if rc not in (0, B.ERR_UNSUPPORTED):
+        B.check(rc)
+    if rc != 0:
+      B.check(B.lib.ngb_maxpool_fwd(xin.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), outer, H, W,
+                                    self.kernel_shape[0], self.kernel_shape[1], self.padding, self.stride, D._st()))
     self._idx = idx
     return self.get_result_tensor(y, inputs)
 
@@ -166,7 +174,14 @@ class _MaxPool(Operation, Conv):
       B.check(B.lib.ngb_maxpool_bwd(ug.ptr, ctypes.c_void_p(idx.data_ptr()), dst.ptr, outer, H, W, KH, KW, pad, stride,
                                     int(acc), D._st()))
       return dst
-    inputs.set_grad_fn(GradFn(into))
+
+    def lazy(ug):
+      # the input gradient as a deferred array: a ReLU backward that consumes it fuses the routing with its mask
+      if not D.LAZY_FUSION:
+        return None
+      shape = inputs.shape
+      return D.LazyArray(shape, lambda: into(ug, None, False), 'maxpool_bwd', (ug, idx, outer, H, W, KH, KW, pad, stride))
+    inputs.set_grad_fn(GradFn(into, None, lazy))
 
   def validate_inputs(self, inputs):
     if len(inputs.shape) != self.NDIM:

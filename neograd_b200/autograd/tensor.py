@@ -21,10 +21,13 @@ class GradFn:
   """A grad_fn the engine can fuse.  `into(ug, dst, accumulate)` must write (accumulate=False) or add
   (accumulate=True) the operand-shaped gradient into `dst`; `dst=None` means allocate.  Calling the object like the
   reference's lambdas (`grad_fn(ug) -> array`) still works."""
-  __slots__ = ('into', 'alias')
+  __slots__ = ('into', 'alias', 'lazy')
 
-  def __init__(self, into, alias=None):
+  def __init__(self, into, alias=None, lazy=None):
     self.into = into
+    # lazy(ug) -> a device.LazyArray standing for this operand's gradient (produced on first use), or None.  Same
+    # conditions as `alias`; lets the operand's own backward fuse with the producing kernel (MaxPool -> ReLU).
+    self.lazy = lazy
     # alias(ug) -> a view of ug that IS this operand's gradient (Add / reshape pass-through), or None.  The engine uses
     # it instead of a copy kernel when the operand has a single consumer and no gradient yet (buffers then become
     # copy-on-write, see Tensor._grad_shared).
@@ -172,11 +175,15 @@ class Tensor:
           gf = self.grad_fn
           if isinstance(gf, GradFn):
             view = None
-            if gf.alias is not None and not self._grad_live and not self._grad_pinned and len(node.children) == 1:
+            single = not self._grad_live and not self._grad_pinned and len(node.children) == 1
+            if gf.alias is not None and single:
               view = gf.alias(upper_grad)
+            deferred = gf.lazy(upper_grad) if (view is None and gf.lazy is not None and single and node.parents) else None
             if view is not None:                     # pass-through gradient: share the buffer, no copy kernel
               self._grad, self._grad_live, self._grad_shared = view, True, True
               ct._grad_shared = True
+            elif deferred is not None:               # produced when (and if) somebody reads it
+              self._grad, self._grad_live, self._grad_shared = deferred, True, False
             else:
               self._ensure_grad_buffer()
               if self._grad_live:
@@ -210,6 +217,8 @@ class Tensor:
       return
     node.backward_fn(*[n.tens for n in node.parents])
     upper_grad = self._grad if self._grad_live else DeviceArray.zeros(self.shape)
+    if getattr(upper_grad, 'pending', False):
+      upper_grad.t                                   # a deferred gradient is produced HERE, on the main stream, once
     ready = None
     for p in leaves:
       t = p.tens

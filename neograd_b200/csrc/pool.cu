@@ -184,6 +184,9 @@ __device__ __forceinline__ void max4(float a, float b, float c, float d, float& 
   if (d > best) { best = d; arg = 3; }
 }
 
+// RELU: the input is max(0, x) of the given buffer (the ReLU in front of the pool is applied on load, its output is
+// never written: ngb_maxpool_relu_fwd).
+template <bool RELU>
 __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                              uint8_t* __restrict__ idx, int64_t outer, Pool2Geo g) {
   extern __shared__ float sm[];
@@ -208,7 +211,11 @@ __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __rest
       g.d_tp.divmod(rest, gi, lp);
       if ((int)lp >= tp) continue;
       const float* r0 = x + ((o0 + gi) * g.H + 2 * (p0 + (int)lp)) * (int64_t)g.W + 4 * c4;
-      const float4 a = ld_stream4(r0), b = ld_stream4(r0 + g.W);
+      float4 a = ld_stream4(r0), b = ld_stream4(r0 + g.W);
+      if (RELU) {   // same expression as the elementwise ReLU kernel (elementwise.cu): fmaxf(0, x)
+        a.x = fmaxf(0.f, a.x); a.y = fmaxf(0.f, a.y); a.z = fmaxf(0.f, a.z); a.w = fmaxf(0.f, a.w);
+        b.x = fmaxf(0.f, b.x); b.y = fmaxf(0.f, b.y); b.z = fmaxf(0.f, b.z); b.w = fmaxf(0.f, b.w);
+      }
       float v0, v1;
       int a0, a1;
       max4(a.x, a.y, b.x, b.y, v0, a0);
@@ -235,8 +242,12 @@ __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __rest
   }
 }
 
+// MASK: the result is additionally multiplied by the ReLU gradient mask (xm >= 0) of the buffer the ReLU in front of
+// the pool read: one kernel for maxpool backward + relu backward (ngb_maxpool_relu_bwd).
+template <bool MASK>
 __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __restrict__ ug, const uint8_t* __restrict__ idx,
-                                                             float* __restrict__ dx, int64_t outer, Pool2Geo g, int accumulate) {
+                                                             float* __restrict__ dx, int64_t outer, Pool2Geo g, int accumulate,
+                                                             const float* __restrict__ xm) {
   extern __shared__ float sm[];
   const int TPp = g.TP | 1;
   float* sg = sm;
@@ -309,8 +320,14 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __rest
         const int a = si[s0 + TPp];
         r0.z = a == 0 ? gv : 0.f; r0.w = a == 1 ? gv : 0.f; r1.z = a == 2 ? gv : 0.f; r1.w = a == 3 ? gv : 0.f;
       }
-      float* d0 = dx + ((o0 + gi) * g.H + 2 * (p0 + (int)lp)) * (int64_t)g.W + 4 * c4;
+      const int64_t off0 = ((o0 + gi) * g.H + 2 * (p0 + (int)lp)) * (int64_t)g.W + 4 * c4;
+      float* d0 = dx + off0;
       float* d1 = d0 + g.W;
+      if (MASK) {   // relu backward: gradient passes where the relu input was >= 0 (activations.py:31)
+        const float4 m0 = ld_stream4(xm + off0), m1 = ld_stream4(xm + off0 + g.W);
+        r0.x = m0.x >= 0.f ? r0.x : 0.f; r0.y = m0.y >= 0.f ? r0.y : 0.f; r0.z = m0.z >= 0.f ? r0.z : 0.f; r0.w = m0.w >= 0.f ? r0.w : 0.f;
+        r1.x = m1.x >= 0.f ? r1.x : 0.f; r1.y = m1.y >= 0.f ? r1.y : 0.f; r1.z = m1.z >= 0.f ? r1.z : 0.f; r1.w = m1.w >= 0.f ? r1.w : 0.f;
+      }
       if (accumulate) {
         const float4 o0v = *reinterpret_cast<const float4*>(d0), o1v = *reinterpret_cast<const float4*>(d1);
         r0.x += o0v.x; r0.y += o0v.y; r0.z += o0v.z; r0.w += o0v.w;
@@ -456,6 +473,45 @@ static int make_pool_geo(PoolGeo* g, int64_t outer, int64_t H, int64_t W, int64_
   return NGB_OK;
 }
 
+// y = maxpool(relu(x)) and its argmax over relu(x), without materialising relu(x).  Only the 2x2 / stride 2 / pad 0
+// geometry on 16-byte aligned rows (the specialised kernel); anything else returns NGB_ERR_UNSUPPORTED and the caller
+// runs ReLU and the pool separately.
+extern "C" int ngb_maxpool_relu_fwd(const float* x, float* y, uint8_t* idx, int64_t outer, int64_t H, int64_t W, int64_t KH,
+                                    int64_t KW, int64_t pad, int64_t stride, ngb_stream_t stream) {
+  int64_t Ho, Wo;
+  int rc = pool_geometry(H, W, KH, KW, pad, stride, &Ho, &Wo);
+  if (rc) return rc;
+  Pool2Geo g2;
+  if (outer * Ho * Wo == 0 || !make_pool2_geo(&g2, outer, H, W, KH, KW, pad, stride, Ho, Wo, x, x))
+    return fail(NGB_ERR_UNSUPPORTED, "maxpool+relu fusion: only 2x2 / stride 2 / pad 0 on 16-byte aligned rows");
+  const size_t smem2 = (size_t)g2.G * g2.Wo * (g2.TP | 1) * 5 + 16;
+  const int64_t items2 = ceil_div<int64_t>(outer, g2.G) * g2.strips;
+  const int grid2 = (int)(items2 < (int64_t)kNumSMs * 8 ? items2 : (int64_t)kNumSMs * 8);
+  maxpool2x2_fwd_kernel<true><<<grid2, 256, smem2, as_stream(stream)>>>(x, y, idx, outer, g2);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+// dx (+)= (xm >= 0) * maxpool_backward(ug, idx): the ReLU backward of the layer in front of the pool applied in the same
+// pass (xm = the buffer that ReLU read).  Same geometry restriction as ngb_maxpool_relu_fwd.
+extern "C" int ngb_maxpool_relu_bwd(const float* ug, const uint8_t* idx, const float* xm, float* dx, int64_t outer, int64_t H,
+                                    int64_t W, int64_t KH, int64_t KW, int64_t pad, int64_t stride, int accumulate,
+                                    ngb_stream_t stream) {
+  int64_t Ho, Wo;
+  int rc = pool_geometry(H, W, KH, KW, pad, stride, &Ho, &Wo);
+  if (rc) return rc;
+  NGB_CHECK_ARG(idx != nullptr && xm != nullptr, "ngb_maxpool_relu_bwd needs the argmax indices and the relu input");
+  Pool2Geo g2;
+  if (outer * H * W == 0 || (H & 1) || !aligned16(xm) || !make_pool2_geo(&g2, outer, H, W, KH, KW, pad, stride, Ho, Wo, dx, dx))
+    return fail(NGB_ERR_UNSUPPORTED, "maxpool+relu fusion: only 2x2 / stride 2 / pad 0, even H, 16-byte aligned rows");
+  const size_t smem2 = (size_t)g2.G * g2.Wo * (g2.TP | 1) * 5 + 16;
+  const int64_t items2 = ceil_div<int64_t>(outer, g2.G) * g2.strips;
+  const int grid2 = (int)(items2 < (int64_t)kNumSMs * 8 ? items2 : (int64_t)kNumSMs * 8);
+  maxpool2x2_bwd_kernel<true><<<grid2, 256, smem2, as_stream(stream)>>>(ug, idx, dx, outer, g2, accumulate, xm);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
 extern "C" int ngb_maxpool_fwd(const float* x, float* y, uint8_t* idx, int64_t outer, int64_t H, int64_t W, int64_t KH,
                                int64_t KW, int64_t pad, int64_t stride, ngb_stream_t stream) {
   int64_t Ho, Wo;
@@ -467,7 +523,7 @@ extern "C" int ngb_maxpool_fwd(const float* x, float* y, uint8_t* idx, int64_t o
     const size_t smem2 = (size_t)g2.G * g2.Wo * (g2.TP | 1) * 5 + 16;
     const int64_t items2 = ceil_div<int64_t>(outer, g2.G) * g2.strips;
     const int grid2 = (int)(items2 < (int64_t)kNumSMs * 8 ? items2 : (int64_t)kNumSMs * 8);
-    maxpool2x2_fwd_kernel<<<grid2, 256, smem2, as_stream(stream)>>>(x, y, idx, outer, g2);
+    maxpool2x2_fwd_kernel<false><<<grid2, 256, smem2, as_stream(stream)>>>(x, y, idx, outer, g2);
     NGB_LAUNCH_CHECK();
     return NGB_OK;
   }
@@ -500,7 +556,7 @@ extern "C" int ngb_maxpool_bwd(const float* ug, const uint8_t* idx, float* dx, i
     const size_t smem2 = (size_t)g2.G * g2.Wo * (g2.TP | 1) * 5 + 16;
     const int64_t items2 = ceil_div<int64_t>(outer, g2.G) * g2.strips;
     const int grid2 = (int)(items2 < (int64_t)kNumSMs * 8 ? items2 : (int64_t)kNumSMs * 8);
-    maxpool2x2_bwd_kernel<<<grid2, 256, smem2, as_stream(stream)>>>(ug, idx, dx, outer, g2, accumulate);
+    maxpool2x2_bwd_kernel<false><<<grid2, 256, smem2, as_stream(stream)>>>(ug, idx, dx, outer, g2, accumulate, nullptr);
     NGB_LAUNCH_CHECK();
     return NGB_OK;
   }

@@ -287,6 +287,63 @@ def binary_bwd(op, side, ug, a, b, grad_out=None, accumulate=False):
   return grad_out
 
 
+class LazyArray(DeviceArray):
+  """A DeviceArray whose buffer is produced on first use (`thunk() -> DeviceArray`).
+
+  Used where the next op can consume the PRODUCER's inputs directly with a fused kernel and the array itself would
+  only be written to HBM and read back once (ReLU in front of MaxPool; MaxPool's input gradient in front of ReLU's
+  backward).  `tag` / `args` tell such a consumer what the array stands for; anything else that touches `.t` / `.ptr`
+  simply triggers the producing kernel, so the rest of the engine treats it as an ordinary array.  Metadata (shape,
+  ndim, size) never materialises it."""
+  __slots__ = ('_shape', '_thunk', 'tag', 'args')
+
+  def __init__(self, shape, thunk, tag, args):
+    self._shape = tuple(int(s) for s in shape)
+    self._thunk = thunk
+    self.tag = tag
+    self.args = args
+
+  @property
+  def pending(self):
+    return self._thunk is not None
+
+  @property
+  def t(self):
+    if self._thunk is not None:
+      thunk, self._thunk = self._thunk, None
+      DeviceArray.t.__set__(self, thunk().t)
+      self.args = None
+    return DeviceArray.t.__get__(self)
+
+  @t.setter
+  def t(self, value):
+    self._thunk, self.args = None, None
+    DeviceArray.t.__set__(self, value)
+
+  @property
+  def shape(self):
+    return self._shape
+
+  @property
+  def ndim(self):
+    return len(self._shape)
+
+  @property
+  def size(self):
+    n = 1
+    for s in self._shape:
+      n *= s
+    return n
+
+  def __len__(self):
+    if not self._shape:
+      raise TypeError('len() of unsized object')
+    return self._shape[0]
+
+
+LAZY_FUSION = True   # ReLU -> MaxPool pairs run as fused kernels (set False to materialise every op's output eagerly)
+
+
 def unary(op, x, alpha=0.0):
   out = DeviceArray(_alloc(x.shape))
   B.check(B.lib.ngb_ew_unary_fwd(op, float(alpha), x.ptr, out.ptr, x.size, _st()))

@@ -128,6 +128,35 @@ def maxpool_bwd(ug, idx, xshape, k, pad, stride):
   return host(dx)
 
 
+def maxpool_relu_fwd(x, k, pad, stride):
+  """fused maxpool(relu(x)); returns None when the geometry is not supported by the fused kernel"""
+  H, W = x.shape[-2:]
+  outer = int(np.prod(x.shape[:-2]))
+  Ho, Wo = (H + 2 * pad - k[0]) // stride + 1, (W + 2 * pad - k[1]) // stride + 1
+  X = dev(x)
+  y = torch.full(x.shape[:-2] + (Ho, Wo), float('nan'), device='cuda')
+  idx = torch.full(x.shape[:-2] + (Ho, Wo), 255, device='cuda', dtype=torch.uint8)
+  B.ensure_runtime()
+  rc = lib.ngb_maxpool_relu_fwd(ptr(X), ptr(y), ptr(idx), outer, H, W, k[0], k[1], pad, stride, st())
+  if rc == B.ERR_UNSUPPORTED:
+    return None
+  B.check(rc)
+  return host(y), host(idx)
+
+
+def maxpool_relu_bwd(ug, idx, xm, k, pad, stride):
+  H, W = xm.shape[-2:]
+  outer = int(np.prod(xm.shape[:-2]))
+  U, I, X = dev(ug), dev(idx, torch.uint8), dev(xm)
+  dx = torch.full(tuple(xm.shape), float('nan'), device='cuda')
+  B.ensure_runtime()
+  rc = lib.ngb_maxpool_relu_bwd(ptr(U), ptr(I), ptr(X), ptr(dx), outer, H, W, k[0], k[1], pad, stride, 0, st())
+  if rc == B.ERR_UNSUPPORTED:
+    return None
+  B.check(rc)
+  return host(dx)
+
+
 def binary_fwd(op, a, b):
   a, b = np.asarray(a), np.asarray(b)
   out_shape = np.broadcast_shapes(a.shape, b.shape)

@@ -338,6 +338,35 @@ def test_no_pipeline_timeouts(U):
   U.call('ngb_debug_check_pipelines')
 
 
+@pytest.mark.parametrize('shape', [(64, 6, 24, 24), (33, 16, 8, 8), (5, 12, 20), (3, 2, 10, 36)])
+def test_maxpool_relu_fused_is_bit_exact(U, shape):
+  """ngb_maxpool_relu_fwd / _bwd (ReLU applied on load / ReLU mask applied on store) against the separate kernels and
+  the oracle: values, argmax indices (ties between clamped zeros included) and input gradients are bit-identical."""
+  rng = np.random.default_rng(sum(shape))
+  x = f32(rng.standard_normal(shape))
+  x[0] = -np.abs(x[0])                      # whole windows of negatives: relu makes them all-zero ties
+  x[..., ::3, ::2] = 0.0                    # exact zeros: relu gradient is 1 there (activations.py:31)
+  got = U.maxpool_relu_fwd(x, (2, 2), 0, 2)
+  assert got is not None
+  y, idx = got
+  yr, idxr = U.maxpool_fwd(np.maximum(x, 0.0), (2, 2), 0, 2)
+  assert np.array_equal(y, yr) and np.array_equal(idx, idxr)
+  yo = ops.maxpool_fwd(np.maximum(x, 0.0), (2, 2), 0, 2)
+  yo = yo[0] if isinstance(yo, tuple) else yo
+  assert np.array_equal(y, yo.astype(np.float32))
+  ug = f32(rng.standard_normal(y.shape))
+  dx = U.maxpool_relu_bwd(ug, idx, x, (2, 2), 0, 2)
+  assert dx is not None
+  ref = U.maxpool_bwd(ug, idx, x.shape, (2, 2), 0, 2) * (x >= 0)
+  assert np.array_equal(dx, ref.astype(np.float32))
+
+
+def test_maxpool_relu_fused_rejects_other_geometries(U):
+  x = np.zeros((2, 3, 9, 9))
+  assert U.maxpool_relu_fwd(x, (3, 3), 0, 3) is None
+  assert U.maxpool_relu_fwd(np.zeros((2, 3, 8, 6)), (2, 2), 0, 2) is None     # rows not 16-byte multiples
+
+
 def test_conv_errors(U):
   x, w, b = np.zeros((1, 1, 5, 5)), np.zeros((1, 1, 3, 3)), np.zeros(1)
   import torch

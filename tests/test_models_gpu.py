@@ -248,3 +248,33 @@ def test_backward_lanes_change_nothing(ng, captured):
   assert results[1][0] == results[2][0]                     # same configuration twice: bit-identical
   for a, b in zip(results[1][1:], results[2][1:]):
     assert np.array_equal(a, b)
+
+
+def test_lazy_relu_pool_fusion_changes_nothing(ng):
+  """ReLU -> MaxPool pairs run as fused kernels (the ReLU output and the pool's input gradient are never written);
+  the arithmetic is unchanged, so a LeNet-B trajectory is bit-identical with the fusion switched off."""
+  from neograd_b200 import device as D
+  from neograd_b200.configs import lenet_synthetic, train_step
+  results = []
+  for fused in (False, True):
+    prev, D.LAZY_FUSION = D.LAZY_FUSION, fused
+    try:
+      np.random.seed(0)
+      model, Xh, Yh = lenet_synthetic('b', 256)
+      X, Y = ng.tensor(Xh), ng.tensor(Yh)
+      optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
+      loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+      for _ in range(4):
+        loss = train_step(model, optim, loss_fn, X, Y)
+      results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
+    finally:
+      D.LAZY_FUSION = prev
+  assert results[0][0] == results[1][0]
+  for a, b in zip(results[0][1:], results[1][1:]):
+    assert np.array_equal(a, b)
+  # a lazily produced activation is an ordinary array for everything else
+  x = ng.tensor(np.array([[-1.0, 2.0], [0.0, -3.0]]), requires_grad=True)
+  r = ng.nn.ReLU()(x)
+  assert np.array_equal(r.data.numpy(), [[0.0, 2.0], [0.0, 0.0]]) and r.shape == (2, 2)
+  r.sum().backward()
+  assert np.array_equal(x.grad.numpy(), [[0.0, 1.0], [1.0, 0.0]])
