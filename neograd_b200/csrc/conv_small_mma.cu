@@ -31,6 +31,14 @@ __device__ __forceinline__ uint32_t lds32(uint32_t addr) {
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr));
   return v;
 }
+__device__ __forceinline__ void st_global_pred(float* p, float v, bool pred) {   // @pred st.global.f32 [p], v
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q st.global.f32 [%0], %1;\n\t}" ::"l"(p),
+      "f"(v), "r"((int)pred)
+      : "memory");
+}
 template <int I, int N, class F>
 __device__ __forceinline__ void static_for(F&& f) {     // compile-time loop: the index can be a template argument
   if constexpr (I < N) {
@@ -91,7 +99,7 @@ struct GatherGeo {
 };
 
 template <int MT, int NT, bool ACC>
-__global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __restrict__ in, const float* __restrict__ w,
+__global__ void __launch_bounds__(256, 4) conv_gather_mma_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ out,
                                                               GatherGeo g, FastDiv d_plane, FastDiv d_cols,
                                                               FastDiv d_fdiv, FastDiv d_mti, FastDiv d_npp, FastDiv d_op8,
@@ -279,22 +287,25 @@ __global__ void __launch_bounds__(384) conv_gather_mma_kernel(const float* __res
           for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a[i][0], a[i][1], a[i][2], a[i][3], b[j].x, b[j].y);
       }
 
-      // ---- epilogue: lanes of equal t hold 8 consecutive outputs of one channel -> 32-byte store segments
+      // ---- epilogue: lanes of equal t hold 8 consecutive outputs of one channel -> 32-byte store segments.
+      // One 64-bit pointer per (tile, channel column); the stores are PREDICATED (no branch per element).
 #pragma unroll
       for (int i = 0; i < MT; ++i) {
-        if (eo[i] < 0) continue;
+        const bool tile_ok = eo[i] >= 0;
+        const bool r0 = tile_ok && (full_tiles || tile_f[i] + gq < g.F), r1 = tile_ok && (full_tiles || tile_f[i] + gq + 8 < g.F);
+        float* const pt = obase + (tile_ok ? eo[i] : 0);
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {            // rows g, g+8
-          if (!full_tiles && tile_f[i] + gq + 8 * h >= g.F) continue;
+        for (int j = 0; j < NT; ++j) {
 #pragma unroll
-          for (int j = 0; j < NT; ++j) {
-#pragma unroll
-            for (int b2 = 0; b2 < 2; ++b2) {
-              if (cvalid[j][b2]) {
-                float* o = obase + (eo[i] + coff[j][b2] + 8 * h);
-                const float v = acc[i][j][2 * h + b2] + bv[j][b2];
-                if (ACC) *o += v; else *o = v;
-              }
+          for (int b2 = 0; b2 < 2; ++b2) {
+            float* const pc = pt + coff[j][b2];
+            const float bias_v = bv[j][b2];
+            if (ACC) {
+              if (cvalid[j][b2] && r0) pc[0] += acc[i][j][b2] + bias_v;
+              if (cvalid[j][b2] && r1) pc[8] += acc[i][j][2 + b2] + bias_v;
+            } else {
+              st_global_pred(pc, acc[i][j][b2] + bias_v, cvalid[j][b2] && r0);
+              st_global_pred(pc + 8, acc[i][j][2 + b2] + bias_v, cvalid[j][b2] && r1);
             }
           }
         }
@@ -343,24 +354,10 @@ static int launch_gather(const float* in, const float* w, const float* bias, flo
   int grid = 1;
   int rc = balance_images(conv_gather_mma_kernel<MT, NT, ACC>, 256, fixed, per_img, g.N, 1, gmax, corun_hint() != 0, &g.G, &grid);
   if (rc) return rc;
-  // warps: cover the G*MTI tiles of a pass (MT per warp) with as little idle tail as possible
-  const int units = g.G * g.MTI;
-  int nwarps = 8;
-  double best_eff = -1.0;
-  const int cand[] = {8, 9, 10, 12, 7, 6, 11};
-  for (int nw : cand) {
-    const int rounds = ceil_div(units, nw * MT);
-    const double eff = (double)units / ((double)rounds * nw * MT);
-    if (eff > best_eff + 1e-9) { best_eff = eff; nwarps = nw; }
-  }
+  // 8 warps at <= 64 registers: four CTAs (32 warps) per SM.  (9-12 warp blocks tile some pass sizes without an idle
+  // tail, but their register footprint drops the SM to two CTAs, which costs more than the tail.)
+  const int nwarps = 8;
   const size_t smem = fixed + (size_t)g.G * per_img;
-  if (nwarps != 8) {   // occupancy of the final block size (G stays)
-    int occ = 1;
-    NGB_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, conv_gather_mma_kernel<MT, NT, ACC>, nwarps * 32, smem));
-    if (occ < 1) occ = 1;
-    if (corun_hint() && occ > 1) occ = (occ + 1) / 2;
-    grid = g.N < kNumSMs * occ ? g.N : kNumSMs * occ;
-  }
   conv_gather_mma_kernel<MT, NT, ACC><<<grid, nwarps * 32, smem, st>>>(
       in, w, bias, out, g, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.fdiv),
       FastDiv((uint32_t)g.MTI), FastDiv((uint32_t)g.NPp), FastDiv((uint32_t)g.Op8), FastDiv((uint32_t)g.KW),
