@@ -449,7 +449,7 @@ struct RowsGeo {
   int hl, P, plane, uimg;      // staged ug: left halo, row pitch, plane pitch, image pitch (floats)
   int NPOS, NT8;               // Ho*W positions per image, tiles of 8
   int HWp, dimg;               // dx accumulator plane pitch (even) and image pitch
-  int MTC, IP;                 // channel-pair tiles, images in flight per CTA
+  int MTC, IP;                 // m-tiles of (c,kh) rows, images in flight per CTA
   int pair_ok;                 // 64-bit read-modify-write possible (W and HWp even)
 };
 
@@ -457,7 +457,7 @@ template <int KW, int OB>
 __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* __restrict__ ug, const float* __restrict__ w,
                                                                   float* __restrict__ dx, RowsGeo g, int accumulate,
                                                                   FastDiv d_w, FastDiv d_howo, FastDiv d_ho, FastDiv d_hw,
-                                                                  FastDiv d_o) {
+                                                                  FastDiv d_o, FastDiv d_c, FastDiv d_howo4, FastDiv d_ho4) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   constexpr int KS = KW * OB;
   int* boff = reinterpret_cast<int*>(smem_u);               // [NT8*8] byte offset of position n in a staged plane
@@ -470,7 +470,11 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
   const int j = warp % g.MTC, slot = warp / g.MTC;
   const int KK = g.KH * KW;
 
-  // ---- stationary A fragments: rows r -> (c = 2j + r/8, kh = r%8), k-step ks = kw*OB + ob, labels t / t+4 -> o = 8ob + t (+4)
+  // ---- stationary A fragments: rows are the (c, kh) pairs packed densely, r = c*KH + kh (tile j holds rows 16j..16j+15),
+  // k-step ks = kw*OB + ob, labels t / t+4 -> o = 8ob + t (+4)
+  const int rowa = 16 * j + gq, rowb = rowa + 8;             // this lane's two rows (fragment rows g and g+8)
+  const int ca = rowa / g.KH, kha = rowa - ca * g.KH, cb = rowb / g.KH, khb = rowb - cb * g.KH;
+  const bool oka = ca < g.C, okb = cb < g.C;
   uint32_t a[KS][4];
 #pragma unroll
   for (int kw = 0; kw < KW; ++kw)
@@ -479,10 +483,10 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
       const int ks = kw * OB + ob;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        const int c = 2 * j + (e & 1);
+        const int c = (e & 1) ? cb : ca, kh = (e & 1) ? khb : kha;
         const int o = ob * 8 + t + ((e & 2) ? 4 : 0);
         float v = 0.f;
-        if (gq < g.KH && c < g.C && o < g.O) v = __ldg(w + ((int64_t)o * g.C + c) * KK + gq * KW + kw);
+        if (c < g.C && o < g.O) v = __ldg(w + ((int64_t)o * g.C + c) * KK + kh * KW + kw);
         a[ks][e] = to_tf32(v);
       }
     }
@@ -510,29 +514,43 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
   cta_image_range(g.N, img_lo, img_cnt);
   for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.IP) {
     const int ng = min(g.IP, img_lo + img_cnt - n0);
-    // ---- stage: global [o][q][p] (p contiguous) -> smem [o][p][hl + q]
+    // ---- stage: global [o][q][p] (p contiguous) -> smem [o][p][hl + q].  The staging costs issue slots, not bandwidth
+    // (it was as many instructions as the MMA phase): 128-bit loads along p, one index decomposition per four elements.
     {
       const float* src = ug + (int64_t)n0 * g.O * HoWo;
       const int raw = ng * g.O * HoWo;
+      if ((g.Ho & 3) == 0 && (reinterpret_cast<uintptr_t>(src) & 15u) == 0) {
+        const int pl_stride_pad = (g.uimg - g.O * g.plane);       // gap between images in the staged copy (padded planes)
+#pragma unroll 2
+        for (int e4 = tid; e4 < (raw >> 2); e4 += nthr) {
+          const float4 v = ld_stream4(src + 4 * (int64_t)e4);
+          uint32_t pl, f4, q, p4, img, o;
+          d_howo4.divmod((uint32_t)e4, pl, f4);                     // pl = img*O + o
+          d_ho4.divmod(f4, q, p4);
+          d_o.divmod(pl, img, o);
+          uint32_t* d = us + pl * g.plane + img * pl_stride_pad + (p4 * 4) * g.P + g.hl + q;
+          d[0] = to_tf32(v.x); d[g.P] = to_tf32(v.y); d[2 * g.P] = to_tf32(v.z); d[3 * g.P] = to_tf32(v.w);
+        }
+      } else {
 #pragma unroll 4
-      for (int e = tid; e < raw; e += nthr) {
-        uint32_t pl, f, q, p;
-        d_howo.divmod((uint32_t)e, pl, f);                 // pl = img*O + o
-        d_ho.divmod(f, q, p);
-        uint32_t img, o;
-        d_o.divmod(pl, img, o);
-        us[img * g.uimg + o * g.plane + p * g.P + g.hl + q] = to_tf32(__ldg(src + e));
+        for (int e = tid; e < raw; e += nthr) {
+          uint32_t pl, f, q, p;
+          d_howo.divmod((uint32_t)e, pl, f);                 // pl = img*O + o
+          d_ho.divmod(f, q, p);
+          uint32_t img, o;
+          d_o.divmod(pl, img, o);
+          us[img * g.uimg + o * g.plane + p * g.P + g.hl + q] = to_tf32(__ldg(src + e));
+        }
       }
     }
     __syncthreads();
 
     if (slot < ng) {
-      const int c0 = 2 * j;
-      // this lane's two accumulator rows: (c0, kh = gq) and (c0 + 1, kh = gq)
-      const bool row_ok = gq < g.KH;
-      const bool c_ok0 = c0 < g.C, c_ok1 = c0 + 1 < g.C;
-      const int rbase = (gq - g.pad) * g.W + 2 * t;          // element offset inside a channel plane, before + n0
-      float* const dx_c0 = dxs + slot * g.dimg + c0 * g.HWp;
+      // Every m-tile (warp j) adds into ITS OWN copy of the image's dx accumulator, so no two warps ever touch the same
+      // word (a channel's kh rows may straddle two tiles); the copies are summed when the image is written out.
+      float* const dx_j = dxs + (slot * g.MTC + j) * g.C * g.HWp;
+      float* const dxa = dx_j + ca * g.HWp + (kha - g.pad) * g.W + 2 * t;    // + n0: element (c, h = p + kh - pad, w)
+      float* const dxb = dx_j + cb * g.HWp + (khb - g.pad) * g.W + 2 * t;
       // no padding, whole tiles, even W: every (row, position) of a tile lands inside the plane, 8-byte aligned
       const bool fast = g.pad == 0 && (g.NPOS & 7) == 0 && g.pair_ok;
       uint32_t base[OB][2];                                  // planes of o = 8ob + t and o + 4 (byte addresses)
@@ -543,21 +561,22 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
       }
       auto shift_add = [&](const float (&acc)[4], int nt) {
         // T[(c,kh)][n] -> dxs[c][(p + kh - pad)*W + w] = dxs[c][(kh - pad)*W + n]
-        if (row_ok) {
-          const int e0 = rbase + nt * 8;
-          if (fast) {
-            if (c_ok0) { float2* q2 = reinterpret_cast<float2*>(dx_c0 + e0); float2 o2 = *q2; o2.x += acc[0]; o2.y += acc[1]; *q2 = o2; }
-            if (c_ok1) { float2* q2 = reinterpret_cast<float2*>(dx_c0 + g.HWp + e0); float2 o2 = *q2; o2.x += acc[2]; o2.y += acc[3]; *q2 = o2; }
-          } else {
-            const int nb = nt * 8 + 2 * t;
-            const int h0 = prow[nb] + gq - g.pad, h1 = prow[nb + 1] + gq - g.pad;
-            const bool v0 = nb < g.NPOS && h0 >= 0 && h0 < g.H, v1 = nb + 1 < g.NPOS && h1 >= 0 && h1 < g.H;
-            float* q0 = dx_c0 + e0;
-            float* q1 = q0 + g.HWp;
-            if (c_ok0 && v0) q0[0] += acc[0];
-            if (c_ok0 && v1) q0[1] += acc[1];
-            if (c_ok1 && v0) q1[0] += acc[2];
-            if (c_ok1 && v1) q1[1] += acc[3];
+        if (fast) {
+          if (oka) { float2* q2 = reinterpret_cast<float2*>(dxa + nt * 8); float2 o2 = *q2; o2.x += acc[0]; o2.y += acc[1]; *q2 = o2; }
+          if (okb) { float2* q2 = reinterpret_cast<float2*>(dxb + nt * 8); float2 o2 = *q2; o2.x += acc[2]; o2.y += acc[3]; *q2 = o2; }
+        } else {
+          const int nb = nt * 8 + 2 * t;
+          const int p0 = prow[nb], p1 = prow[nb + 1];
+          const bool n0ok = nb < g.NPOS, n1ok = nb + 1 < g.NPOS;
+          if (oka) {
+            const int h0 = p0 + kha - g.pad, h1 = p1 + kha - g.pad;
+            if (n0ok && h0 >= 0 && h0 < g.H) dxa[nt * 8] += acc[0];
+            if (n1ok && h1 >= 0 && h1 < g.H) dxa[nt * 8 + 1] += acc[1];
+          }
+          if (okb) {
+            const int h0 = p0 + khb - g.pad, h1 = p1 + khb - g.pad;
+            if (n0ok && h0 >= 0 && h0 < g.H) dxb[nt * 8] += acc[2];
+            if (n1ok && h1 >= 0 && h1 < g.H) dxb[nt * 8 + 1] += acc[3];
           }
         }
         __syncwarp();   // the next tile's read-modify-write may hit addresses other lanes just wrote
@@ -591,29 +610,37 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
       }
     }
     __syncthreads();
-    // ---- write the accumulators out (coalesced) and clear them for the next pass
+    // ---- write the accumulators out (coalesced; the per-m-tile copies are summed in a fixed order) and clear them
     {
       const int HW = g.H * g.W;
       float* dst = dx + (int64_t)n0 * g.C * HW;
       const int total = ng * g.C * HW;
-      if ((HW & 3) == 0 && (g.HWp & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
+      const int copy = g.C * g.HWp;                          // one m-tile's copy of an image
+      if ((HW & 3) == 0 && (reinterpret_cast<uintptr_t>(dst) & 15u) == 0) {
         for (int e4 = tid; e4 < (total >> 2); e4 += nthr) {
-          uint32_t pl, f;
+          uint32_t pl, f, img, c;
           d_hw.divmod((uint32_t)e4 * 4u, pl, f);            // pl = img*C + c
-          float4* sp = reinterpret_cast<float4*>(dxs + pl * g.HWp + f);
-          float4 v = *sp;
-          *sp = make_float4(0.f, 0.f, 0.f, 0.f);
+          d_c.divmod(pl, img, c);
+          float* sp = dxs + (img * g.MTC) * copy + c * g.HWp + f;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          for (int m = 0; m < g.MTC; ++m) {
+            float4* s4 = reinterpret_cast<float4*>(sp + m * copy);
+            const float4 u = *s4;
+            *s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+          }
           float4* gp = reinterpret_cast<float4*>(dst + 4 * (int64_t)e4);
           if (accumulate) { const float4 o4 = *gp; v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w; }
           *gp = v;
         }
       } else {
         for (int e = tid; e < total; e += nthr) {
-          uint32_t pl, f;
+          uint32_t pl, f, img, c;
           d_hw.divmod((uint32_t)e, pl, f);
-          float* sp = dxs + pl * g.HWp + f;
-          const float v = *sp;
-          *sp = 0.f;
+          d_c.divmod(pl, img, c);
+          float* sp = dxs + (img * g.MTC) * copy + c * g.HWp + f;
+          float v = 0.f;
+          for (int m = 0; m < g.MTC; ++m) { v += sp[m * copy]; sp[m * copy] = 0.f; }
           dst[e] = accumulate ? dst[e] + v : v;
         }
       }
@@ -640,7 +667,9 @@ static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const R
   const int grid = (int)(passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ);
   conv_dgrad_rows_mma_kernel<KW, OB><<<grid, threads, smem, st>>>(ug, w, dx, g, accumulate, FastDiv((uint32_t)g.W),
                                                                    FastDiv((uint32_t)(g.Ho * g.Wo)), FastDiv((uint32_t)g.Ho),
-                                                                   FastDiv((uint32_t)(g.H * g.W)), FastDiv((uint32_t)g.O));
+                                                                   FastDiv((uint32_t)(g.H * g.W)), FastDiv((uint32_t)g.O), FastDiv((uint32_t)g.C),
+                                                                   FastDiv((uint32_t)((g.Ho * g.Wo) / 4 > 0 ? (g.Ho * g.Wo) / 4 : 1)),
+                                                                   FastDiv((uint32_t)(g.Ho / 4 > 0 ? g.Ho / 4 : 1)));
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
@@ -661,8 +690,8 @@ int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C
   g.NPOS = Ho * W;
   g.NT8 = ceil_div(g.NPOS, 8);
   g.HWp = (H * W + 3) & ~3;
-  g.dimg = C * g.HWp;
-  g.MTC = ceil_div(C, 2);
+  g.MTC = ceil_div(C * KH, 16);                  // (c, kh) rows packed densely into 16-row tiles
+  g.dimg = g.MTC * C * g.HWp;                    // one accumulator copy per m-tile
   g.pair_ok = (W % 2 == 0) ? 1 : 0;
   // the last position tile reads up to 7 positions past NPOS at offset 0 (valid); every real read stays inside the plane:
   // max col = W - 1 + KW - 1 = Wo + 2*hl - 1 < P
