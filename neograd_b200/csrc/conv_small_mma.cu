@@ -862,27 +862,37 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
     }
     __syncthreads();
 
-    const int units = ng * g.KSI;
-    for (int u = kq; u < units; u += g.KS) {
-      uint32_t img, ks;
-      d_ksi.divmod((uint32_t)u, img, ks);
-      const uint32_t f0b = ks * 32u + (uint32_t)t * 8u;                      // byte offset of position f0 + 2t
-      const uint2 pp = lds64(po_sa + f0b);
-      const uint32_t xb = xs_sa + img * ximg_b;
-      const uint32_t ub = us_sa + img * uimg_b + f0b;
-      uint2 b[NT];
-#pragma unroll
-      for (int j = 0; j < NT; ++j) b[j] = lds64(ub + (uint32_t)j * up8_b);
-      uint32_t a[MTW][4];
+    // warp kq takes k-steps kq, kq+KS, ... of EVERY image (no index division in the loop; per-image bases are hoisted:
+    // the kernel is issue-bound, every integer instruction in this loop costs as much as a load)
+    for (int img = 0; img < ng; ++img) {
+      uint32_t xa0[MTW], xa1[MTW];
 #pragma unroll
       for (int i = 0; i < MTW; ++i) {
-        a[i][0] = lds32(xb + M0[i] + pp.x); a[i][1] = lds32(xb + M1[i] + pp.x);
-        a[i][2] = lds32(xb + M0[i] + pp.y); a[i][3] = lds32(xb + M1[i] + pp.y);
+        xa0[i] = xs_sa + (uint32_t)img * ximg_b + (uint32_t)M0[i];
+        xa1[i] = xs_sa + (uint32_t)img * ximg_b + (uint32_t)M1[i];
       }
+      uint32_t pq = po_sa + (uint32_t)kq * 32u + (uint32_t)t * 8u;            // &poff[8*ks + 2t], ks = kq
+      uint32_t ub = us_sa + (uint32_t)img * uimg_b + (uint32_t)kq * 32u + (uint32_t)t * 8u;
+      const uint32_t kstep_b = (uint32_t)g.KS * 32u;
+#pragma unroll 2
+      for (int ks = kq; ks < g.KSI; ks += g.KS) {
+        const uint2 pp = lds64(pq);
+        uint2 b[NT];
 #pragma unroll
-      for (int i = 0; i < MTW; ++i)
+        for (int j = 0; j < NT; ++j) b[j] = lds64(ub + (uint32_t)j * up8_b);
+        pq += kstep_b;
+        ub += kstep_b;
+        uint32_t a[MTW][4];
 #pragma unroll
-        for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a[i][0], a[i][1], a[i][2], a[i][3], b[j].x, b[j].y);
+        for (int i = 0; i < MTW; ++i) {
+          a[i][0] = lds32(xa0[i] + pp.x); a[i][1] = lds32(xa1[i] + pp.x);
+          a[i][2] = lds32(xa0[i] + pp.y); a[i][3] = lds32(xa1[i] + pp.y);
+        }
+#pragma unroll
+        for (int i = 0; i < MTW; ++i)
+#pragma unroll
+          for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a[i][0], a[i][1], a[i][2], a[i][3], b[j].x, b[j].y);
+      }
     }
   }
 
