@@ -193,6 +193,11 @@ def call_work(name, a):
 
 # --------------------------------------------------------------------------------------------- device arm
 def run_device(args):
+  # stdout carries exactly ONE JSON line: everything else that writes to fd 1 (NCCL prints a version banner there at
+  # communicator creation) goes to stderr; the result is written to the saved descriptor at the end.
+  sys.stdout.flush()
+  json_fd = os.dup(1)
+  os.dup2(2, 1)
   import torch
   import neograd_b200 as ng
   from neograd_b200 import _backend as B
@@ -205,7 +210,6 @@ def run_device(args):
   local = int(os.environ.get('LOCAL_RANK', '0'))
   torch.cuda.set_device(local)
   if world > 1:
-    os.environ['NCCL_DEBUG'] = 'WARN'    # the image's default (VERSION) prints a banner on stdout: keep it to ONE JSON line
     dist.init('nccl')
   pk = peaks()
   kind = args.workload[-1]
@@ -431,7 +435,8 @@ def run_device(args):
       'eager': {'value': total_samples / (eager_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': eager_ms / args.steps},
       'roofline': roofline, 'cpu_baseline': cpu, 'kernel_breakdown': breakdown,
     }
-    print(json.dumps(out), flush=True)
+    sys.stdout.flush()
+    os.write(json_fd, (json.dumps(out) + '\n').encode())
   if world > 1:
     # NCCL teardown after a graph-captured collective was seen to hang on exit: synchronise, then leave without running
     # the communicator destructors (the process is ending anyway).
