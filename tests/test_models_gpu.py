@@ -165,6 +165,45 @@ def test_gan_choreography_small(ng):
   assert model.parameters()[0].momentum_grad.shape == model.parameters()[0].shape
 
 
+def test_c4_gan_matches_reference_trajectory(ng):
+  """Config C4 at notebook scale against the UNMODIFIED reference's recorded run (tests/golden/step_c4_gan.npz, generated
+  by oracle/gen_golden_gan.py): three generator + discriminator iterations with freeze / unfreeze,
+  zero_grad(all_members=True), BCE and two Adam optimizers sharing the moments stored on the Params."""
+  from neograd_b200.configs import GAN, set_params
+  nn = ng.nn
+  g = load_golden('step_c4_gan')
+  np.random.seed(0)
+  model = GAN(64, 50, 25)
+  n = len(model.parameters())
+  set_params(model, [g[f'init_{i}'] for i in range(n)])
+  real = ng.tensor(g['real'])
+  optim_g, optim_d = nn.optim.Adam(model.parameters(), 5e-3), nn.optim.Adam(model.parameters(), 5e-3)
+  loss_fn = nn.loss.BCE()
+  ones, zeros = ng.tensor(np.ones((200, 1))), ng.tensor(np.zeros((200, 1)))
+  lg, ld = [], []
+  for it in range(len(g['losses_g'])):
+    model.discriminator.freeze()
+    optim_g.zero_grad(all_members=True)
+    loss_g = loss_fn(model(ng.tensor(g['noise_g'][it])), ones)
+    loss_g.backward()
+    optim_g.step()
+    model.discriminator.unfreeze()
+    model.generator.freeze()
+    optim_d.zero_grad(all_members=True)
+    fake = model.generator(ng.tensor(g['noise_d'][it]))
+    loss_d = loss_fn(model.discriminator(real), ones) + loss_fn(model.discriminator(fake), zeros)
+    loss_d.backward()
+    optim_d.step()
+    model.generator.unfreeze()
+    lg.append(float(loss_g.data))
+    ld.append(float(loss_d.data))
+  assert dist(lg, g['losses_g']) < 1e-4, (lg, g['losses_g'])
+  assert dist(ld, g['losses_d']) < 1e-4, (ld, g['losses_d'])
+  for i, p in enumerate(model.parameters()):
+    d = dist(p.data.numpy(), g[f'final_{i}'])
+    assert d < 2e-3, (i, d)
+
+
 def test_grad_check_passes_on_device(ng):
   """neograd's acceptance tool (autograd/utils.py:195-234) with device-appropriate epsilon."""
   from neograd_b200.configs import MLPCircles
