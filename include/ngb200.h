@@ -180,6 +180,17 @@ int ngb_momentum_step(float* p, const float* g, float* m, int64_t n, double lr, 
 int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, double lr, double beta, double epsilon,
                      double grad_scale, ngb_stream_t stream);                               /* optim.py:112-118, 134-140 */
 
+/* ---- data parallel over NVLink peer memory (new) -------------------------------------------------------
+ * Every rank keeps its flat gradient buffer in symmetric (peer-mapped) memory.  `peer_ptrs_dev` / `flag_ptrs_dev` are DEVICE
+ * arrays of `world` pointers: rank r's gradient buffer / rank r's flag words (>= world uint32, zero-initialised).
+ * ngb_xgpu_barrier: rank publishes (*epoch_dev + 1) into every peer's flag word [rank] and waits until all peers have
+ *   published it here; *epoch_dev is advanced by the kernel itself, so a captured step replays correctly.  Bounded wait.
+ * ngb_xgpu_reduce_sum: out[i] = sum over ranks (in rank order) of peer r's buffer[i], loaded over NVLink.
+ * Sequence per step: barrier (all gradients final) -> reduce_sum -> barrier (all peers have read) -> optimizer on `out`. */
+int ngb_xgpu_barrier(const void* flag_ptrs_dev, int rank, int world, uint32_t* epoch_dev, ngb_stream_t stream);
+int ngb_xgpu_reduce_sum(const void* peer_ptrs_dev, float* out, int64_t n, int world, ngb_stream_t stream);
+int ngb_xgpu_check(void);   /* NGB_ERR_CUDA if a cross-GPU barrier timed out since the last call (synchronises) */
+
 #ifdef __cplusplus
 }
 #endif

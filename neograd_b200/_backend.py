@@ -55,6 +55,9 @@ SIGNATURES = {
   'ngb_set_default_engine': ([c_int], c_int),
   'ngb_set_lane': ([c_int], c_int),
   'ngb_set_corun': ([c_int], c_int),
+  'ngb_xgpu_barrier': ([_P, c_int, c_int, _P, _S], c_int),
+  'ngb_xgpu_reduce_sum': ([_P, _P, c_int64, c_int, _S], c_int),
+  'ngb_xgpu_check': ([], c_int),
   'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
   'ngb_launch_count': ([], c_int64),
   'ngb_gemm': ([c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _S], c_int),
@@ -236,7 +239,7 @@ class profile_calls:
   `records` is a list of (name, args, start_event, end_event); call `summary()` after the block (it synchronises).
   Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
   SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
-          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane', 'ngb_set_corun')
+          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane', 'ngb_set_corun', 'ngb_xgpu_check')
 
   def __enter__(self):
     import torch

@@ -33,7 +33,15 @@ class Arena:
       n += (p.data.size + 3) & ~3
     self.numel = n
     self.data = DeviceArray.zeros((max(n, 1),))
-    self.grad = DeviceArray.zeros((max(n, 1),))
+    # data parallel on one node: the gradient buffer lives in symmetric (peer-mapped) memory and the ranks sum each
+    # other's buffers over NVLink themselves (distributed.PeerExchange); otherwise a plain buffer + NCCL allreduce
+    self.exchange = dist.PeerExchange.create(n)
+    if self.exchange is not None:
+      self.grad = DeviceArray(self.exchange.grad[:max(n, 1)])
+      self.grad_sum = DeviceArray(self.exchange.summed[:max(n, 1)])
+    else:
+      self.grad = DeviceArray.zeros((max(n, 1),))
+      self.grad_sum = self.grad
     self.state = {}
     for p, off in zip(self.params, self.offsets):
       size, shape = p.data.size, p.shape
@@ -107,10 +115,15 @@ class Optimizer:
       param.zero_grad()
 
   def _sync_grads(self):
-    """Data parallel: sum the flat gradient buffer over ranks (one NCCL allreduce over NVLink); returns grad_scale."""
-    self.arena.prepare_grads()
+    """Data parallel: sum the flat gradient buffer over ranks -- peer-memory exchange over NVLink (the summed gradient is
+    then `arena.grad_sum`), or one NCCL allreduce in place when peer memory is unavailable; returns grad_scale."""
+    a = self.arena
+    a.prepare_grads()
     if dist.is_initialized() and dist.world_size() > 1:
-      dist.all_reduce_sum(self.arena.grad)
+      if a.exchange is not None:
+        a.exchange.run(a.numel, _st())
+      else:
+        dist.all_reduce_sum(a.grad)
       return 1.0 / dist.world_size()
     return 1.0
 
@@ -125,7 +138,7 @@ class GD(Optimizer):
     gs = self._sync_grads()
     a = self.arena
     for b, e in a.ranges():
-      B.check(B.lib.ngb_sgd_step(_off(a.data, b), _off(a.grad, b), e - b, self.lr, gs, _st()))
+      B.check(B.lib.ngb_sgd_step(_off(a.data, b), _off(a.grad_sum, b), e - b, self.lr, gs, _st()))
 
   def __repr__(self):
     return f'GD(params={self.params}, lr={self.lr})'
@@ -148,7 +161,7 @@ class Momentum(Optimizer):
     gs = self._sync_grads()
     a = self.arena
     for b, e in a.ranges():
-      B.check(B.lib.ngb_momentum_step(_off(a.data, b), _off(a.grad, b), _off(self._m, b), e - b, self.lr, self.beta, gs, _st()))
+      B.check(B.lib.ngb_momentum_step(_off(a.data, b), _off(a.grad_sum, b), _off(self._m, b), e - b, self.lr, self.beta, gs, _st()))
 
   def __repr__(self):
     return f'Momentum(params={self.params}, lr={self.lr}, beta={self.beta})'
@@ -172,7 +185,7 @@ class RMSProp(Optimizer):
     gs = self._sync_grads()
     a = self.arena
     for b, e in a.ranges():
-      B.check(B.lib.ngb_rmsprop_step(_off(a.data, b), _off(a.grad, b), _off(self._r, b), e - b, self.lr, self.beta,
+      B.check(B.lib.ngb_rmsprop_step(_off(a.data, b), _off(a.grad_sum, b), _off(self._r, b), e - b, self.lr, self.beta,
                                      self.epsilon, gs, _st()))
 
   def __repr__(self):
@@ -204,7 +217,7 @@ class Adam(Optimizer):
     tick = 1
     t_ptr = ctypes.c_void_p(self._t_dev.data_ptr())
     for b, e in a.ranges():
-      B.check(B.lib.ngb_adam_step_dev(_off(a.data, b), _off(a.grad, b), _off(self._m, b), _off(self._v, b), e - b, self.lr,
+      B.check(B.lib.ngb_adam_step_dev(_off(a.data, b), _off(a.grad_sum, b), _off(self._m, b), _off(self._v, b), e - b, self.lr,
                                       self.beta1, self.beta2, self.epsilon, t_ptr, tick, gs, _st()))
       tick = 0
 
