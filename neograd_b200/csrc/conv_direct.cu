@@ -263,7 +263,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_direct_kernel(const float* __r
 // LSU-bound).  Forward: outputs run along p (neograd order), window slides along kh.  Data gradient: outputs run along
 // w, window slides along kw over the un-scrambled upstream gradient.
 constexpr int RT = 8;   // outputs per thread along the contiguous axis
-constexpr int CT = 4;   // channels per thread
+// CT = output channels per thread: 4 for multi-channel layers, 1 for neograd's single-filter Conv2D (conv.py:131-152),
+// where a 4-wide channel tile would spend three quarters of its FMAs and weight loads on padding
 
 struct SmallGeo {
   int N, Cin, Cout;      // input / output channels of THIS pass (dgrad: Cin = O, Cout = C)
@@ -279,6 +280,7 @@ struct SmallGeo {
 // out[n][co][ja][jb] (jb contiguous).  fprop: (ja, jb) = (q, p); staged input rows = w, cols = h?  -- see the two wrappers:
 // the kernel itself only knows: out[ja][jb] = sum_{ci, ka, kb} in_s[ci][ja + ka][jb + kb] * wts[ci][ka][kb][co]
 // where in_s is the staged plane with its CONTIGUOUS axis along jb.
+template <int CT>
 __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict__ in, const float* __restrict__ wts_g,
                                                          const float* __restrict__ bias, float* __restrict__ out, SmallGeo g,
                                                          int accumulate, FastDiv d_cols, FastDiv d_plane, FastDiv d_tpi,
@@ -303,14 +305,33 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict
     }
     const int raw = ng * g.Cin * g.in_plane;
     const float* src = in + (int64_t)n0 * g.Cin * g.in_plane;
+    // (the staging is paid in issue slots: 128-bit loads and one index decomposition per four elements when rows allow)
+    const bool vec4 = (g.in_cols & 3) == 0 && ((reinterpret_cast<uintptr_t>(src) & 15u) == 0);
+    if (vec4) {
+#pragma unroll 2
+      for (int e4 = t; e4 < (raw >> 2); e4 += 256) {
+        uint32_t pl, f, r, c;
+        d_plane.divmod((uint32_t)e4 * 4u, pl, f);          // pl = image*Cin + ci
+        d_cols.divmod(f, r, c);                              // raw plane is [in_rows][in_cols], cols contiguous
+        const float4 v = ld_stream4(src + 4 * (int64_t)e4);
+        if (g.transpose_in) {                                // [q][p] -> staged [p][q]
+          float* d = sx + pl * plane_s + (c + g.pad_a) * g.Bx + r + g.pad_b;
+          d[0] = v.x; d[g.Bx] = v.y; d[2 * g.Bx] = v.z; d[3 * g.Bx] = v.w;
+        } else {
+          float* d = sx + pl * plane_s + (r + g.pad_a) * g.Bx + c + g.pad_b;
+          d[0] = v.x; d[1] = v.y; d[2] = v.z; d[3] = v.w;
+        }
+      }
+    } else {
 #pragma unroll 4
-    for (int e = t; e < raw; e += 256) {
-      uint32_t pl, f, r, c;
-      d_plane.divmod(e, pl, f);          // pl = image*Cin + ci
-      d_cols.divmod(f, r, c);            // raw plane is [in_rows][in_cols], cols contiguous
-      const float v = __ldg(src + e);
-      if (g.transpose_in) sx[pl * plane_s + (c + g.pad_a) * g.Bx + r + g.pad_b] = v;   // [q][p] -> staged [p][q]
-      else sx[pl * plane_s + (r + g.pad_a) * g.Bx + c + g.pad_b] = v;
+      for (int e = t; e < raw; e += 256) {
+        uint32_t pl, f, r, c;
+        d_plane.divmod(e, pl, f);          // pl = image*Cin + ci
+        d_cols.divmod(f, r, c);            // raw plane is [in_rows][in_cols], cols contiguous
+        const float v = __ldg(src + e);
+        if (g.transpose_in) sx[pl * plane_s + (c + g.pad_a) * g.Bx + r + g.pad_b] = v;   // [q][p] -> staged [p][q]
+        else sx[pl * plane_s + (r + g.pad_a) * g.Bx + c + g.pad_b] = v;
+      }
     }
     __syncthreads();
     // ---- compute: thread <-> (image, co group, ja, jb block)
@@ -338,13 +359,19 @@ __global__ void __launch_bounds__(256) conv_small_kernel(const float* __restrict
 #pragma unroll
             for (int i = 0; i < RT - 1; ++i) win[i] = win[i + 1];
             win[RT - 1] = row[kb + RT - 1];
-            const float4 w4 = *reinterpret_cast<const float4*>(wr + kb * g.co_groups * CT);
+            if (CT == 4) {
+              const float4 w4 = *reinterpret_cast<const float4*>(wr + kb * g.co_groups * CT);
 #pragma unroll
-            for (int i = 0; i < RT; ++i) {
-              acc[0][i] = fmaf(win[i], w4.x, acc[0][i]);
-              acc[1][i] = fmaf(win[i], w4.y, acc[1][i]);
-              acc[2][i] = fmaf(win[i], w4.z, acc[2][i]);
-              acc[3][i] = fmaf(win[i], w4.w, acc[3][i]);
+              for (int i = 0; i < RT; ++i) {
+                acc[0][i] = fmaf(win[i], w4.x, acc[0][i]);
+                acc[1 % CT][i] = fmaf(win[i], w4.y, acc[1 % CT][i]);
+                acc[2 % CT][i] = fmaf(win[i], w4.z, acc[2 % CT][i]);
+                acc[3 % CT][i] = fmaf(win[i], w4.w, acc[3 % CT][i]);
+              }
+            } else {
+              const float w1 = wr[kb * g.co_groups * CT];
+#pragma unroll
+              for (int i = 0; i < RT; ++i) acc[0][i] = fmaf(win[i], w1, acc[0][i]);
             }
           }
         }
@@ -418,6 +445,7 @@ static int conv_small(const float* in, const float* w, const float* bias, float*
   g.transpose_in = 1;
   g.pad_a = padA; g.pad_b = padB;
   g.in_plane = g.in_rows * g.in_cols;
+  const int CT = g.Cout == 1 ? 1 : 4;
   g.co_groups = ceil_div(g.Cout, CT);
   g.jb_blocks = ceil_div(g.JB, RT);
   // the sliding window reads RT + KB - 1 columns from jb0: keep that inside the staged row
@@ -440,9 +468,14 @@ static int conv_small(const float* in, const float* w, const float* bias, float*
   NGB_LAUNCH_CHECK();
   const int64_t passes = ceil_div<int64_t>(g.N, g.G);
   const int grid = (int)(passes < (int64_t)kNumSMs * 4 ? passes : (int64_t)kNumSMs * 4);
-  conv_small_kernel<<<grid, 256, smem, st>>>(in, wp, bias, out, g, accumulate, FastDiv((uint32_t)g.in_cols),
-                                            FastDiv((uint32_t)g.in_plane), FastDiv((uint32_t)g.tpi), FastDiv((uint32_t)g.jb_blocks),
-                                            FastDiv((uint32_t)g.JA));
+  if (CT == 1)
+    conv_small_kernel<1><<<grid, 256, smem, st>>>(in, wp, bias, out, g, accumulate, FastDiv((uint32_t)g.in_cols),
+                                                 FastDiv((uint32_t)g.in_plane), FastDiv((uint32_t)g.tpi),
+                                                 FastDiv((uint32_t)g.jb_blocks), FastDiv((uint32_t)g.JA));
+  else
+    conv_small_kernel<4><<<grid, 256, smem, st>>>(in, wp, bias, out, g, accumulate, FastDiv((uint32_t)g.in_cols),
+                                                 FastDiv((uint32_t)g.in_plane), FastDiv((uint32_t)g.tpi),
+                                                 FastDiv((uint32_t)g.jb_blocks), FastDiv((uint32_t)g.JA));
   NGB_LAUNCH_CHECK();
   *done = true;
   return NGB_OK;
