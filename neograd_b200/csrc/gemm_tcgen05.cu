@@ -321,7 +321,14 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   if (!aligned16(A) || !aligned16(B)) return fail(NGB_ERR_UNSUPPORTED, "tcgen05 GEMM needs 16-byte aligned operands");
   const int a_mn = transA ? 1 : 0;  // A stored [K,M] (M contiguous) -> MN-major
   const int b_mn = transB ? 0 : 1;  // B stored [K,N] (N contiguous) -> MN-major; stored [N,K] -> K-major
-  const int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  // widest tile that still gives the grid about a full wave of CTAs: a 256-wide tile on an 8192 x 256 output leaves
+  // 64 CTAs for 148 SMs (and needs split-K plus a reduce pass to fill them), two 128-wide tiles per row do not
+  int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
+  {
+    const int64_t tm = ceil_div<int64_t>(M, BLOCK_M);
+    while (BN > 64 && tm * ceil_div<int64_t>(N, BN) < (3 * kNumSMs) / 4 && ceil_div<int64_t>(N, BN / 2) > ceil_div<int64_t>(N, BN))
+      BN /= 2;
+  }
 
   CUtensorMap ta, tb;
   // An MN-major operand whose MN extent is a multiple of 32 is described as {32, K, MN/32} (outer stride 128 B) so that a
