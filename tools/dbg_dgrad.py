@@ -1,3 +1,5 @@
+"""Times ngb_conv_dgrad on the LeNet-B conv2 shape (events + CUPTI kernel durations); used for phase ablations of the
+row-decomposed kernel (the phase times were additive, i.e. the kernel is issue-bound)."""
 import ctypes, os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
