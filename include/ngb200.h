@@ -100,6 +100,18 @@ int ngb_conv_wgrad(const float* ug, const float* x, float* dw,
 int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo,
                    int accumulate, ngb_stream_t stream);                                    /* conv.py:323-327, 198-199 */
 
+/* Conv -> ReLU -> MaxPool(2x2, stride 2) blocks, backward: the gradient of the convolution's output is three quarters
+ * zeros (one cell per pooling window) and never has to exist in HBM.  ngb_conv_wgrad_pooled computes conv.py:311-321 from
+ * the pool's upstream gradient ug_pool, the pool's output y_pool, its argmax indices idx and the conv output z (= the ReLU's
+ * input): mask and scatter happen in the kernel's shared memory.  ngb_maxpool_relu_mask writes the compact masked gradient
+ * gm[e] = ug_pool[e] * relu'(z at the argmax); the bias gradient (conv.py:323-327) is ngb_conv_bgrad(gm, ..., HoWo/4).
+ * NGB_ERR_UNSUPPORTED -> materialise the gradient with ngb_maxpool_relu_bwd and use ngb_conv_wgrad. */
+int ngb_maxpool_relu_mask(const float* ug_pool, const float* y_pool, const float* z, float* gm, int64_t outer, int64_t H,
+                          int64_t W, ngb_stream_t stream);
+int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* x,
+                          float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                          int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);
+
 /* ---- MaxPool2D / MaxPool3D: neograd/autograd/ops/conv.py:362-542 ------------------------------------------- */
 /* x (outer,H,W) with outer = N or N*C.  y and idx (uint8, position of the FIRST maximum inside the zero-padded
  * window, row-major in the window; np.argmax conv.py:424/523) are (outer,Ho,Wo) in neograd order.  idx may be NULL. */

@@ -69,6 +69,8 @@ SIGNATURES = {
   'ngb_maxpool_bwd': ([_P, _P, _P] + [c_int64] * 7 + [c_int, _S], c_int),
   'ngb_maxpool_relu_fwd': ([_P, _P, _P] + [c_int64] * 7 + [_S], c_int),
   'ngb_maxpool_relu_bwd': ([_P, _P, _P, _P] + [c_int64] * 7 + [c_int, _S], c_int),
+  'ngb_maxpool_relu_mask': ([_P, _P, _P, _P] + [c_int64] * 3 + [_S], c_int),
+  'ngb_conv_wgrad_pooled': ([_P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
   'ngb_ew_binary_fwd': ([c_int, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, _S], c_int),
   'ngb_ew_binary_bwd': ([c_int, c_int, _P, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, c_int, _S], c_int),
   'ngb_ew_unary_fwd': ([c_int, c_float, _P, _P, c_int64, _S], c_int),

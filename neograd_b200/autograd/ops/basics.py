@@ -112,7 +112,7 @@ class _Unary(Operation):
     def into(ug, dst, accumulate):
       if op == B.RELU and isinstance(ug, D.LazyArray) and ug.pending and ug.tag == 'maxpool_bwd':
         # upstream gradient = input gradient of a MaxPool that has not been written yet: route + mask in one kernel
-        pug, idx, outer, H, W, KH, KW, pad, stride = ug.args
+        pug, idx, outer, H, W, KH, KW, pad, stride, _ = ug.args
         if dst is None:
           dst, accumulate = D.DeviceArray.empty(x.shape), False
         rc = B.lib.ngb_maxpool_relu_bwd(pug.ptr, ctypes.c_void_p(idx.data_ptr()), x.ptr, dst.ptr, outer, H, W, KH, KW, pad, stride,
@@ -125,7 +125,19 @@ class _Unary(Operation):
         return D.unary_bwd(op, x, ug, alpha)
       B.check(B.lib.ngb_ew_unary_bwd(op, float(alpha), x.ptr, ug.ptr, dst.ptr, x.size, int(accumulate), D._st()))
       return dst
-    tens.set_grad_fn(GradFn(into))
+
+    def lazy(ug):
+      # ReLU behind a still-deferred 2x2 / stride 2 MaxPool backward: stay deferred.  A convolution that consumes this
+      # gradient takes its compact pooled form (conv.py here: ngb_conv_wgrad_pooled, bias gradient of the pooled map);
+      # anything else materialises it with the fused route-and-mask kernel above.
+      if not (op == B.RELU and D.LAZY_FUSION and D.POOLED_CONV_GRADS and isinstance(ug, D.LazyArray) and ug.pending
+              and ug.tag == 'maxpool_bwd'):
+        return None
+      pug, idx, outer, H, W, KH, KW, pad, stride, ypool = ug.args
+      if (KH, KW, stride, pad) != (2, 2, 2, 0) or H % 2 or W % 2 or ypool is None:
+        return None
+      return D.LazyArray(x.shape, lambda: into(ug, None, False), 'pool_relu_bwd', D.PoolReluGrad(pug, idx, ypool, x, outer, H, W))
+    tens.set_grad_fn(GradFn(into, None, lazy))
 
 
 class Exp(_Unary):

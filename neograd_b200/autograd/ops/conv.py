@@ -50,21 +50,41 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
     B.check(B.lib.ngb_conv_dgrad(ug.ptr, w.ptr, dst.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st()))
     return dst
 
+  def pooled(ug):
+    """The upstream gradient as (masked pooled gradient, argmax indices) if it is a still-deferred ReLU+MaxPool backward
+    (device.PoolReluGrad): three quarters of the full-resolution gradient are zeros, the kernels below never build it."""
+    if isinstance(ug, D.LazyArray) and ug.pending and ug.tag == 'pool_relu_bwd':
+      return ug.args
+    return None
+
   def wgrad(ug, dst, acc):
     if dst is None:
       dst, acc = D.DeviceArray.empty(kernel.shape), False
+    pg = pooled(ug)
+    if pg is not None:
+      rc = B.lib.ngb_conv_wgrad_pooled(pg.pug.ptr, pg.ypool.ptr, ctypes.c_void_p(pg.idx.data_ptr()), pg.x.ptr, x.ptr, dst.ptr,
+                                       N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st())
+      if rc == 0:
+        return dst
+      if rc != B.ERR_UNSUPPORTED:
+        B.check(rc)
     B.check(B.lib.ngb_conv_wgrad(ug.ptr, x.ptr, dst.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st()))
     return dst
 
   def bgrad(ug, dst, acc):
     if dst is None:
       dst, acc = D.DeviceArray.empty(bias.shape), False
+    pg = pooled(ug)
+    if pg is not None:      # the sum over a plane of the scattered gradient is the sum over its pooled form
+      gm = pg.gm()
+      B.check(B.lib.ngb_conv_bgrad(gm.ptr, dst.ptr, N, O, gm.size // max(N * O, 1), int(acc), D._st()))
+      return dst
     B.check(B.lib.ngb_conv_bgrad(ug.ptr, dst.ptr, N, O, ug.size // max(N * O, 1), int(acc), D._st()))
     return dst
 
   inputs.set_grad_fn(GradFn(dgrad))
-  kernel.set_grad_fn(GradFn(wgrad))
-  bias.set_grad_fn(GradFn(bgrad))
+  kernel.set_grad_fn(GradFn(wgrad, lazy_ok=True))
+  bias.set_grad_fn(GradFn(bgrad, lazy_ok=True))
 
 
 class Conv2D(Operation, Conv):
@@ -137,6 +157,7 @@ class _MaxPool(Operation, Conv):
     self.padding = padding
     self.stride = stride
     self._idx = None
+    self._y = None
 
   def forward(self, inputs):
     inputs = self.get_tensors(inputs)
@@ -159,11 +180,11 @@ class _MaxPool(Operation, Conv):
     if rc != 0:
       B.check(B.lib.ngb_maxpool_fwd(xin.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), outer, H, W,
                                     self.kernel_shape[0], self.kernel_shape[1], self.padding, self.stride, D._st()))
-    self._idx = idx
+    self._idx, self._y = idx, y
     return self.get_result_tensor(y, inputs)
 
   def backward(self, inputs):
-    idx, (KH, KW), pad, stride = self._idx, self.kernel_shape, self.padding, self.stride
+    idx, ypool, (KH, KW), pad, stride = self._idx, self._y, self.kernel_shape, self.padding, self.stride
     lead = inputs.shape[:-2]
     H, W = inputs.shape[-2:]
     outer = int(np.prod(lead))
@@ -180,7 +201,7 @@ class _MaxPool(Operation, Conv):
       if not D.LAZY_FUSION:
         return None
       shape = inputs.shape
-      return D.LazyArray(shape, lambda: into(ug, None, False), 'maxpool_bwd', (ug, idx, outer, H, W, KH, KW, pad, stride))
+      return D.LazyArray(shape, lambda: into(ug, None, False), 'maxpool_bwd', (ug, idx, outer, H, W, KH, KW, pad, stride, ypool))
     inputs.set_grad_fn(GradFn(into, None, lazy))
 
   def validate_inputs(self, inputs):

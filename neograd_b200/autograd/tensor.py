@@ -21,10 +21,12 @@ class GradFn:
   """A grad_fn the engine can fuse.  `into(ug, dst, accumulate)` must write (accumulate=False) or add
   (accumulate=True) the operand-shaped gradient into `dst`; `dst=None` means allocate.  Calling the object like the
   reference's lambdas (`grad_fn(ug) -> array`) still works."""
-  __slots__ = ('into', 'alias', 'lazy')
+  __slots__ = ('into', 'alias', 'lazy', 'lazy_ok')
 
-  def __init__(self, into, alias=None, lazy=None):
+  def __init__(self, into, alias=None, lazy=None, lazy_ok=False):
     self.into = into
+    # lazy_ok: `into` understands a still-deferred upstream gradient (device.LazyArray) and need not have it materialised
+    self.lazy_ok = lazy_ok
     # lazy(ug) -> a device.LazyArray standing for this operand's gradient (produced on first use), or None.  Same
     # conditions as `alias`; lets the operand's own backward fuse with the producing kernel (MaxPool -> ReLU).
     self.lazy = lazy
@@ -218,8 +220,21 @@ class Tensor:
     node.backward_fn(*[n.tens for n in node.parents])
     upper_grad = self._grad if self._grad_live else DeviceArray.zeros(self.shape)
     if getattr(upper_grad, 'pending', False):
-      upper_grad.t                                   # a deferred gradient is produced HERE, on the main stream, once
+      # a deferred gradient is produced HERE, on the main stream, once -- or, when every consumer below understands its
+      # deferred form, only that form's shared pre-computation (the lanes must not race to create it)
+      prep = getattr(upper_grad.args, 'prep', None)
+      if prep is not None and all(isinstance(p.tens.grad_fn, GradFn) and p.tens.grad_fn.lazy_ok for p in leaves):
+        prep()
+      else:
+        upper_grad.t
     ready = None
+    # End of a chain (corun False): nothing else is left for the main stream, so the largest leaf's gradient (the weight
+    # gradient) runs THERE -- on the high-priority capture stream it is not queued behind the other layers' side-lane
+    # kernels, which became ready at the same moment -- and the small ones go to the lanes.
+    on_main = None
+    if not corun:
+      on_main = max(leaves, key=lambda p: p.tens.data.size).tens
+      leaves = [p for p in leaves if p.tens is not on_main] + [p for p in leaves if p.tens is on_main]
     for p in leaves:
       t = p.tens
       gf = t.grad_fn
@@ -234,7 +249,10 @@ class Tensor:
       if t._grad_live:
         t._unshare_grad()
       dst, live = t._grad, t._grad_live
-      _lanes.run(t, lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live), (upper_grad, gf, node), ready, corun)
+      if t is on_main:
+        gf.into(upper_grad, dst, live)               # (issued last: the lanes' waits on `ready` are already queued)
+      else:
+        _lanes.run(t, lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live), (upper_grad, gf, node), ready, corun)
       t._grad_live = True
       if node.lane_done is None:
         node.lane_done = {}

@@ -25,7 +25,8 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
 int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
                     int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done);
 int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int H, int W, int O, int KH, int KW, int pad,
-                   int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done);
+                   int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done, const uint8_t* pidx = nullptr,
+                   const float* ypool = nullptr, const float* zmask = nullptr);
 
 int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C, int H, int W, int O, int KH, int KW, int pad,
                         int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done);
@@ -905,6 +906,27 @@ extern "C" int ngb_conv_wgrad(const float* ug, const float* x, float* dw, int64_
   conv_wgrad_direct_kernel<<<grid, 256, 0, st>>>(ug, x, scratch_ptr(), g, (int)ips);
   NGB_LAUNCH_CHECK();
   return launch_sum_partials(scratch_ptr(), (int)splits, nw, dw, accumulate, st);
+}
+
+// dw (+)= wgrad of a convolution that is followed by ReLU and a 2x2 / stride 2 MaxPool, straight from the POOLED upstream
+// gradient: ug_pool (gradient of the pool's output), y_pool (the pool's output), idx (its argmax indices) and z (the conv
+// output = ReLU input).  The kernel applies the ReLU mask and rebuilds the full-resolution gradient (three quarters zeros)
+// in shared memory only.  Small-channel tensor-core path only (NGB_ERR_UNSUPPORTED otherwise: the caller materialises the
+// gradient with ngb_maxpool_relu_bwd and calls ngb_conv_wgrad).
+extern "C" int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* x,
+                                     float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                                     int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream) {
+  ConvGeo g;
+  int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
+  if (rc) return rc;
+  NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr && z != nullptr, "ngb_conv_wgrad_pooled needs the pool output, its argmax indices and the conv output");
+  if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wgrad_pooled: empty batch");
+  bool done = false;
+  rc = conv_mma_wgrad(ug_pool, x, dw, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, accumulate, as_stream(stream),
+                      &done, idx, y_pool, z);
+  if (rc) return rc;
+  if (!done) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wgrad_pooled: geometry not served by the small-channel tensor-core kernel");
+  return NGB_OK;
 }
 
 extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate,

@@ -349,6 +349,9 @@ static int launch_gather(const float* in, const float* w, const float* bias, flo
   static bool attr = false;
   if (!attr) {
     NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    // maximum shared-memory carveout: a kernel of another lane can only become co-resident on an SM whose L1 / shared split
+    // already has room for it -- with the default (smallest fitting) split the second kernel waits for the first to drain
+    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT, ACC>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   int grid = 1;
@@ -656,6 +659,9 @@ static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const R
   static bool attr = false;
   if (!attr) {
     NGB_CUDA(cudaFuncSetAttribute(conv_dgrad_rows_mma_kernel<KW, OB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    // maximum shared-memory carveout: a kernel of another lane can only become co-resident on an SM whose L1 / shared split
+    // already has room for it -- with the default (smallest fitting) split the second kernel waits for the first to drain
+    NGB_CUDA(cudaFuncSetAttribute(conv_dgrad_rows_mma_kernel<KW, OB>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   const int threads = g.MTC * g.IP * 32;
@@ -733,11 +739,14 @@ struct WgradGeo {
   int a_mod, a_div;                          // poff(f) = (f % Ho) * a_mod + (f / Ho) * a_div
   int MS, KS, G;
   int xcontig;                               // staged x == raw x (no halo, pitch == row length)
+  int pooled, Wo, Fp, Hp;                    // ug is a 2x2-pooled gradient + argmax indices: scattered into the staged tile
 };
 
 template <int MTW, int NT>
 __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __restrict__ ug, const float* __restrict__ x,
-                                                             float* __restrict__ part, WgradGeo g, FastDiv d_plane,
+                                                             const uint8_t* __restrict__ pidx, const float* __restrict__ ypool,
+                                                             const float* __restrict__ zmask, float* __restrict__ part, WgradGeo g,
+                                                             FastDiv d_fp, FastDiv d_hp, FastDiv d_plane,
                                                              FastDiv d_cols, FastDiv d_ho, FastDiv d_ksi, FastDiv d_kk,
                                                              FastDiv d_kw, FastDiv d_f, FastDiv d_ckk, FastDiv d_o) {
   extern __shared__ __align__(16) uint32_t smem_u[];
@@ -836,6 +845,56 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
         xs[pl * g.splane + (r + g.halo) * g.spitch + c + g.halo] = to_tf32(__ldg(src + e));
       }
     }
+    if (g.pooled) {
+      // ---- ug arrives POOLED (2x2 / stride 2, already masked by the ReLU gradient) with the argmax index of every window:
+      // the full-resolution gradient (three quarters zeros) is rebuilt right here in shared memory and never exists in HBM
+      const int rows4 = ng * g.uimg / 4;
+      for (int e4 = tid; e4 < rows4; e4 += nthr) reinterpret_cast<uint4*>(us)[e4] = make_uint4(0u, 0u, 0u, 0u);
+      __syncthreads();
+      const int64_t base = (int64_t)n0 * g.O * g.Fp;
+      const int raw = ng * g.O * g.Fp;
+      const int pad_planes = g.NP - g.O;
+      // value of pooled element e: ug[e] * relu'(z at the window's argmax).  y > 0: the argmax cell passed the ReLU (mask 1);
+      // y == 0: the whole window was clamped, the argmax is its first cell and the mask is z_first >= 0 (activations.py:31).
+      auto masked = [&](float gv, float yv, uint32_t pl, uint32_t p, uint32_t q) {
+        if (!(yv > 0.f)) {
+          const float zv = __ldg(zmask + ((int64_t)n0 * g.O + pl) * g.F + (2 * p) * (uint32_t)g.Wo + 2 * q);
+          gv = zv >= 0.f ? gv : 0.f;
+        }
+        return gv;
+      };
+      if ((g.Hp & 3) == 0 && (((uintptr_t)(ug + base) | (uintptr_t)(ypool + base)) & 15u) == 0 && ((uintptr_t)(pidx + base) & 3u) == 0) {
+        // four pooled positions along p' per thread: one index decomposition, 128-bit loads of ug / y, 32-bit load of idx
+#pragma unroll 2
+        for (int e4 = tid; e4 < (raw >> 2); e4 += nthr) {
+          uint32_t pl, fe, q, p;
+          d_fp.divmod((uint32_t)e4 * 4u, pl, fe);        // pl = img*O + o; pooled position (p', q') sits at q'*Hp + p'
+          d_hp.divmod(fe, q, p);
+          const uint32_t img = d_o.div(pl);
+          const float4 gv = ld_stream4(ug + base + 4 * (int64_t)e4);
+          const float4 yv = ld_stream4(ypool + base + 4 * (int64_t)e4);
+          const uint32_t a4 = *reinterpret_cast<const uint32_t*>(pidx + base + 4 * (int64_t)e4);
+          uint32_t* row = us + (pl + img * pad_planes) * g.Up + 2 * q;
+          const float gs[4] = {gv.x, gv.y, gv.z, gv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t a = (a4 >> (8 * j)) & 0xFFu;
+            row[(2 * (p + j) + (a >> 1)) * (uint32_t)g.Wo + (a & 1)] = to_tf32(masked(gs[j], ys[j], pl, p + j, q));
+          }
+        }
+      } else {
+#pragma unroll 4
+        for (int e = tid; e < raw; e += nthr) {
+          uint32_t pl, fe, q, p;
+          d_fp.divmod((uint32_t)e, pl, fe);
+          d_hp.divmod(fe, q, p);
+          const uint32_t img = d_o.div(pl);
+          const uint32_t a = pidx[base + e];              // argmax inside the window, row-major (kh, kw)
+          const uint32_t f = (2 * p + (a >> 1)) * (uint32_t)g.Wo + 2 * q + (a & 1);
+          us[(pl + img * pad_planes) * g.Up + f] = to_tf32(masked(__ldg(ug + base + e), __ldg(ypool + base + e), pl, p, q));
+        }
+      }
+    } else
     {  // ---- ug: [o][f] as stored (neograd order), plane pitch Up
       const float* src = ug + (int64_t)n0 * uraw_img;
       const int raw = ng * uraw_img;
@@ -925,11 +984,14 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
 }
 
 template <int MTW, int NT>
-static int launch_wgrad(const float* ug, const float* x, float* part, WgradGeo g, int nwarps, int gmin, int gmax, size_t fixed,
-                        size_t per_img, int* grid_out, cudaStream_t st) {
+static int launch_wgrad(const float* ug, const float* x, const uint8_t* pidx, const float* ypool, const float* zmask, float* part,
+                        WgradGeo g, int nwarps, int gmin, int gmax, size_t fixed, size_t per_img, int* grid_out, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
     NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    // maximum shared-memory carveout: a kernel of another lane can only become co-resident on an SM whose L1 / shared split
+    // already has room for it -- with the default (smallest fitting) split the second kernel waits for the first to drain
+    NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   // Beside the data-gradient chain (ngb_set_corun) a persistent grid at full occupancy would hold every register of
@@ -945,19 +1007,26 @@ static int launch_wgrad(const float* ug, const float* x, float* part, WgradGeo g
   if (grid < 1) return fail(NGB_ERR_SCRATCH, "conv wgrad: scratch arena too small for %lld filter elements", (long long)nwts);
   *grid_out = (int)grid;
   conv_wgrad_mma_kernel<MTW, NT><<<(unsigned)grid, nwarps * 32, smem, st>>>(
-      ug, x, part, g, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.Ho),
+      ug, x, pidx, ypool, zmask, part, g, FastDiv((uint32_t)(g.Fp > 0 ? g.Fp : 1)), FastDiv((uint32_t)(g.Hp > 0 ? g.Hp : 1)),
+      FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.Ho),
       FastDiv((uint32_t)g.KSI), FastDiv((uint32_t)(g.KH * g.KW)), FastDiv((uint32_t)g.KW), FastDiv((uint32_t)g.F),
       FastDiv((uint32_t)g.CKK), FastDiv((uint32_t)g.O));
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
 
+// pidx != null: `ug` is the 2x2 / stride 2 POOLED gradient [N][O][Ho/2 * Wo/2] (pooled position (p', q') at q'*(Ho/2) + p'),
+// pidx the argmax index of every pooling window, ypool the pool's output and zmask the conv output (= ReLU input); the kernel
+// applies the ReLU mask and scatters the gradient into the full-resolution tile itself.
 int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int H, int W, int O, int KH, int KW, int pad,
-                   int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done) {
+                   int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done, const uint8_t* pidx,
+                   const float* ypool, const float* zmask) {
   *done = false;
   if (g_default_engine.load() == NGB_GEMM_SIMT) return NGB_OK;
   if (O < 4 || O > 16) return NGB_OK;
+  if (pidx && ((Ho & 1) || (Wo & 1))) return NGB_OK;
   WgradGeo g;
+  g.pooled = pidx ? 1 : 0; g.Wo = Wo; g.Hp = Ho / 2; g.Fp = (Ho / 2) * (Wo / 2);
   g.N = N; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.Ho = Ho;
   g.raw_rows = H; g.raw_cols = W; g.raw_plane = H * W; g.halo = pad;
   g.spitch = round_up_mod(W + 2 * pad, 8, 4);
@@ -993,7 +1062,7 @@ int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int
   if (nw * 4 * kNumSMs * 4 > scratch_bytes()) return NGB_OK;
   int grid = 0;
   float* part = scratch_ptr();
-#define NGB_WGRAD(M_, N_) rc = launch_wgrad<M_, N_>(ug, x, part, g, nwarps, gmin, G, fixed, per_img, &grid, st)
+#define NGB_WGRAD(M_, N_) rc = launch_wgrad<M_, N_>(ug, x, pidx, ypool, zmask, part, g, nwarps, gmin, G, fixed, per_img, &grid, st)
   if (NT == 1) {
     switch (MTW) { case 1: NGB_WGRAD(1, 1); break; case 2: NGB_WGRAD(2, 1); break; case 3: NGB_WGRAD(3, 1); break;
                    case 4: NGB_WGRAD(4, 1); break; default: NGB_WGRAD(5, 1); break; }

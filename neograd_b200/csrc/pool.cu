@@ -512,6 +512,40 @@ extern "C" int ngb_maxpool_relu_bwd(const float* ug, const uint8_t* idx, const f
   return NGB_OK;
 }
 
+// gm[e] = ug[e] * relu'(x at the window's argmax), per POOLED element (2x2 / stride 2): the ReLU+pool backward pair kept
+// in its compact, pooled form for consumers that scatter it themselves (ngb_conv_wgrad_pooled) or only need its sum (bias
+// gradient).  y > 0 means the argmax cell passed the ReLU with a positive value (mask 1); y == 0 means every cell of the
+// window was clamped, the argmax is the first cell, and the mask is x_first >= 0 (activations.py:31) -- only those windows
+// read x at all.
+__global__ void __launch_bounds__(256) maxpool_relu_mask_kernel(const float* __restrict__ ug, const float* __restrict__ y,
+                                                                const float* __restrict__ x, float* __restrict__ gm, int64_t total,
+                                                                int H, int W, FastDiv d_plane, FastDiv d_hp) {
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const float g = ug[e];
+    float out = g;
+    if (!(y[e] > 0.f)) {
+      uint32_t plane, fe, q, p;
+      d_plane.divmod((uint32_t)e, plane, fe);       // pooled maps are stored with position (p', q') at q'*Hp + p'
+      d_hp.divmod(fe, q, p);
+      const float xv = __ldg(x + ((int64_t)plane * H + 2 * p) * W + 2 * q);
+      out = xv >= 0.f ? g : 0.f;
+    }
+    gm[e] = out;
+  }
+}
+
+extern "C" int ngb_maxpool_relu_mask(const float* ug, const float* y, const float* x, float* gm, int64_t outer, int64_t H,
+                                     int64_t W, ngb_stream_t stream) {
+  NGB_CHECK_ARG(outer >= 0 && H >= 2 && W >= 2 && (H % 2) == 0 && (W % 2) == 0, "ngb_maxpool_relu_mask: 2x2 / stride 2 pooling of even planes only");
+  const int64_t total = outer * (H / 2) * (W / 2);
+  if (total == 0) return NGB_OK;
+  NGB_CHECK_ARG(total < (int64_t(1) << 32), "ngb_maxpool_relu_mask: tensor too large");
+  maxpool_relu_mask_kernel<<<grid_for(total, 256), 256, 0, as_stream(stream)>>>(ug, y, x, gm, total, (int)H, (int)W,
+                                                                               FastDiv((uint32_t)((H / 2) * (W / 2))), FastDiv((uint32_t)(H / 2)));
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
 extern "C" int ngb_maxpool_fwd(const float* x, float* y, uint8_t* idx, int64_t outer, int64_t H, int64_t W, int64_t KH,
                                int64_t KW, int64_t pad, int64_t stride, ngb_stream_t stream) {
   int64_t Ho, Wo;

@@ -341,6 +341,30 @@ class LazyArray(DeviceArray):
     return self._shape[0]
 
 
+class PoolReluGrad:
+  """What a deferred ReLU+MaxPool(2x2, stride 2) backward stands for: the pooled upstream gradient `pug`, the pooling
+  argmax indices `idx`, the pool's output `ypool` and the ReLU's input `x`.  The convolution's weight gradient consumes
+  these directly (ngb_conv_wgrad_pooled); `gm()` is the compact masked gradient pug * relu'(x at the argmax) for its
+  bias gradient, computed once (ngb_maxpool_relu_mask) and cached -- by its only consumer, on that consumer's stream."""
+  __slots__ = ('pug', 'idx', 'ypool', 'x', 'outer', 'H', 'W', '_gm')
+
+  def __init__(self, pug, idx, ypool, x, outer, H, W):
+    self.pug, self.idx, self.ypool, self.x, self.outer, self.H, self.W = pug, idx, ypool, x, outer, H, W
+    self._gm = None
+
+  def gm(self):
+    if self._gm is None:
+      out = DeviceArray(_alloc(self.pug.shape))
+      B.check(B.lib.ngb_maxpool_relu_mask(self.pug.ptr, self.ypool.ptr, self.x.ptr, out.ptr, self.outer, self.H, self.W, _st()))
+      self._gm = out
+    return self._gm
+
+  def prep(self):
+    """Nothing is shared between the consumers (autograd/tensor.py:_issue_leaf_grads calls this before the lanes start)."""
+
+
+import os as _os
+POOLED_CONV_GRADS = _os.environ.get('NGB_NO_POOLED') != '1'   # conv weight / bias gradients straight from a pooled gradient
 LAZY_FUSION = True   # ReLU -> MaxPool pairs run as fused kernels (set False to materialise every op's output eagerly)
 
 

@@ -157,6 +157,29 @@ def maxpool_relu_bwd(ug, idx, xm, k, pad, stride):
   return host(dx)
 
 
+def maxpool_relu_mask(ug_pool, y_pool, x):
+  H, W = x.shape[-2:]
+  outer = int(np.prod(x.shape[:-2]))
+  U, Y, X = dev(ug_pool), dev(y_pool), dev(x)
+  gm = torch.full(tuple(ug_pool.shape), float('nan'), device='cuda')
+  call('ngb_maxpool_relu_mask', ptr(U), ptr(Y), ptr(X), ptr(gm), outer, H, W, st())
+  return host(gm)
+
+
+def conv_wgrad_pooled(ug_pool, y_pool, idx, z, x, wshape, pad, stride):
+  """returns None when the geometry is not served by the pooled-gradient kernel"""
+  N, C, H, W = x.shape
+  O, _, KH, KW = wshape
+  dw = torch.full(tuple(wshape), float('nan'), device='cuda')
+  G, Y, I, Z, X = dev(ug_pool), dev(y_pool), dev(idx, torch.uint8), dev(z), dev(x)
+  B.ensure_runtime()
+  rc = lib.ngb_conv_wgrad_pooled(ptr(G), ptr(Y), ptr(I), ptr(Z), ptr(X), ptr(dw), N, C, H, W, O, KH, KW, pad, stride, 0, st())
+  if rc == B.ERR_UNSUPPORTED:
+    return None
+  B.check(rc)
+  return host(dw)
+
+
 def binary_fwd(op, a, b):
   a, b = np.asarray(a), np.asarray(b)
   out_shape = np.broadcast_shapes(a.shape, b.shape)

@@ -361,6 +361,42 @@ def test_maxpool_relu_fused_is_bit_exact(U, shape):
   assert np.array_equal(dx, ref.astype(np.float32))
 
 
+@pytest.mark.parametrize('N,C,H,W,O,K', [(64, 1, 28, 28, 6, 5), (33, 6, 12, 12, 16, 5), (5, 3, 10, 14, 8, 3)])
+def test_conv_wgrad_from_pooled_gradient(U, N, C, H, W, O, K):
+  """Conv -> ReLU -> MaxPool(2x2, s2) backward without the full-resolution gradient: ngb_maxpool_relu_mask keeps the
+  conv-output gradient in pooled form, ngb_conv_wgrad_pooled scatters it inside the kernel.  Against the separate kernels:
+  the scattered compact gradient is bit-identical to ngb_maxpool_relu_bwd's, the weight gradient is bit-identical to
+  ngb_conv_wgrad on that full gradient (same operands, same summation order), the bias gradient agrees to fp32 rounding."""
+  rng = np.random.default_rng(N + C + H + O)
+  xin = f32(rng.standard_normal((N, C, H, W)))
+  Ho, Wo = H - K + 1, W - K + 1
+  z = f32(rng.standard_normal((N, O, Ho, Wo)))             # the conv output = ReLU input
+  z[0] = -np.abs(z[0]) - 0.5                              # fully clamped windows
+  z[1, :, ::2, ::2] = 0.0                                   # exact zeros at window origins: relu'(0) = 1
+  y, idx = U.maxpool_relu_fwd(z, (2, 2), 0, 2)
+  ugp = f32(rng.standard_normal(y.shape))
+  gm = U.maxpool_relu_mask(ugp, y, z)
+  full = U.maxpool_relu_bwd(ugp, idx, z, (2, 2), 0, 2)
+  # scatter gm by idx on the host: pooled (p', q') sits at q'*Hp + p'; window cell (kh, kw) -> (2p'+kh, 2q'+kw)
+  Hp, Wp = Ho // 2, Wo // 2
+  gmr, idr = gm.reshape(N, O, Wp, Hp), idx.reshape(N, O, Wp, Hp)
+  scat = np.zeros((N, O, Ho, Wo), np.float32)
+  for qq in range(Wp):
+    for pp in range(Hp):
+      a = idr[:, :, qq, pp].astype(int)
+      for kh in range(2):
+        for kw in range(2):
+          m = a == kh * 2 + kw
+          scat[:, :, 2 * pp + kh, 2 * qq + kw] = np.where(m, gmr[:, :, qq, pp], scat[:, :, 2 * pp + kh, 2 * qq + kw])
+  assert np.array_equal(scat, full)
+  dw = U.conv_wgrad_pooled(ugp, y, idx, z, xin, (O, C, K, K), 0, 1)
+  assert dw is not None
+  ref = U.conv_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1)
+  assert np.array_equal(dw, ref)
+  close(dw, ops.conv3d_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1), TOLTF32)
+  close(U.conv_bgrad(gm.astype(np.float64)), U.conv_bgrad(full.astype(np.float64)), 4 * TOL32)
+
+
 def test_maxpool_relu_fused_rejects_other_geometries(U):
   x = np.zeros((2, 3, 9, 9))
   assert U.maxpool_relu_fwd(x, (3, 3), 0, 3) is None

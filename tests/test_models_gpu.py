@@ -290,8 +290,10 @@ def test_backward_lanes_change_nothing(ng, captured):
 
 
 def test_lazy_relu_pool_fusion_changes_nothing(ng):
-  """ReLU -> MaxPool pairs run as fused kernels (the ReLU output and the pool's input gradient are never written);
-  the arithmetic is unchanged, so a LeNet-B trajectory is bit-identical with the fusion switched off."""
+  """ReLU -> MaxPool pairs run as fused kernels (the ReLU output and the pool's input gradient are never written) and the
+  first convolution's weight / bias gradients are taken from the pooled gradient; products and summation orders are
+  unchanged except in the conv1 bias gradient (sum over the pooled map instead of the 4x larger one with zeros), so a
+  LeNet-B trajectory agrees to fp32 rounding with the fusion switched off."""
   from neograd_b200 import device as D
   from neograd_b200.configs import lenet_synthetic, train_step
   results = []
@@ -308,9 +310,9 @@ def test_lazy_relu_pool_fusion_changes_nothing(ng):
       results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
     finally:
       D.LAZY_FUSION = prev
-  assert results[0][0] == results[1][0]
+  assert abs(results[0][0] - results[1][0]) <= 1e-6 * abs(results[0][0])
   for a, b in zip(results[0][1:], results[1][1:]):
-    assert np.array_equal(a, b)
+    assert dist(a, b) < 1e-6, dist(a, b)
   # a lazily produced activation is an ordinary array for everything else
   x = ng.tensor(np.array([[-1.0, 2.0], [0.0, -3.0]]), requires_grad=True)
   r = ng.nn.ReLU()(x)
