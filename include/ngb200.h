@@ -104,10 +104,13 @@ int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoW
  * zeros (one cell per pooling window) and never has to exist in HBM.  ngb_conv_wgrad_pooled computes conv.py:311-321 from
  * the pool's upstream gradient ug_pool, the pool's output y_pool, its argmax indices idx and the conv output z (= the ReLU's
  * input): mask and scatter happen in the kernel's shared memory.  ngb_maxpool_relu_mask writes the compact masked gradient
- * gm[e] = ug_pool[e] * relu'(z at the argmax); the bias gradient (conv.py:323-327) is ngb_conv_bgrad(gm, ..., HoWo/4).
+ * gm[e] = ug_pool[e] * relu'(z at the argmax); the bias gradient (conv.py:323-327) is the sum of gm, computed without
+ * writing it by ngb_conv_bgrad_pooled (Ho x Wo = the conv output plane).
  * NGB_ERR_UNSUPPORTED -> materialise the gradient with ngb_maxpool_relu_bwd and use ngb_conv_wgrad. */
 int ngb_maxpool_relu_mask(const float* ug_pool, const float* y_pool, const float* z, float* gm, int64_t outer, int64_t H,
                           int64_t W, ngb_stream_t stream);
+int ngb_conv_bgrad_pooled(const float* ug_pool, const float* y_pool, const float* z, float* db, int64_t N, int64_t O,
+                          int64_t Ho, int64_t Wo, int accumulate, ngb_stream_t stream);
 int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* x,
                           float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
                           int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);

@@ -75,9 +75,8 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
     if dst is None:
       dst, acc = D.DeviceArray.empty(bias.shape), False
     pg = pooled(ug)
-    if pg is not None:      # the sum over a plane of the scattered gradient is the sum over its pooled form
-      gm = pg.gm()
-      B.check(B.lib.ngb_conv_bgrad(gm.ptr, dst.ptr, N, O, gm.size // max(N * O, 1), int(acc), D._st()))
+    if pg is not None:      # the sum over a plane of the scattered gradient is the sum over its masked pooled form
+      B.check(B.lib.ngb_conv_bgrad_pooled(pg.pug.ptr, pg.ypool.ptr, pg.x.ptr, dst.ptr, N, O, pg.H, pg.W, int(acc), D._st()))
       return dst
     B.check(B.lib.ngb_conv_bgrad(ug.ptr, dst.ptr, N, O, ug.size // max(N * O, 1), int(acc), D._st()))
     return dst

@@ -747,12 +747,27 @@ static int conv_wgrad_small(const float* ug, const float* x, float* dw, const Co
 // ---------------------------------------------------------------------------------------------- bgrad
 // db[o] = sum_{n,f} ug[n,o,f].  grid = (O, splits over N); every image contributes one contiguous HoWo run: 128-bit loads,
 // four in flight per thread, no 64-bit divides.
+// MASKED: ug is the pooled gradient of a Conv -> ReLU -> MaxPool(2x2, s2) block and the sum runs over ug * relu'(z at the
+// window's argmax) -- y (the pool's output) > 0 means mask 1, otherwise the mask is z_first >= 0 (see maxpool_relu_mask_kernel);
+// the bias gradient then needs neither the full-resolution gradient nor the compact masked copy.
+template <bool MASKED>
 __global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict__ ug, float* __restrict__ part, int64_t N,
-                                                         int64_t O, int64_t HW, int64_t imgs_per_split, FastDiv d_hw4, int vec) {
+                                                         int64_t O, int64_t HW, int64_t imgs_per_split, FastDiv d_hw4, int vec,
+                                                         const float* __restrict__ y, const float* __restrict__ z, int Hp, int Wo,
+                                                         FastDiv d_hp) {
   __shared__ float red[32];
   const int64_t o = blockIdx.x;
   const int64_t nb = (int64_t)blockIdx.y * imgs_per_split, ne = min(N, nb + imgs_per_split);
   float acc = 0.f;
+  auto masked = [&](float gv, float yv, int64_t plane, uint32_t f) {
+    if (!(yv > 0.f)) {
+      uint32_t q, p;
+      d_hp.divmod(f, q, p);                         // pooled position (p', q') sits at q'*Hp + p'
+      const float zv = __ldg(z + plane * (4 * HW) + (int64_t)(2 * p) * Wo + 2 * q);
+      gv = zv >= 0.f ? gv : 0.f;
+    }
+    return gv;
+  };
   if (vec) {
     const uint32_t hw4 = (uint32_t)(HW >> 2);
     const uint32_t span4 = (uint32_t)((ne - nb) * hw4);
@@ -761,7 +776,13 @@ __global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict
     for (uint32_t i = threadIdx.x; i < span4; i += 256) {
       uint32_t n, f4;
       d_hw4.divmod(i, n, f4);
-      const float4 v = ld_stream4(ug + ((nb + n) * O + o) * HW + 4 * (int64_t)f4);
+      const int64_t plane = (nb + n) * O + o;
+      float4 v = ld_stream4(ug + plane * HW + 4 * (int64_t)f4);
+      if (MASKED) {
+        const float4 yv = ld_stream4(y + plane * HW + 4 * (int64_t)f4);
+        v.x = masked(v.x, yv.x, plane, 4 * f4); v.y = masked(v.y, yv.y, plane, 4 * f4 + 1);
+        v.z = masked(v.z, yv.z, plane, 4 * f4 + 2); v.w = masked(v.w, yv.w, plane, 4 * f4 + 3);
+      }
       a0 += v.x; a1 += v.y; a2 += v.z; a3 += v.w;
     }
     acc = (a0 + a1) + (a2 + a3);
@@ -769,7 +790,9 @@ __global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict
     const int64_t span = (ne - nb) * HW;
     for (int64_t i = threadIdx.x; i < span; i += blockDim.x) {
       const int64_t n = nb + i / HW, f = i % HW;
-      acc += ug[(n * O + o) * HW + f];
+      float v = ug[(n * O + o) * HW + f];
+      if (MASKED) v = masked(v, y[(n * O + o) * HW + f], n * O + o, (uint32_t)f);
+      acc += v;
     }
   }
   acc = block_sum(acc, red);
@@ -929,8 +952,8 @@ extern "C" int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, 
   return NGB_OK;
 }
 
-extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate,
-                              ngb_stream_t stream) {
+static int conv_bgrad_impl(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate, const float* y,
+                           const float* z, int64_t Hp, int64_t Wo_full, ngb_stream_t stream) {
   NGB_CHECK_ARG(N >= 0 && O >= 1 && HoWo >= 0, "conv bgrad: bad dimensions");
   cudaStream_t st = as_stream(stream);
   if (N == 0 || HoWo == 0) {
@@ -948,8 +971,26 @@ extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, 
   const int64_t ips = ceil_div<int64_t>(N, splits);
   splits = ceil_div<int64_t>(N, ips);
   dim3 grid((unsigned)O, (unsigned)splits);
-  const int vec = (HoWo % 4 == 0) && aligned16(ug) && (ips * (HoWo / 4) < (int64_t(1) << 32));
-  conv_bgrad_kernel<<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips, FastDiv((uint32_t)(vec ? HoWo / 4 : 1)), vec);
+  const int vec = (HoWo % 4 == 0) && aligned16(ug) && (y == nullptr || aligned16(y)) && (ips * (HoWo / 4) < (int64_t(1) << 32));
+  const FastDiv dhw4((uint32_t)(vec ? HoWo / 4 : 1)), dhp((uint32_t)(Hp > 0 ? Hp : 1));
+  if (y)
+    conv_bgrad_kernel<true><<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips, dhw4, vec, y, z, (int)Hp, (int)Wo_full, dhp);
+  else
+    conv_bgrad_kernel<false><<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips, dhw4, vec, nullptr, nullptr, 1, 1, dhp);
   NGB_LAUNCH_CHECK();
   return launch_sum_partials(scratch_ptr(), (int)splits, O, db, accumulate, st);
+}
+
+extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate,
+                              ngb_stream_t stream) {
+  return conv_bgrad_impl(ug, db, N, O, HoWo, accumulate, nullptr, nullptr, 0, 0, stream);
+}
+
+// db (+)= bias gradient of a convolution followed by ReLU and a 2x2 / stride 2 MaxPool, straight from the pooled upstream
+// gradient: sum over n and pooled positions of ug_pool * relu'(z at the argmax).  Ho x Wo = the conv output plane (even).
+extern "C" int ngb_conv_bgrad_pooled(const float* ug_pool, const float* y_pool, const float* z, float* db, int64_t N, int64_t O,
+                                     int64_t Ho, int64_t Wo, int accumulate, ngb_stream_t stream) {
+  NGB_CHECK_ARG(y_pool != nullptr && z != nullptr && Ho >= 2 && Wo >= 2 && Ho % 2 == 0 && Wo % 2 == 0,
+                "ngb_conv_bgrad_pooled: needs the pool output, the conv output and an even output plane");
+  return conv_bgrad_impl(ug_pool, db, N, O, (Ho / 2) * (Wo / 2), accumulate, y_pool, z, Ho / 2, Wo, stream);
 }

@@ -282,6 +282,37 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
   }
 }
 
+// Same sum for MANY partials of a SHORT row (the per-CTA partials of the persistent conv weight-gradient kernels: ~600 x 150):
+// 8 columns x 32 split lanes per CTA, so a thread walks splits/32 rows instead of splits/8 -- the kernel is a chain of
+// dependent L2 round trips, its time is the length of that chain.  Lane sums are combined in a fixed order.
+__global__ void __launch_bounds__(256) sum_partials_tall_kernel(const float* __restrict__ part, int splits, int64_t K,
+                                                                float* __restrict__ out, int accumulate) {
+  __shared__ float tile[32][9];
+  const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
+  for (int64_t k0 = (int64_t)blockIdx.x * 8; k0 < K; k0 += (int64_t)gridDim.x * 8) {
+    const int64_t k = k0 + tx;
+    float s = 0.f;
+    if (k < K) {
+      int j = ty;
+      for (; j + 96 < splits; j += 128) {
+        const float a = part[(int64_t)j * K + k], b = part[(int64_t)(j + 32) * K + k];
+        const float c = part[(int64_t)(j + 64) * K + k], d = part[(int64_t)(j + 96) * K + k];
+        s += (a + b) + (c + d);
+      }
+      for (; j < splits; j += 32) s += part[(int64_t)j * K + k];
+    }
+    tile[ty][tx] = s;
+    __syncthreads();
+    if (ty == 0 && k < K) {
+      float r = tile[0][tx];
+#pragma unroll
+      for (int j = 1; j < 32; ++j) r += tile[j][tx];
+      out[k] = accumulate ? out[k] + r : r;
+    }
+    __syncthreads();
+  }
+}
+
 // Row reduction, pattern [K][R]: one warp per kept row, lanes stride the contiguous reduced axis.
 __global__ void __launch_bounds__(256) ew_bwd_rowreduce_kernel(int op, int side, const float* __restrict__ ug,
                                                                const float* __restrict__ a, float as, int64_t sa0, int64_t sa1,
@@ -611,7 +642,10 @@ static int reduce_dispatch(int op, int side, const BDims& d, int64_t total, cons
 }
 
 int launch_sum_partials(const float* part, int splits, int64_t K, float* out, int accumulate, cudaStream_t st) {
-  sum_partials_kernel<<<grid_for(K * 8, 256), 256, 0, st>>>(part, splits, K, out, accumulate);
+  if (splits >= 128 && K <= 8192)
+    sum_partials_tall_kernel<<<grid_for(K * 32, 256), 256, 0, st>>>(part, splits, K, out, accumulate);
+  else
+    sum_partials_kernel<<<grid_for(K * 8, 256), 256, 0, st>>>(part, splits, K, out, accumulate);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }

@@ -166,6 +166,14 @@ def maxpool_relu_mask(ug_pool, y_pool, x):
   return host(gm)
 
 
+def conv_bgrad_pooled(ug_pool, y_pool, z):
+  N, O, Ho, Wo = z.shape
+  db = torch.full((O,), float('nan'), device='cuda')
+  G, Y, Z = dev(ug_pool), dev(y_pool), dev(z)
+  call('ngb_conv_bgrad_pooled', ptr(G), ptr(Y), ptr(Z), ptr(db), N, O, Ho, Wo, 0, st())
+  return host(db)
+
+
 def conv_wgrad_pooled(ug_pool, y_pool, idx, z, x, wshape, pad, stride):
   """returns None when the geometry is not served by the pooled-gradient kernel"""
   N, C, H, W = x.shape

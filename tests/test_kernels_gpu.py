@@ -395,6 +395,7 @@ def test_conv_wgrad_from_pooled_gradient(U, N, C, H, W, O, K):
   assert np.array_equal(dw, ref)
   close(dw, ops.conv3d_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1), TOLTF32)
   close(U.conv_bgrad(gm.astype(np.float64)), U.conv_bgrad(full.astype(np.float64)), 4 * TOL32)
+  close(U.conv_bgrad_pooled(ugp, y, z), full.astype(np.float64).sum(axis=(0, 2, 3)), 4 * TOL32)
 
 
 def test_maxpool_relu_fused_rejects_other_geometries(U):
