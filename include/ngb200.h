@@ -111,6 +111,9 @@ int ngb_maxpool_relu_mask(const float* ug_pool, const float* y_pool, const float
                           int64_t W, ngb_stream_t stream);
 int ngb_conv_bgrad_pooled(const float* ug_pool, const float* y_pool, const float* z, float* db, int64_t N, int64_t O,
                           int64_t Ho, int64_t Wo, int accumulate, ngb_stream_t stream);
+int ngb_conv_dgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* w,
+                          float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                          int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);    /* conv.py:299-309 */
 int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* x,
                           float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
                           int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);

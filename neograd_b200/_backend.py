@@ -71,6 +71,7 @@ SIGNATURES = {
   'ngb_maxpool_relu_bwd': ([_P, _P, _P, _P] + [c_int64] * 7 + [c_int, _S], c_int),
   'ngb_maxpool_relu_mask': ([_P, _P, _P, _P] + [c_int64] * 3 + [_S], c_int),
   'ngb_conv_bgrad_pooled': ([_P, _P, _P, _P] + [c_int64] * 4 + [c_int, _S], c_int),
+  'ngb_conv_dgrad_pooled': ([_P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
   'ngb_conv_wgrad_pooled': ([_P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
   'ngb_ew_binary_fwd': ([c_int, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, _S], c_int),
   'ngb_ew_binary_bwd': ([c_int, c_int, _P, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, c_int, _S], c_int),

@@ -44,18 +44,26 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
   pad, stride = op.padding, op.stride
   x, w = inputs.data, kernel.data
 
-  def dgrad(ug, dst, acc):
-    if dst is None:
-      dst, acc = D.DeviceArray.empty(inputs.shape), False
-    B.check(B.lib.ngb_conv_dgrad(ug.ptr, w.ptr, dst.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st()))
-    return dst
-
   def pooled(ug):
     """The upstream gradient as (masked pooled gradient, argmax indices) if it is a still-deferred ReLU+MaxPool backward
     (device.PoolReluGrad): three quarters of the full-resolution gradient are zeros, the kernels below never build it."""
     if isinstance(ug, D.LazyArray) and ug.pending and ug.tag == 'pool_relu_bwd':
       return ug.args
     return None
+
+  def dgrad(ug, dst, acc):
+    if dst is None:
+      dst, acc = D.DeviceArray.empty(inputs.shape), False
+    pg = pooled(ug) if D.POOLED_CONV_DGRAD else None
+    if pg is not None:
+      rc = B.lib.ngb_conv_dgrad_pooled(pg.pug.ptr, pg.ypool.ptr, ctypes.c_void_p(pg.idx.data_ptr()), pg.x.ptr, w.ptr, dst.ptr,
+                                       N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st())
+      if rc == 0:
+        return dst
+      if rc != B.ERR_UNSUPPORTED:
+        B.check(rc)
+    B.check(B.lib.ngb_conv_dgrad(ug.ptr, w.ptr, dst.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st()))
+    return dst
 
   def wgrad(ug, dst, acc):
     if dst is None:

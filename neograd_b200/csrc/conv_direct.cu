@@ -29,7 +29,8 @@ int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int
                    const float* ypool = nullptr, const float* zmask = nullptr);
 
 int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C, int H, int W, int O, int KH, int KW, int pad,
-                        int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done);
+                        int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done, const uint8_t* pidx = nullptr,
+                        const float* ypool = nullptr, const float* zmask = nullptr);
 
 constexpr int OT = 8;  // output channels per thread (register tile)
 
@@ -984,6 +985,24 @@ static int conv_bgrad_impl(const float* ug, float* db, int64_t N, int64_t O, int
 extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate,
                               ngb_stream_t stream) {
   return conv_bgrad_impl(ug, db, N, O, HoWo, accumulate, nullptr, nullptr, 0, 0, stream);
+}
+
+// dx (+)= data gradient (conv.py:299-309) of a convolution followed by ReLU and a 2x2 / stride 2 MaxPool, straight from the
+// pooled upstream gradient (same operands as ngb_conv_wgrad_pooled).  Row-decomposed tensor-core kernel only.
+extern "C" int ngb_conv_dgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* w,
+                                     float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                                     int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream) {
+  ConvGeo g;
+  int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
+  if (rc) return rc;
+  NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr && z != nullptr, "ngb_conv_dgrad_pooled needs the pool output, its argmax indices and the conv output");
+  if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_dgrad_pooled: empty batch");
+  bool done = false;
+  rc = conv_mma_dgrad_rows(ug_pool, w, dx, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, accumulate,
+                           as_stream(stream), &done, idx, y_pool, z);
+  if (rc) return rc;
+  if (!done) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_dgrad_pooled: geometry not served by the row-decomposed tensor-core kernel");
+  return NGB_OK;
 }
 
 // db (+)= bias gradient of a convolution followed by ReLU and a 2x2 / stride 2 MaxPool, straight from the pooled upstream

@@ -454,10 +454,13 @@ struct RowsGeo {
   int HWp, dimg;               // dx accumulator plane pitch (even) and image pitch
   int MTC, IP;                 // m-tiles of (c,kh) rows, images in flight per CTA
   int pair_ok;                 // 64-bit read-modify-write possible (W and HWp even)
+  int pooled, Hp, Fp;          // ug is a 2x2-pooled gradient (+ pool output, argmax indices, conv output): masked and scattered on the way in
 };
 
 template <int KW, int OB>
 __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* __restrict__ ug, const float* __restrict__ w,
+                                                                  const uint8_t* __restrict__ pidx, const float* __restrict__ ypool,
+                                                                  const float* __restrict__ zmask, FastDiv d_fp, FastDiv d_hp,
                                                                   float* __restrict__ dx, RowsGeo g, int accumulate,
                                                                   FastDiv d_w, FastDiv d_howo, FastDiv d_ho, FastDiv d_hw,
                                                                   FastDiv d_o, FastDiv d_c, FastDiv d_howo4, FastDiv d_ho4) {
@@ -517,6 +520,37 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
   cta_image_range(g.N, img_lo, img_cnt);
   for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.IP) {
     const int ng = min(g.IP, img_lo + img_cnt - n0);
+    if (g.pooled) {
+      // ---- ug arrives as the POOLED gradient of a ReLU + 2x2/s2 MaxPool behind this convolution: zero the interiors, then
+      // every pooled element is masked (relu') and dropped at its window's argmax cell; the full gradient never exists in HBM
+      for (int e = tid; e < ng * g.O * g.Ho; e += nthr) {          // interior rows [hl, hl + Wo) of every (img, o, p)
+        uint32_t pl, p, img, o;
+        d_ho.divmod((uint32_t)e, pl, p);
+        d_o.divmod(pl, img, o);
+        uint32_t* row = us + img * g.uimg + o * g.plane + p * g.P + g.hl;
+        for (int q = 0; q < g.Wo; ++q) row[q] = 0u;
+      }
+      __syncthreads();
+      const int64_t base = (int64_t)n0 * g.O * g.Fp;
+      const int raw = ng * g.O * g.Fp;
+#pragma unroll 2
+      for (int e = tid; e < raw; e += nthr) {
+        uint32_t pl, fe, qq, pp, img, o;
+        d_fp.divmod((uint32_t)e, pl, fe);                 // pl = img*O + o; pooled position (p', q') sits at q'*Hp + p'
+        d_hp.divmod(fe, qq, pp);
+        d_o.divmod(pl, img, o);
+        float gv = __ldg(ug + base + e);
+        if (!(__ldg(ypool + base + e) > 0.f)) {           // whole window clamped: argmax = first cell, mask = z_first >= 0
+          const float zv = __ldg(zmask + ((int64_t)n0 * g.O + pl) * HoWo + (2 * pp) * (uint32_t)g.Wo + 2 * qq);
+          gv = zv >= 0.f ? gv : 0.f;
+        }
+        const uint32_t a = pidx[base + e];
+        const uint32_t fx = (2 * pp + (a >> 1)) * (uint32_t)g.Wo + 2 * qq + (a & 1);   // flat index in the stored (Ho, Wo) plane
+        uint32_t q, p;
+        d_ho.divmod(fx, q, p);                            // ... which the convolution reads as position (p, q) = q*Ho + p
+        us[img * g.uimg + o * g.plane + p * g.P + g.hl + q] = to_tf32(gv);
+      }
+    } else
     // ---- stage: global [o][q][p] (p contiguous) -> smem [o][p][hl + q].  The staging costs issue slots, not bandwidth
     // (it was as many instructions as the MMA phase): 128-bit loads along p, one index decomposition per four elements.
     {
@@ -653,8 +687,8 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
 }
 
 template <int KW, int OB>
-static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const RowsGeo& g, int accumulate, size_t smem,
-                             cudaStream_t st) {
+static int launch_dgrad_rows(const float* ug, const float* w, const uint8_t* pidx, const float* ypool, const float* zmask, float* dx,
+                             const RowsGeo& g, int accumulate, size_t smem, cudaStream_t st) {
   // (images per pass = image slots of the block, fixed by its warp count: only the grid is balanced here)
   static bool attr = false;
   if (!attr) {
@@ -671,7 +705,8 @@ static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const R
   if (corun_hint() && occ > 1) occ = (occ + 1) / 2;
   const int64_t passes = ceil_div<int64_t>(g.N, g.IP);
   const int grid = (int)(passes < (int64_t)kNumSMs * occ ? passes : (int64_t)kNumSMs * occ);
-  conv_dgrad_rows_mma_kernel<KW, OB><<<grid, threads, smem, st>>>(ug, w, dx, g, accumulate, FastDiv((uint32_t)g.W),
+  conv_dgrad_rows_mma_kernel<KW, OB><<<grid, threads, smem, st>>>(ug, w, pidx, ypool, zmask, FastDiv((uint32_t)(g.Fp > 0 ? g.Fp : 1)),
+                                                                   FastDiv((uint32_t)(g.Hp > 0 ? g.Hp : 1)), dx, g, accumulate, FastDiv((uint32_t)g.W),
                                                                    FastDiv((uint32_t)(g.Ho * g.Wo)), FastDiv((uint32_t)g.Ho),
                                                                    FastDiv((uint32_t)(g.H * g.W)), FastDiv((uint32_t)g.O), FastDiv((uint32_t)g.C),
                                                                    FastDiv((uint32_t)((g.Ho * g.Wo) / 4 > 0 ? (g.Ho * g.Wo) / 4 : 1)),
@@ -681,14 +716,17 @@ static int launch_dgrad_rows(const float* ug, const float* w, float* dx, const R
 }
 
 int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C, int H, int W, int O, int KH, int KW, int pad,
-                        int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done) {
+                        int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done, const uint8_t* pidx,
+                        const float* ypool, const float* zmask) {
   *done = false;
   if (g_default_engine.load() == NGB_GEMM_SIMT) return NGB_OK;
+  if (pidx && ((Ho & 1) || (Wo & 1))) return NGB_OK;
   if (stride != 1 || pad > KW - 1 || pad > KH - 1 || KH > 8 || C < 3 || C > 8 || W < 8) return NGB_OK;
   const int OB = (O + 7) / 8;
   if (!((KW == 5 || KW == 3) && (OB == 1 || OB == 2)) && !(KW == 3 && OB == 4)) return NGB_OK;
   RowsGeo g;
   g.N = N; g.C = C; g.O = O; g.H = H; g.W = W; g.Ho = Ho; g.Wo = Wo; g.KH = KH; g.pad = pad;
+  g.pooled = pidx ? 1 : 0; g.Hp = Ho / 2; g.Fp = (Ho / 2) * (Wo / 2);
   g.hl = KW - 1 - pad;
   g.P = round_up_mod(Wo + 2 * g.hl, 8, 4);
   g.plane = round_up_mod(Ho * g.P, 32, 8);
@@ -712,7 +750,7 @@ int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C
   const size_t smem = fixed + (size_t)IP * per_img;
   int rc = ensure_init();
   if (rc) return rc;
-#define NGB_ROWS(KW_, OB_) rc = launch_dgrad_rows<KW_, OB_>(ug, w, dx, g, accumulate, smem, st)
+#define NGB_ROWS(KW_, OB_) rc = launch_dgrad_rows<KW_, OB_>(ug, w, pidx, ypool, zmask, dx, g, accumulate, smem, st)
   if (KW == 5 && OB == 1) NGB_ROWS(5, 1);
   else if (KW == 5 && OB == 2) NGB_ROWS(5, 2);
   else if (KW == 3 && OB == 1) NGB_ROWS(3, 1);

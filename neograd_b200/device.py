@@ -365,6 +365,7 @@ class PoolReluGrad:
 
 import os as _os
 POOLED_CONV_GRADS = _os.environ.get('NGB_NO_POOLED') != '1'   # conv weight / bias gradients straight from a pooled gradient
+POOLED_CONV_DGRAD = _os.environ.get('NGB_NO_POOLED_DGRAD') != '1'
 LAZY_FUSION = True   # ReLU -> MaxPool pairs run as fused kernels (set False to materialise every op's output eagerly)
 
 

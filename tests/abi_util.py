@@ -174,6 +174,20 @@ def conv_bgrad_pooled(ug_pool, y_pool, z):
   return host(db)
 
 
+def conv_dgrad_pooled(ug_pool, y_pool, idx, z, w, xshape, pad, stride):
+  """returns None when the geometry is not served by the pooled-gradient kernel"""
+  N, C, H, W = xshape
+  O, _, KH, KW = w.shape
+  dx = torch.full((N, C, H, W), float('nan'), device='cuda')
+  G, Y, I, Z, Wt = dev(ug_pool), dev(y_pool), dev(idx, torch.uint8), dev(z), dev(w)
+  B.ensure_runtime()
+  rc = lib.ngb_conv_dgrad_pooled(ptr(G), ptr(Y), ptr(I), ptr(Z), ptr(Wt), ptr(dx), N, C, H, W, O, KH, KW, pad, stride, 0, st())
+  if rc == B.ERR_UNSUPPORTED:
+    return None
+  B.check(rc)
+  return host(dx)
+
+
 def conv_wgrad_pooled(ug_pool, y_pool, idx, z, x, wshape, pad, stride):
   """returns None when the geometry is not served by the pooled-gradient kernel"""
   N, C, H, W = x.shape

@@ -396,6 +396,11 @@ def test_conv_wgrad_from_pooled_gradient(U, N, C, H, W, O, K):
   close(dw, ops.conv3d_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1), TOLTF32)
   close(U.conv_bgrad(gm.astype(np.float64)), U.conv_bgrad(full.astype(np.float64)), 4 * TOL32)
   close(U.conv_bgrad_pooled(ugp, y, z), full.astype(np.float64).sum(axis=(0, 2, 3)), 4 * TOL32)
+  if C >= 3:                                               # data gradient: the row-decomposed kernel serves 3 <= C <= 8
+    wt = f32(rng.standard_normal((O, C, K, K)) / np.sqrt(C * K * K))
+    dxp = U.conv_dgrad_pooled(ugp, y, idx, z, wt, xin.shape, 0, 1)
+    assert dxp is not None
+    assert np.array_equal(dxp, U.conv_dgrad(full.astype(np.float64), wt, xin.shape, 0, 1))
 
 
 def test_maxpool_relu_fused_rejects_other_geometries(U):
