@@ -147,6 +147,27 @@ def call_work(name, a):
     N, C, H, W, O, KH, KW, pad, stride = a[o:o + 9]
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
     return 4 * (N * C * H * W + O * C * KH * KW + N * O * Ho * Wo), 2 * N * O * C * KH * KW * Ho * Wo
+  if name in ('ngb_conv_dgrad_pooled', 'ngb_conv_wgrad_pooled'):
+    # the conv gradient taken from the 2x2-pooled upstream gradient: per pooling window the kernel needs ug_pool, y_pool
+    # (4 B each), idx (1 B) and ONE z value (4 B) instead of the 4 full-resolution gradient values (16 B)
+    N, C, H, W, O, KH, KW, pad, stride = a[6:15]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    win = N * O * (Ho // 2) * (Wo // 2)
+    return 4 * (N * C * H * W + O * C * KH * KW) + 13 * win, 2 * N * O * C * KH * KW * Ho * Wo
+  if name == 'ngb_conv_bgrad_pooled':
+    win = a[4] * a[5] * (a[6] // 2) * (a[7] // 2)
+    return 12 * win + 4 * a[5], win
+  if name == 'ngb_maxpool_relu_mask':
+    win = a[4] * (a[5] // 2) * (a[6] // 2)
+    return 16 * win, win
+  if name == 'ngb_maxpool_relu_fwd':
+    outer, H, W, KH, KW, pad, stride = a[3:10]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    return 4 * outer * H * W + 5 * outer * Ho * Wo, outer * Ho * Wo * KH * KW
+  if name == 'ngb_maxpool_relu_bwd':
+    outer, H, W, KH, KW, pad, stride = a[4:11]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    return 8 * outer * H * W + 5 * outer * Ho * Wo, outer * Ho * Wo * KH * KW
   if name == 'ngb_conv_bgrad':
     return 4 * (a[2] * a[3] * a[4] + a[3]), a[2] * a[3] * a[4]
   if name in ('ngb_maxpool_fwd', 'ngb_maxpool_bwd'):

@@ -138,11 +138,15 @@ class Tensor:
       if self.shape != ():
         raise ValueError("Shapes of grad and Tensor data must match!")
       upper_grad = DeviceArray.full((), upper_grad)
+      if not self._grad_live and not self._grad_pinned:
+        self._grad, self._grad_live, self._grad_shared = upper_grad, True, False   # our own fresh buffer: no copy needed
+      else:
+        self.accumulate_grad(upper_grad)
     else:
       upper_grad = process_data(upper_grad)
       if self.shape != upper_grad.shape:
         raise ValueError("Shapes of grad and Tensor data must match!")
-    self.accumulate_grad(upper_grad)
+      self.accumulate_grad(upper_grad)
     node = graph.get_node(self)
     try:
       node.backward(retain_graph)
