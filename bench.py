@@ -154,6 +154,15 @@ def call_work(name, a):
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
     win = N * O * (Ho // 2) * (Wo // 2)
     return 4 * (N * C * H * W + O * C * KH * KW) + 13 * win, 2 * N * O * C * KH * KW * Ho * Wo
+  if name == 'ngb_conv_wbgrad_pooled':
+    # weight + bias gradient in one pass: reads x, the pooled gradient and the argmax bytes; one window cell carries gradient
+    N, C, H, W, O, KH, KW, pad, stride = a[7:16]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    win = N * O * (Ho // 2) * (Wo // 2)
+    return 4 * (N * C * H * W + O * C * KH * KW + O) + 5 * win, 2 * win * C * KH * KW + win
+  if name == 'ngb_conv_bgrad_pooled_idx':
+    win = a[3] * a[4] * a[5]
+    return 5 * win + 4 * a[4], win
   if name == 'ngb_conv_bgrad_pooled':
     win = a[4] * a[5] * (a[6] // 2) * (a[7] // 2)
     return 12 * win + 4 * a[5], win

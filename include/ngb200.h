@@ -106,17 +106,31 @@ int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoW
  * input): mask and scatter happen in the kernel's shared memory.  ngb_maxpool_relu_mask writes the compact masked gradient
  * gm[e] = ug_pool[e] * relu'(z at the argmax); the bias gradient (conv.py:323-327) is the sum of gm, computed without
  * writing it by ngb_conv_bgrad_pooled (Ho x Wo = the conv output plane).
+ * idx must be the bytes ngb_maxpool_relu_fwd wrote: bits 0-1 = argmax cell (kh*2 + kw), bit 2 = relu'(z at the argmax);
+ * the conv-gradient kernels take the mask from those bytes (y_pool and z are read by ngb_maxpool_relu_mask and
+ * ngb_conv_bgrad_pooled only).
  * NGB_ERR_UNSUPPORTED -> materialise the gradient with ngb_maxpool_relu_bwd and use ngb_conv_wgrad. */
 int ngb_maxpool_relu_mask(const float* ug_pool, const float* y_pool, const float* z, float* gm, int64_t outer, int64_t H,
                           int64_t W, ngb_stream_t stream);
 int ngb_conv_bgrad_pooled(const float* ug_pool, const float* y_pool, const float* z, float* db, int64_t N, int64_t O,
                           int64_t Ho, int64_t Wo, int accumulate, ngb_stream_t stream);
+/* same sum from ug_pool and the argmax bytes alone (bit 2 = relu'(z at the argmax)); HpWp = pooled positions per plane */
+int ngb_conv_bgrad_pooled_idx(const float* ug_pool, const uint8_t* idx, float* db, int64_t N, int64_t O, int64_t HpWp,
+                              int accumulate, ngb_stream_t stream);
 int ngb_conv_dgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* w,
                           float* dx, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
                           int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);    /* conv.py:299-309 */
 int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* x,
                           float* dw, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
                           int64_t pad, int64_t stride, int accumulate, ngb_stream_t stream);
+/* dw and db (conv.py:311-327) in one call; db may be NULL.  First layers (C <= 3) get both from ONE pass over the pooled
+ * gradient: only the argmax cell of a window carries gradient, so the weight gradient is C*KH*KW fp32 FMAs per (window, o). */
+int ngb_conv_wbgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* x,
+                           float* dw, float* db, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH,
+                           int64_t KW, int64_t pad, int64_t stride, int accumulate_w, int accumulate_b, ngb_stream_t stream);
+/* 1 when ngb_conv_wbgrad_pooled serves the geometry with ONE kernel, else 0 (it then runs the two separate kernels). */
+int ngb_conv_wbgrad_pooled_is_fused(int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                                    int64_t pad, int64_t stride);
 
 /* ---- MaxPool2D / MaxPool3D: neograd/autograd/ops/conv.py:362-542 ------------------------------------------- */
 /* x (outer,H,W) with outer = N or N*C.  y and idx (uint8, position of the FIRST maximum inside the zero-padded
@@ -131,7 +145,10 @@ int ngb_maxpool_bwd(const float* ug, const uint8_t* idx, float* dx, int64_t oute
 /* ReLU -> MaxPool pairs (activations.py:20 followed by conv.py:384-402) without the ReLU's output ever touching HBM:
  *   fwd: y / idx = maxpool(max(0, x));    bwd: dx (+)= (xm >= 0) * maxpool_bwd(ug, idx)   (xm = the ReLU's input).
  * Only 2x2 / stride 2 / pad 0 on 16-byte aligned rows (even H for bwd); other geometries return NGB_ERR_UNSUPPORTED
- * and the caller runs the two ops separately.  Results are bit-identical to the separate kernels. */
+ * and the caller runs the two ops separately.  Results are bit-identical to the separate kernels, except that the fused
+ * forward also records the ReLU gradient at the argmax in bit 2 of every idx byte (1 = gradient flows: the maximum is
+ * positive, or the window was clamped and its first cell is exactly zero or above -- activations.py:31).  Every kernel that
+ * reads the idx of a pool with at most four cells ignores that bit; the pooled conv-gradient kernels above use it. */
 int ngb_maxpool_relu_fwd(const float* x, float* y, uint8_t* idx, int64_t outer, int64_t H, int64_t W,
                          int64_t KH, int64_t KW, int64_t pad, int64_t stride, ngb_stream_t stream);
 int ngb_maxpool_relu_bwd(const float* ug, const uint8_t* idx, const float* xm, float* dx, int64_t outer, int64_t H,

@@ -73,6 +73,9 @@ SIGNATURES = {
   'ngb_conv_bgrad_pooled': ([_P, _P, _P, _P] + [c_int64] * 4 + [c_int, _S], c_int),
   'ngb_conv_dgrad_pooled': ([_P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
   'ngb_conv_wgrad_pooled': ([_P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
+  'ngb_conv_wbgrad_pooled': ([_P, _P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, c_int, _S], c_int),
+  'ngb_conv_wbgrad_pooled_is_fused': ([c_int64] * 9, c_int),
+  'ngb_conv_bgrad_pooled_idx': ([_P, _P, _P, c_int64, c_int64, c_int64, c_int, _S], c_int),
   'ngb_ew_binary_fwd': ([c_int, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, _S], c_int),
   'ngb_ew_binary_bwd': ([c_int, c_int, _P, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, c_int, _S], c_int),
   'ngb_ew_unary_fwd': ([c_int, c_float, _P, _P, c_int64, _S], c_int),
@@ -179,15 +182,24 @@ class _Lanes:
     ev.record()
     return ev
 
-  def run(self, key, fn, keep, ready=None, corun=True):
+  def can_share(self, a, b):
+    """Whether one kernel may write both tensors' gradients: their accumulations must not already sit on different lanes."""
+    la, lb = self.assign.get(id(a)), self.assign.get(id(b))
+    return la is None or lb is None or la == lb
+
+  def run(self, key, fn, keep, ready=None, corun=True, also=None):
     import torch
     if self.streams is None or len(self.streams) != self.n:
       self._init()
     lane = self.assign.get(id(key))
+    if lane is None and also is not None:
+      lane = self.assign.get(id(also))
     if lane is None:                         # all accumulations into one tensor stay on one stream (ordered)
       lane = 1 + self.rr % self.n
       self.rr += 1
-      self.assign[id(key)] = lane
+    self.assign[id(key)] = lane
+    if also is not None:
+      self.assign[id(also)] = lane
     side = self.streams[lane]
     if ready is not None:
       side.wait_event(ready)

@@ -84,13 +84,37 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
       dst, acc = D.DeviceArray.empty(bias.shape), False
     pg = pooled(ug)
     if pg is not None:      # the sum over a plane of the scattered gradient is the sum over its masked pooled form
-      B.check(B.lib.ngb_conv_bgrad_pooled(pg.pug.ptr, pg.ypool.ptr, pg.x.ptr, dst.ptr, N, O, pg.H, pg.W, int(acc), D._st()))
+      B.check(B.lib.ngb_conv_bgrad_pooled_idx(pg.pug.ptr, ctypes.c_void_p(pg.idx.data_ptr()), dst.ptr, N, O,
+                                              (pg.H // 2) * (pg.W // 2), int(acc), D._st()))
       return dst
     B.check(B.lib.ngb_conv_bgrad(ug.ptr, dst.ptr, N, O, ug.size // max(N * O, 1), int(acc), D._st()))
     return dst
 
+  def wbgrad(ug, dst_w, acc_w, dst_b, acc_b):
+    """Weight and bias gradient from ONE pass over a pooled upstream gradient (ngb_conv_wbgrad_pooled); otherwise the two
+    kernels above, one after the other."""
+    pg = pooled(ug)
+    if pg is not None:
+      rc = B.lib.ngb_conv_wbgrad_pooled(pg.pug.ptr, pg.ypool.ptr, ctypes.c_void_p(pg.idx.data_ptr()), pg.x.ptr, x.ptr, dst_w.ptr,
+                                        dst_b.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc_w), int(acc_b), D._st())
+      if rc == 0:
+        return
+      if rc != B.ERR_UNSUPPORTED:
+        B.check(rc)
+    wgrad(ug, dst_w, acc_w)
+    bgrad(ug, dst_b, acc_b)
+
   inputs.set_grad_fn(GradFn(dgrad))
-  kernel.set_grad_fn(GradFn(wgrad, lazy_ok=True))
+  fused = []
+
+  def joint_ok(ug):          # only when ONE kernel yields both: otherwise the two run beside each other on two lanes
+    if pooled(ug) is None:
+      return False
+    if not fused:
+      fused.append(B.lib.ngb_conv_wbgrad_pooled_is_fused(N, C, H, W, O, KH, KW, pad, stride) == 1)
+    return fused[0]
+
+  kernel.set_grad_fn(GradFn(wgrad, lazy_ok=True, joint=(bias, wbgrad, joint_ok)))
   bias.set_grad_fn(GradFn(bgrad, lazy_ok=True))
 
 
@@ -187,7 +211,8 @@ class _MaxPool(Operation, Conv):
     if rc != 0:
       B.check(B.lib.ngb_maxpool_fwd(xin.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), outer, H, W,
                                     self.kernel_shape[0], self.kernel_shape[1], self.padding, self.stride, D._st()))
-    self._idx, self._y = idx, y
+    # only the fused kernel records the ReLU gradient in bit 2 of the argmax bytes, which the pooled conv-gradient kernels read
+    self._idx, self._y = idx, (y if rc == 0 else None)
     return self.get_result_tensor(y, inputs)
 
   def backward(self, inputs):

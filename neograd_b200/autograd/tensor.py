@@ -21,10 +21,14 @@ class GradFn:
   """A grad_fn the engine can fuse.  `into(ug, dst, accumulate)` must write (accumulate=False) or add
   (accumulate=True) the operand-shaped gradient into `dst`; `dst=None` means allocate.  Calling the object like the
   reference's lambdas (`grad_fn(ug) -> array`) still works."""
-  __slots__ = ('into', 'alias', 'lazy', 'lazy_ok')
+  __slots__ = ('into', 'alias', 'lazy', 'lazy_ok', 'joint')
 
-  def __init__(self, into, alias=None, lazy=None, lazy_ok=False):
+  def __init__(self, into, alias=None, lazy=None, lazy_ok=False, joint=None):
     self.into = into
+    # joint = (other_leaf, fn, usable): fn(ug, dst, accumulate, other_dst, other_accumulate) produces this operand's AND
+    # other_leaf's gradient in one go (conv weight + bias from one pass over the upstream gradient) when usable(ug); used by
+    # the backward lanes when both are leaves waiting on the same upstream gradient
+    self.joint = joint
     # lazy_ok: `into` understands a still-deferred upstream gradient (device.LazyArray) and need not have it materialised
     self.lazy_ok = lazy_ok
     # lazy(ug) -> a device.LazyArray standing for this operand's gradient (produced on first use), or None.  Same
@@ -239,6 +243,33 @@ class Tensor:
     if not corun:
       on_main = max(leaves, key=lambda p: p.tens.data.size).tens
       leaves = [p for p in leaves if p.tens is not on_main] + [p for p in leaves if p.tens is on_main]
+    def pending(t):
+      return isinstance(t.grad_fn, GradFn) and not (node.lane_done is not None and id(t) in node.lane_done)
+
+    # leaves whose gradient comes out of another leaf's joint kernel (conv bias beside the conv weight)
+    by_tensor = {id(p.tens): p.tens for p in leaves}
+    partner_of = {}
+    for p in leaves:
+      gf = p.tens.grad_fn
+      if isinstance(gf, GradFn) and gf.joint is not None and pending(p.tens):
+        other = by_tensor.get(id(gf.joint[0]))
+        if (other is not None and other is not p.tens and pending(other) and _lanes.can_share(p.tens, other)
+            and gf.joint[2](upper_grad)):
+          partner_of[id(p.tens)] = other
+    produced_by_partner = {id(o) for o in partner_of.values()}
+
+    def prepare(t):
+      t._ensure_grad_buffer()
+      if t._grad_live:
+        t._unshare_grad()
+      return t._grad, t._grad_live
+
+    def mark(t):
+      t._grad_live = True
+      if node.lane_done is None:
+        node.lane_done = {}
+      node.lane_done[id(t)] = 'lane'
+
     for p in leaves:
       t = p.tens
       gf = t.grad_fn
@@ -247,20 +278,24 @@ class Tensor:
         continue
       if not isinstance(gf, GradFn) or (node.lane_done is not None and id(t) in node.lane_done):
         continue                                     # user-defined grad_fn: the reference's path at the leaf's own visit
+      if id(t) in produced_by_partner:
+        continue
       if ready is None:
         ready = _lanes.mark_ready()                  # main stream: this tensor's gradient is complete
-      t._ensure_grad_buffer()
-      if t._grad_live:
-        t._unshare_grad()
-      dst, live = t._grad, t._grad_live
-      if t is on_main:
-        gf.into(upper_grad, dst, live)               # (issued last: the lanes' waits on `ready` are already queued)
+      dst, live = prepare(t)
+      other = partner_of.get(id(t))
+      if other is not None:
+        odst, olive = prepare(other)
+        fn = lambda gf=gf, dst=dst, live=live, odst=odst, olive=olive: gf.joint[1](upper_grad, dst, live, odst, olive)
       else:
-        _lanes.run(t, lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live), (upper_grad, gf, node), ready, corun)
-      t._grad_live = True
-      if node.lane_done is None:
-        node.lane_done = {}
-      node.lane_done[id(t)] = 'lane'
+        fn = lambda gf=gf, dst=dst, live=live: gf.into(upper_grad, dst, live)
+      if t is on_main:
+        fn()                                         # (issued last: the lanes' waits on `ready` are already queued)
+      else:
+        _lanes.run(t, fn, (upper_grad, gf, node), ready, corun, also=other)
+      mark(t)
+      if other is not None:
+        mark(other)
 
   def _ensure_grad_buffer(self):
     if self._grad is None:

@@ -24,6 +24,10 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
 // conv_small_mma.cu: TF32 mma.sync kernels for small-channel layers (fprop mode 0 / dgrad mode 1, wgrad)
 int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
                     int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done);
+bool conv_sparse_serves(int C, int H, int W, int O, int KH, int KW, int pad, int Ho, int Wo);
+int conv_sparse_wbgrad_pooled(const float* ug, const float* ypool, const uint8_t* pidx, const float* z, const float* x, float* dw,
+                              float* db, int N, int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo,
+                              int acc_w, int acc_b, cudaStream_t st, bool* done);
 int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int H, int W, int O, int KH, int KW, int pad,
                    int stride, int Ho, int Wo, int accumulate, cudaStream_t st, bool* done, const uint8_t* pidx = nullptr,
                    const float* ypool = nullptr, const float* zmask = nullptr);
@@ -751,11 +755,12 @@ static int conv_wgrad_small(const float* ug, const float* x, float* dw, const Co
 // MASKED: ug is the pooled gradient of a Conv -> ReLU -> MaxPool(2x2, s2) block and the sum runs over ug * relu'(z at the
 // window's argmax) -- y (the pool's output) > 0 means mask 1, otherwise the mask is z_first >= 0 (see maxpool_relu_mask_kernel);
 // the bias gradient then needs neither the full-resolution gradient nor the compact masked copy.
-template <bool MASKED>
+// FLAGGED: the mask comes from bit 2 of the pool's argmax bytes instead (ngb_maxpool_relu_fwd): ug and one byte per element.
+template <bool MASKED, bool FLAGGED = false>
 __global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict__ ug, float* __restrict__ part, int64_t N,
                                                          int64_t O, int64_t HW, int64_t imgs_per_split, FastDiv d_hw4, int vec,
                                                          const float* __restrict__ y, const float* __restrict__ z, int Hp, int Wo,
-                                                         FastDiv d_hp) {
+                                                         FastDiv d_hp, const uint8_t* __restrict__ idx = nullptr) {
   __shared__ float red[32];
   const int64_t o = blockIdx.x;
   const int64_t nb = (int64_t)blockIdx.y * imgs_per_split, ne = min(N, nb + imgs_per_split);
@@ -779,7 +784,11 @@ __global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict
       d_hw4.divmod(i, n, f4);
       const int64_t plane = (nb + n) * O + o;
       float4 v = ld_stream4(ug + plane * HW + 4 * (int64_t)f4);
-      if (MASKED) {
+      if (FLAGGED) {
+        const uint32_t a4 = __ldg(reinterpret_cast<const uint32_t*>(idx + plane * HW + 4 * (int64_t)f4));
+        v.x = (a4 & 0x4u) ? v.x : 0.f; v.y = (a4 & 0x400u) ? v.y : 0.f;
+        v.z = (a4 & 0x40000u) ? v.z : 0.f; v.w = (a4 & 0x4000000u) ? v.w : 0.f;
+      } else if (MASKED) {
         const float4 yv = ld_stream4(y + plane * HW + 4 * (int64_t)f4);
         v.x = masked(v.x, yv.x, plane, 4 * f4); v.y = masked(v.y, yv.y, plane, 4 * f4 + 1);
         v.z = masked(v.z, yv.z, plane, 4 * f4 + 2); v.w = masked(v.w, yv.w, plane, 4 * f4 + 3);
@@ -792,7 +801,8 @@ __global__ void __launch_bounds__(256) conv_bgrad_kernel(const float* __restrict
     for (int64_t i = threadIdx.x; i < span; i += blockDim.x) {
       const int64_t n = nb + i / HW, f = i % HW;
       float v = ug[(n * O + o) * HW + f];
-      if (MASKED) v = masked(v, y[(n * O + o) * HW + f], n * O + o, (uint32_t)f);
+      if (FLAGGED) v = (idx[(n * O + o) * HW + f] & 4) ? v : 0.f;
+      else if (MASKED) v = masked(v, y[(n * O + o) * HW + f], n * O + o, (uint32_t)f);
       acc += v;
     }
   }
@@ -946,6 +956,9 @@ extern "C" int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, 
   NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr && z != nullptr, "ngb_conv_wgrad_pooled needs the pool output, its argmax indices and the conv output");
   if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wgrad_pooled: empty batch");
   bool done = false;
+  rc = conv_sparse_wbgrad_pooled(ug_pool, y_pool, idx, z, x, dw, nullptr, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho,
+                                 g.Wo, accumulate, 0, as_stream(stream), &done);
+  if (rc || done) return rc;
   rc = conv_mma_wgrad(ug_pool, x, dw, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, accumulate, as_stream(stream),
                       &done, idx, y_pool, z);
   if (rc) return rc;
@@ -954,7 +967,7 @@ extern "C" int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, 
 }
 
 static int conv_bgrad_impl(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate, const float* y,
-                           const float* z, int64_t Hp, int64_t Wo_full, ngb_stream_t stream) {
+                           const float* z, int64_t Hp, int64_t Wo_full, ngb_stream_t stream, const uint8_t* idx) {
   NGB_CHECK_ARG(N >= 0 && O >= 1 && HoWo >= 0, "conv bgrad: bad dimensions");
   cudaStream_t st = as_stream(stream);
   if (N == 0 || HoWo == 0) {
@@ -972,9 +985,12 @@ static int conv_bgrad_impl(const float* ug, float* db, int64_t N, int64_t O, int
   const int64_t ips = ceil_div<int64_t>(N, splits);
   splits = ceil_div<int64_t>(N, ips);
   dim3 grid((unsigned)O, (unsigned)splits);
-  const int vec = (HoWo % 4 == 0) && aligned16(ug) && (y == nullptr || aligned16(y)) && (ips * (HoWo / 4) < (int64_t(1) << 32));
+  const int vec = (HoWo % 4 == 0) && aligned16(ug) && (y == nullptr || aligned16(y)) && (ips * (HoWo / 4) < (int64_t(1) << 32)) &&
+                  (idx == nullptr || (reinterpret_cast<uintptr_t>(idx) & 3) == 0);
   const FastDiv dhw4((uint32_t)(vec ? HoWo / 4 : 1)), dhp((uint32_t)(Hp > 0 ? Hp : 1));
-  if (y)
+  if (idx)
+    conv_bgrad_kernel<false, true><<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips, dhw4, vec, nullptr, nullptr, 1, 1, dhp, idx);
+  else if (y)
     conv_bgrad_kernel<true><<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips, dhw4, vec, y, z, (int)Hp, (int)Wo_full, dhp);
   else
     conv_bgrad_kernel<false><<<grid, 256, 0, st>>>(ug, scratch_ptr(), N, O, HoWo, ips, dhw4, vec, nullptr, nullptr, 1, 1, dhp);
@@ -984,7 +1000,46 @@ static int conv_bgrad_impl(const float* ug, float* db, int64_t N, int64_t O, int
 
 extern "C" int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate,
                               ngb_stream_t stream) {
-  return conv_bgrad_impl(ug, db, N, O, HoWo, accumulate, nullptr, nullptr, 0, 0, stream);
+  return conv_bgrad_impl(ug, db, N, O, HoWo, accumulate, nullptr, nullptr, 0, 0, stream, nullptr);
+}
+
+static int conv_bgrad_impl(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo, int accumulate, const float* y,
+                           const float* z, int64_t Hp, int64_t Wo_full, ngb_stream_t stream, const uint8_t* idx = nullptr);
+
+// Weight AND bias gradient (conv.py:311-327) of conv -> ReLU -> MaxPool(2x2, s2) from the pooled upstream gradient in one call:
+// first layers with few input channels get both from one pass over the pooled gradient (sparse fp32 kernel); other geometries
+// run ngb_conv_wgrad_pooled + ngb_conv_bgrad_pooled.  db may be NULL.
+extern "C" int ngb_conv_wbgrad_pooled(const float* ug_pool, const float* y_pool, const uint8_t* idx, const float* z, const float* x,
+                                      float* dw, float* db, int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH,
+                                      int64_t KW, int64_t pad, int64_t stride, int accumulate_w, int accumulate_b,
+                                      ngb_stream_t stream) {
+  ConvGeo g;
+  int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
+  if (rc) return rc;
+  NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr && z != nullptr, "ngb_conv_wbgrad_pooled needs the pool output, its argmax indices and the conv output");
+  if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wbgrad_pooled: empty batch");
+  if ((g.Ho & 1) || (g.Wo & 1)) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wbgrad_pooled: odd conv output plane");
+  bool done = false;
+  rc = conv_sparse_wbgrad_pooled(ug_pool, y_pool, idx, z, x, dw, db, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo,
+                                 accumulate_w, accumulate_b, as_stream(stream), &done);
+  if (rc || done) return rc;
+  rc = conv_mma_wgrad(ug_pool, x, dw, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, accumulate_w, as_stream(stream),
+                      &done, idx, y_pool, z);
+  if (rc) return rc;
+  if (!done) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wbgrad_pooled: geometry not served by the pooled weight-gradient kernels");
+  if (db) return conv_bgrad_impl(ug_pool, db, g.N, g.O, (g.Ho / 2) * (g.Wo / 2), accumulate_b, nullptr, nullptr, 0, 0, stream, idx);
+  return NGB_OK;
+}
+
+// 1 when ngb_conv_wbgrad_pooled serves this geometry with ONE kernel (callers that would otherwise overlap the weight and
+// the bias gradient on two streams ask first), 0 otherwise.
+extern "C" int ngb_conv_wbgrad_pooled_is_fused(int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                                               int64_t pad, int64_t stride) {
+  if (stride < 1 || pad < 0 || N < 1 || C < 1 || O < 1 || KH < 1 || KW < 1 || H + 2 * pad < KH || W + 2 * pad < KW ||
+      N * C * H * W >= (int64_t(1) << 40))
+    return 0;
+  const int Ho = (int)((H + 2 * pad - KH) / stride + 1), Wo = (int)((W + 2 * pad - KW) / stride + 1);
+  return conv_sparse_serves((int)C, (int)H, (int)W, (int)O, (int)KH, (int)KW, (int)pad, Ho, Wo) ? 1 : 0;
 }
 
 // dx (+)= data gradient (conv.py:299-309) of a convolution followed by ReLU and a 2x2 / stride 2 MaxPool, straight from the
@@ -1005,11 +1060,19 @@ extern "C" int ngb_conv_dgrad_pooled(const float* ug_pool, const float* y_pool, 
   return NGB_OK;
 }
 
+// db (+)= sum over n and pooled positions of ug_pool where bit 2 of the argmax byte (ngb_maxpool_relu_fwd: relu'(z at the
+// argmax)) is set: the bias gradient from ug_pool and one byte per element.  HpWp = pooled positions per (n, o) plane.
+extern "C" int ngb_conv_bgrad_pooled_idx(const float* ug_pool, const uint8_t* idx, float* db, int64_t N, int64_t O, int64_t HpWp,
+                                         int accumulate, ngb_stream_t stream) {
+  NGB_CHECK_ARG(idx != nullptr, "ngb_conv_bgrad_pooled_idx needs the argmax bytes of ngb_maxpool_relu_fwd");
+  return conv_bgrad_impl(ug_pool, db, N, O, HpWp, accumulate, nullptr, nullptr, 0, 0, stream, idx);
+}
+
 // db (+)= bias gradient of a convolution followed by ReLU and a 2x2 / stride 2 MaxPool, straight from the pooled upstream
 // gradient: sum over n and pooled positions of ug_pool * relu'(z at the argmax).  Ho x Wo = the conv output plane (even).
 extern "C" int ngb_conv_bgrad_pooled(const float* ug_pool, const float* y_pool, const float* z, float* db, int64_t N, int64_t O,
                                      int64_t Ho, int64_t Wo, int accumulate, ngb_stream_t stream) {
   NGB_CHECK_ARG(y_pool != nullptr && z != nullptr && Ho >= 2 && Wo >= 2 && Ho % 2 == 0 && Wo % 2 == 0,
                 "ngb_conv_bgrad_pooled: needs the pool output, the conv output and an even output plane");
-  return conv_bgrad_impl(ug_pool, db, N, O, (Ho / 2) * (Wo / 2), accumulate, y_pool, z, Ho / 2, Wo, stream);
+  return conv_bgrad_impl(ug_pool, db, N, O, (Ho / 2) * (Wo / 2), accumulate, y_pool, z, Ho / 2, Wo, stream, nullptr);
 }

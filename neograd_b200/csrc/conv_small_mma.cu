@@ -13,6 +13,10 @@
 //
 // All kernels: a persistent CTA stages G whole images (TF32-rounded, zero halo for padding) in shared memory and walks
 // its share of the batch.  Exact-fp32 mode (ngb_set_default_engine(NGB_GEMM_SIMT)) never comes here.
+#include <array>
+#include <map>
+#include <mutex>
+
 #include "common.cuh"
 
 #include <type_traits>
@@ -539,12 +543,9 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
         d_fp.divmod((uint32_t)e, pl, fe);                 // pl = img*O + o; pooled position (p', q') sits at q'*Hp + p'
         d_hp.divmod(fe, qq, pp);
         d_o.divmod(pl, img, o);
-        float gv = __ldg(ug + base + e);
-        if (!(__ldg(ypool + base + e) > 0.f)) {           // whole window clamped: argmax = first cell, mask = z_first >= 0
-          const float zv = __ldg(zmask + ((int64_t)n0 * g.O + pl) * HoWo + (2 * pp) * (uint32_t)g.Wo + 2 * qq);
-          gv = zv >= 0.f ? gv : 0.f;
-        }
-        const uint32_t a = pidx[base + e];
+        const uint32_t ab = pidx[base + e];                // bits 0-1: argmax cell, bit 2: relu'(z at the argmax)
+        const float gv = (ab & 4u) ? __ldg(ug + base + e) : 0.f;
+        const uint32_t a = ab & 3u;
         const uint32_t fx = (2 * pp + (a >> 1)) * (uint32_t)g.Wo + 2 * qq + (a & 1);   // flat index in the stored (Ho, Wo) plane
         uint32_t q, p;
         d_ho.divmod(fx, q, p);                            // ... which the convolution reads as position (p, q) = q*Ho + p
@@ -771,7 +772,8 @@ int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C
 struct WgradGeo {
   int N, C, O, KH, KW, Ho;
   int raw_rows, raw_cols, raw_plane, halo;   // x plane
-  int spitch, splane, ximg;                  // staged x
+  int sr, sc, splane, ximg;                  // staged x: element (c, r, col) at c*splane + r*sr + col*sc (layout search below)
+  int khfast;                                // A rows of one channel ordered kw*KH + kh instead of kh*KW + kw
   int F, F8, KSI, Up, NP, uimg;              // staged ug: [NP][Up] per image, zero tail
   int CKK, Mrows;                            // filter elements per output channel; rows covered by the warps (MS*MTW*16)
   int a_mod, a_div;                          // poff(f) = (f % Ho) * a_mod + (f / Ho) * a_div
@@ -780,13 +782,20 @@ struct WgradGeo {
   int pooled, Wo, Fp, Hp;                    // ug is a 2x2-pooled gradient + argmax indices: scattered into the staged tile
 };
 
-template <int MTW, int NT>
+// PF: register-prefetched staging for the pooled form (host-checked: xcontig, 16-byte aligned operands, Hp % 4 == 0, one group's
+// x <= kPFX and its pooled gradient <= kPFU 128-bit units per thread).  The global loads of group i+1 are issued before the MMA
+// phase of group i and land in registers while the tensor pipe works; the pooled windows are written as whole 2x2 cells
+// (value at the argmax, zeros elsewhere), so the tile needs no separate zeroing pass -- two barriers per group, and no global
+// latency between them.  (ncu, non-PF: 36 % / 22 % issue utilisation, warps parked on long-scoreboard and barrier stalls.)
+constexpr int kPFX = 4, kPFU = 2;
+template <int MTW, int NT, bool PF>
 __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __restrict__ ug, const float* __restrict__ x,
                                                              const uint8_t* __restrict__ pidx, const float* __restrict__ ypool,
                                                              const float* __restrict__ zmask, float* __restrict__ part, WgradGeo g,
                                                              FastDiv d_fp, FastDiv d_hp, FastDiv d_plane,
                                                              FastDiv d_cols, FastDiv d_ho, FastDiv d_ksi, FastDiv d_kk,
-                                                             FastDiv d_kw, FastDiv d_f, FastDiv d_ckk, FastDiv d_o) {
+                                                             FastDiv d_kw, FastDiv d_f, FastDiv d_ckk, FastDiv d_o,
+                                                             FastDiv d_fp4, FastDiv d_wp, FastDiv d_kh) {
   extern __shared__ __align__(16) uint32_t smem_u[];
   int* moff = reinterpret_cast<int*>(smem_u);          // [Mrows]
   int* poff = moff + g.Mrows;                          // [F8]
@@ -798,14 +807,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
   const int ms = warp % g.MS, kq = warp / g.MS;
 
   for (int m = tid; m < g.Mrows; m += nthr) {
-    int off = 0;
-    if (m < g.CKK) {
-      uint32_t c, tap, kh, kw;
-      d_kk.divmod((uint32_t)m, c, tap);
-      d_kw.divmod(tap, kh, kw);
-      off = (int)c * g.splane + (int)kh * g.spitch + (int)kw;
-    }
-    moff[m] = off * 4;   // byte offset
+    // rows past the last filter element repeat it: their lanes then read words another lane reads anyway (a broadcast, not
+    // a bank conflict); their accumulators are never written out
+    uint32_t c, tap, kh, kw;
+    d_kk.divmod((uint32_t)min(m, g.CKK - 1), c, tap);
+    if (g.khfast) d_kh.divmod(tap, kw, kh); else d_kw.divmod(tap, kh, kw);
+    moff[m] = ((int)c * g.splane + (int)kh * g.sr + (int)kw * g.sc) * 4;   // byte offset
   }
   for (int f = tid; f < g.F8; f += nthr) {
     int off = 0;
@@ -841,9 +848,87 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
   const int xraw_img = g.C * g.raw_plane, uraw_img = g.O * g.F;
   int img_lo, img_cnt;
   cta_image_range(g.N, img_lo, img_cnt);
+  // ---- PF state: one group's global data in flight
+  float4 pfx[kPFX], pfg[kPFU];
+  uint32_t pfa[kPFU];
+  const int pad_planes_pf = g.NP - g.O;
+  auto prefetch = [&](int n0, int ng) {
+    const float* src = x + (int64_t)n0 * xraw_img;
+    const int raw4 = (ng * xraw_img) >> 2;
+#pragma unroll
+    for (int i = 0; i < kPFX; ++i) {
+      const int e4 = tid + i * nthr;
+      if (e4 < raw4) pfx[i] = ld_stream4(src + 4 * (int64_t)e4);
+    }
+    const int64_t base = (int64_t)n0 * g.O * g.Fp;
+    const int raw4u = (ng * g.O * g.Fp) >> 2;
+#pragma unroll
+    for (int i = 0; i < kPFU; ++i) {
+      const int e4 = tid + i * nthr;
+      if (e4 < raw4u) {
+        // unit = four pooled positions p' = 4*pg .. 4*pg+3 of column q' (pooled (p', q') sits at q'*Hp + p').  Consecutive
+        // lanes take consecutive q': their scattered 64-bit stores then sit side by side (with p' fastest they were
+        // 8*Wo words apart = the same banks: 3-way conflicts in the ncu source view)
+        uint32_t pl, u, pg, q;
+        d_fp4.divmod((uint32_t)e4, pl, u);             // pl = img*O + o
+        d_wp.divmod(u, pg, q);
+        const uint32_t p = 4u * pg;
+        const int64_t off = base + (int64_t)pl * g.Fp + q * (uint32_t)g.Hp + p;
+        pfg[i] = ld_stream4(ug + off);
+        pfa[i] = __ldg(reinterpret_cast<const uint32_t*>(pidx + off));   // per byte: argmax cell | relu'(z at the argmax) << 2
+      }
+    }
+  };
+  auto commit = [&](int ng) {
+    const int raw4 = (ng * xraw_img) >> 2;
+#pragma unroll
+    for (int i = 0; i < kPFX; ++i) {
+      const int e4 = tid + i * nthr;
+      if (e4 < raw4) {
+        const float4 v = pfx[i];
+        if (g.xcontig) {
+          *reinterpret_cast<uint4*>(xs + 4 * e4) = make_uint4(to_tf32(v.x), to_tf32(v.y), to_tf32(v.z), to_tf32(v.w));
+        } else {   // four elements of one row (raw_cols % 4 == 0) into the searched layout
+          uint32_t pl, f, r, c;
+          d_plane.divmod((uint32_t)e4 * 4u, pl, f);
+          d_cols.divmod(f, r, c);
+          uint32_t* d = xs + pl * g.splane + (r + g.halo) * g.sr + (c + g.halo) * g.sc;
+          d[0] = to_tf32(v.x); d[g.sc] = to_tf32(v.y); d[2 * g.sc] = to_tf32(v.z); d[3 * g.sc] = to_tf32(v.w);
+        }
+      }
+    }
+    const int raw4u = (ng * g.O * g.Fp) >> 2;
+#pragma unroll
+    for (int i = 0; i < kPFU; ++i) {
+      const int e4 = tid + i * nthr;
+      if (e4 < raw4u) {
+        uint32_t pl, u, pg, q;
+        d_fp4.divmod((uint32_t)e4, pl, u);
+        d_wp.divmod(u, pg, q);
+        const uint32_t p = 4u * pg;
+        const uint32_t img = d_o.div(pl);
+        uint32_t* row = us + (pl + img * pad_planes_pf) * g.Up + 2 * q + (2 * p) * (uint32_t)g.Wo;
+        const float gs[4] = {pfg[i].x, pfg[i].y, pfg[i].z, pfg[i].w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const uint32_t ab = (pfa[i] >> (8 * j)) & 0xFFu, a = ab & 3u;
+          const uint32_t tv = to_tf32((ab & 4u) ? gs[j] : 0.f);
+          // the window's 2x2 cells: row kh = a >> 1, column kw = a & 1 holds the value
+          *reinterpret_cast<uint2*>(row + (2 * j) * g.Wo) = make_uint2(a == 0u ? tv : 0u, a == 1u ? tv : 0u);
+          *reinterpret_cast<uint2*>(row + (2 * j + 1) * g.Wo) = make_uint2(a == 2u ? tv : 0u, a == 3u ? tv : 0u);
+        }
+      }
+    }
+  };
+  if constexpr (PF) {
+    if (img_cnt > 0) prefetch(img_lo, min(g.G, img_cnt));
+  }
   for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.G) {
     const int ng = min(g.G, img_lo + img_cnt - n0);
     __syncthreads();
+    if constexpr (PF) {
+      commit(ng);
+    } else {
     if (g.xcontig) {  // ---- x: staged image == raw image
       const float* src = x + (int64_t)n0 * xraw_img;
       const int raw = ng * xraw_img;
@@ -869,7 +954,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
         const float vv[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          xs[pl * g.splane + (r + g.halo) * g.spitch + c + g.halo] = to_tf32(vv[j]);
+          xs[pl * g.splane + (r + g.halo) * g.sr + (c + g.halo) * g.sc] = to_tf32(vv[j]);
           if (++c == (uint32_t)g.raw_cols) {
             c = 0;
             if (++r == (uint32_t)g.raw_rows) { r = 0; ++pl; }
@@ -880,7 +965,7 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
         uint32_t pl, f, r, c;
         d_plane.divmod((uint32_t)e, pl, f);
         d_cols.divmod(f, r, c);
-        xs[pl * g.splane + (r + g.halo) * g.spitch + c + g.halo] = to_tf32(__ldg(src + e));
+        xs[pl * g.splane + (r + g.halo) * g.sr + (c + g.halo) * g.sc] = to_tf32(__ldg(src + e));
       }
     }
     if (g.pooled) {
@@ -892,16 +977,8 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
       const int64_t base = (int64_t)n0 * g.O * g.Fp;
       const int raw = ng * g.O * g.Fp;
       const int pad_planes = g.NP - g.O;
-      // value of pooled element e: ug[e] * relu'(z at the window's argmax).  y > 0: the argmax cell passed the ReLU (mask 1);
-      // y == 0: the whole window was clamped, the argmax is its first cell and the mask is z_first >= 0 (activations.py:31).
-      auto masked = [&](float gv, float yv, uint32_t pl, uint32_t p, uint32_t q) {
-        if (!(yv > 0.f)) {
-          const float zv = __ldg(zmask + ((int64_t)n0 * g.O + pl) * g.F + (2 * p) * (uint32_t)g.Wo + 2 * q);
-          gv = zv >= 0.f ? gv : 0.f;
-        }
-        return gv;
-      };
-      if ((g.Hp & 3) == 0 && (((uintptr_t)(ug + base) | (uintptr_t)(ypool + base)) & 15u) == 0 && ((uintptr_t)(pidx + base) & 3u) == 0) {
+      // value of pooled element e: ug[e] * relu'(z at the window's argmax) = bit 2 of the argmax byte (ngb_maxpool_relu_fwd)
+      if ((g.Hp & 3) == 0 && ((uintptr_t)(ug + base) & 15u) == 0 && ((uintptr_t)(pidx + base) & 3u) == 0) {
         // four pooled positions along p' per thread: one index decomposition, 128-bit loads of ug / y, 32-bit load of idx
 #pragma unroll 2
         for (int e4 = tid; e4 < (raw >> 2); e4 += nthr) {
@@ -910,14 +987,13 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
           d_hp.divmod(fe, q, p);
           const uint32_t img = d_o.div(pl);
           const float4 gv = ld_stream4(ug + base + 4 * (int64_t)e4);
-          const float4 yv = ld_stream4(ypool + base + 4 * (int64_t)e4);
           const uint32_t a4 = *reinterpret_cast<const uint32_t*>(pidx + base + 4 * (int64_t)e4);
           uint32_t* row = us + (pl + img * pad_planes) * g.Up + 2 * q;
-          const float gs[4] = {gv.x, gv.y, gv.z, gv.w}, ys[4] = {yv.x, yv.y, yv.z, yv.w};
+          const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
-            const uint32_t a = (a4 >> (8 * j)) & 0xFFu;
-            row[(2 * (p + j) + (a >> 1)) * (uint32_t)g.Wo + (a & 1)] = to_tf32(masked(gs[j], ys[j], pl, p + j, q));
+            const uint32_t ab = (a4 >> (8 * j)) & 0xFFu, a = ab & 3u;
+            row[(2 * (p + j) + (a >> 1)) * (uint32_t)g.Wo + (a & 1)] = to_tf32((ab & 4u) ? gs[j] : 0.f);
           }
         }
       } else {
@@ -927,9 +1003,9 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
           d_fp.divmod((uint32_t)e, pl, fe);
           d_hp.divmod(fe, q, p);
           const uint32_t img = d_o.div(pl);
-          const uint32_t a = pidx[base + e];              // argmax inside the window, row-major (kh, kw)
+          const uint32_t ab = pidx[base + e], a = ab & 3u;   // argmax inside the window, row-major (kh, kw)
           const uint32_t f = (2 * p + (a >> 1)) * (uint32_t)g.Wo + 2 * q + (a & 1);
-          us[(pl + img * pad_planes) * g.Up + f] = to_tf32(masked(__ldg(ug + base + e), __ldg(ypool + base + e), pl, p, q));
+          us[(pl + img * pad_planes) * g.Up + f] = to_tf32((ab & 4u) ? __ldg(ug + base + e) : 0.f);
         }
       }
     } else
@@ -957,7 +1033,12 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
         }
       }
     }
+    }  // !PF
     __syncthreads();
+    if constexpr (PF) {
+      const int nn = n0 + g.G;
+      if (nn < img_lo + img_cnt) prefetch(nn, min(g.G, img_lo + img_cnt - nn));
+    }
 
     // warp kq takes k-steps kq, kq+KS, ... of EVERY image (no index division in the loop; per-image bases are hoisted:
     // the kernel is issue-bound, every integer instruction in this loop costs as much as a load)
@@ -1017,25 +1098,111 @@ __global__ void __launch_bounds__(256) conv_wgrad_mma_kernel(const float* __rest
   for (int e = tid; e < nw; e += nthr) {
     uint32_t o, m;
     d_ckk.divmod((uint32_t)e, o, m);
+    if (g.khfast) {   // A row of filter element (c, kh, kw)
+      uint32_t c, tap, kh, kw;
+      d_kk.divmod(m, c, tap);
+      d_kw.divmod(tap, kh, kw);
+      m = c * (uint32_t)(g.KH * g.KW) + kw * (uint32_t)g.KH + kh;
+    }
     part[(int64_t)blockIdx.x * nw + e] = red[m * NR + o];
   }
 }
 
-template <int MTW, int NT>
+// Layout of the staged x tile.  Lane (gq, t) of an A-fragment load reads word moff[row gq] + poff[position t]: 8 filter
+// elements x 4 output positions of one k-step.  Words that coincide (filter tap + position shift reach the same pixel) are
+// broadcasts; DIFFERENT words in one bank serialise (the natural pitch gave 2 wavefronts on every gather load: ncu source
+// view, profiles/).  The row / column strides, the plane pitch and the order of the taps in the A rows are free, so the host
+// searches them for the fewest wavefronts per load, then the smallest tile; the result is cached per geometry.
+struct XLayout { int sr, sc, splane, khfast; float wavefronts; };
+
+static float layout_cost(int C, int KH, int KW, int Ho, int F, int stride, int Mrows, int sr, int sc, int splane, int khfast) {
+  const int CKK = C * KH * KW, KSI = (F + 7) / 8;
+  int nks = (Ho % 8 == 0) ? 2 : 2 * ((Ho + 7) / 8) + 1;   // k-steps never straddle a column when Ho % 8 == 0: the pattern repeats
+  if (nks > KSI) nks = KSI;
+  long tot = 0, n = 0;
+  int mo[8], po[4];
+  for (int ks = 0; ks < nks; ++ks)
+    for (int par = 0; par < 2; ++par) {
+      for (int t = 0; t < 4; ++t) {
+        int f = 8 * ks + 2 * t + par;
+        if (f >= F) f = F - 1;
+        po[t] = ((f % Ho) * sr + (f / Ho) * sc) * stride;
+      }
+      for (int rg = 0; rg < Mrows / 8; ++rg) {
+        for (int gq = 0; gq < 8; ++gq) {
+          int m = rg * 8 + gq;
+          if (m > CKK - 1) m = CKK - 1;
+          const int c = m / (KH * KW), tap = m % (KH * KW);
+          const int kh = khfast ? tap % KH : tap / KW, kw = khfast ? tap / KH : tap % KW;
+          mo[gq] = c * splane + kh * sr + kw * sc;
+        }
+        int words[32][4], cnt[32] = {0};
+        int worst = 1;
+        for (int gq = 0; gq < 8; ++gq)
+          for (int t = 0; t < 4; ++t) {
+            const int w = mo[gq] + po[t], b = w & 31;
+            bool seen = false;
+            for (int k = 0; k < cnt[b] && k < 4; ++k) seen |= (words[b][k] == w);
+            if (!seen) {
+              if (cnt[b] < 4) words[b][cnt[b]] = w;
+              ++cnt[b];
+              if (cnt[b] > worst) worst = cnt[b];
+            }
+          }
+        tot += worst;
+        ++n;
+      }
+    }
+  return (float)tot / (float)n;
+}
+
+static XLayout search_x_layout(int C, int H, int W, int KH, int KW, int pad, int stride, int Ho, int Wo, int Mrows) {
+  static std::mutex mu;
+  static std::map<std::array<int, 10>, XLayout> cache;
+  const std::array<int, 10> key = {C, H, W, KH, KW, pad, stride, Ho, Wo, Mrows};
+  std::lock_guard<std::mutex> lk(mu);
+  auto it = cache.find(key);
+  if (it != cache.end()) return it->second;
+  const int R = H + 2 * pad, Cc = W + 2 * pad;
+  XLayout best{Cc, 1, R * Cc, 0, 1e9f};
+  long best_size = 0;
+  for (int tr = 0; tr < 2; ++tr)            // tr: columns strided, rows contiguous
+    for (int S = (tr ? R : Cc); S < (tr ? R : Cc) + 32; ++S) {
+      const int foot = S * (tr ? Cc : R);
+      for (int P = foot; P < foot + (C > 1 ? 32 : 4); ++P) {
+        if ((C * P) & 3) continue;             // images stay 16-byte multiples: plane index img*C + c addresses the group
+        for (int kf = 0; kf < 2; ++kf) {
+          const int sr = tr ? 1 : S, sc = tr ? S : 1;
+          const float c = layout_cost(C, KH, KW, Ho, Ho * Wo, stride, Mrows, sr, sc, P, kf);
+          const long size = (long)C * P;
+          // 2 % of a wavefront is not worth a bigger tile; otherwise fewer wavefronts first
+          if (c < best.wavefronts - 0.02f || (c < best.wavefronts + 0.02f && size < best_size)) {
+            best = XLayout{sr, sc, P, kf, c};
+            best_size = size;
+          }
+        }
+        if (C == 1) break;
+      }
+    }
+  cache[key] = best;
+  return best;
+}
+
+template <int MTW, int NT, bool PF>
 static int launch_wgrad(const float* ug, const float* x, const uint8_t* pidx, const float* ypool, const float* zmask, float* part,
                         WgradGeo g, int nwarps, int gmin, int gmax, size_t fixed, size_t per_img, int* grid_out, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     // maximum shared-memory carveout: a kernel of another lane can only become co-resident on an SM whose L1 / shared split
     // already has room for it -- with the default (smallest fitting) split the second kernel waits for the first to drain
-    NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
+    NGB_CUDA(cudaFuncSetAttribute(conv_wgrad_mma_kernel<MTW, NT, PF>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   // Beside the data-gradient chain (ngb_set_corun) a persistent grid at full occupancy would hold every register of
   // every SM until it ends and stall the chain's next kernel: balance_images then leaves half of each SM free.
   int grid_i = 1;
-  int rc = balance_images(conv_wgrad_mma_kernel<MTW, NT>, nwarps * 32, fixed, per_img, g.N, gmin, gmax, corun_hint() != 0, &g.G,
+  int rc = balance_images(conv_wgrad_mma_kernel<MTW, NT, PF>, nwarps * 32, fixed, per_img, g.N, gmin, gmax, corun_hint() != 0, &g.G,
                           &grid_i);
   if (rc) return rc;
   const size_t smem = fixed + (size_t)g.G * per_img;
@@ -1044,11 +1211,12 @@ static int launch_wgrad(const float* ug, const float* x, const uint8_t* pidx, co
   if (grid * nwts * 4 > scratch_bytes()) grid = scratch_bytes() / (nwts * 4);
   if (grid < 1) return fail(NGB_ERR_SCRATCH, "conv wgrad: scratch arena too small for %lld filter elements", (long long)nwts);
   *grid_out = (int)grid;
-  conv_wgrad_mma_kernel<MTW, NT><<<(unsigned)grid, nwarps * 32, smem, st>>>(
+  conv_wgrad_mma_kernel<MTW, NT, PF><<<(unsigned)grid, nwarps * 32, smem, st>>>(
       ug, x, pidx, ypool, zmask, part, g, FastDiv((uint32_t)(g.Fp > 0 ? g.Fp : 1)), FastDiv((uint32_t)(g.Hp > 0 ? g.Hp : 1)),
       FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.Ho),
       FastDiv((uint32_t)g.KSI), FastDiv((uint32_t)(g.KH * g.KW)), FastDiv((uint32_t)g.KW), FastDiv((uint32_t)g.F),
-      FastDiv((uint32_t)g.CKK), FastDiv((uint32_t)g.O));
+      FastDiv((uint32_t)g.CKK), FastDiv((uint32_t)g.O), FastDiv((uint32_t)(g.Fp >= 4 ? g.Fp / 4 : 1)),
+      FastDiv((uint32_t)(g.Wo >= 2 ? g.Wo / 2 : 1)), FastDiv((uint32_t)g.KH));
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
@@ -1067,22 +1235,26 @@ int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int
   g.pooled = pidx ? 1 : 0; g.Wo = Wo; g.Hp = Ho / 2; g.Fp = (Ho / 2) * (Wo / 2);
   g.N = N; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.Ho = Ho;
   g.raw_rows = H; g.raw_cols = W; g.raw_plane = H * W; g.halo = pad;
-  g.spitch = round_up_mod(W + 2 * pad, 8, 4);
-  g.splane = (H + 2 * pad) * g.spitch;
-  g.ximg = C * g.splane;               // multiple of 4 (spitch is)
-  g.xcontig = (pad == 0 && g.spitch == W) ? 1 : 0;
+  const int mt_total = ceil_div(C * KH * KW, 16);
+  g.MS = ceil_div(mt_total, 5);
+  if (g.MS > 8) return NGB_OK;
+  const int MTW = ceil_div(mt_total, g.MS);
+  g.Mrows = g.MS * MTW * 16;
+  if (getenv("NGB_WGRAD_NATURAL_LAYOUT")) {   // experiments: the pre-search layout
+    g.sr = round_up_mod(W + 2 * pad, 8, 4); g.sc = 1; g.splane = (H + 2 * pad) * g.sr; g.khfast = 0;
+  } else {
+    const XLayout L = search_x_layout(C, H, W, KH, KW, pad, stride, Ho, Wo, g.Mrows);
+    g.sr = L.sr; g.sc = L.sc; g.splane = L.splane; g.khfast = L.khfast;
+  }
+  g.ximg = C * g.splane;               // multiple of 4 (search constraint)
+  g.xcontig = (pad == 0 && g.sc == 1 && g.sr == W && g.splane == H * W) ? 1 : 0;
   g.F = Ho * Wo; g.F8 = (g.F + 7) & ~7; g.KSI = g.F8 / 8;
   g.Up = round_up_mod(g.F8, 32, 8);
   g.NP = (O + 7) & ~7;
   g.uimg = g.NP * g.Up;
   g.CKK = C * KH * KW;
-  g.a_mod = stride * g.spitch; g.a_div = stride;
+  g.a_mod = stride * g.sr; g.a_div = stride * g.sc;
   const int NT = g.NP / 8;
-  const int mt_total = ceil_div(g.CKK, 16);
-  g.MS = ceil_div(mt_total, 5);
-  if (g.MS > 8) return NGB_OK;
-  const int MTW = ceil_div(mt_total, g.MS);
-  g.Mrows = g.MS * MTW * 16;
   g.KS = 8 / g.MS; if (g.KS < 1) g.KS = 1;
   const int nwarps = g.MS * g.KS;
   const size_t fixed = ((size_t)g.Mrows + g.F8) * 4;
@@ -1094,13 +1266,31 @@ int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int
   if (G > N) G = N;
   const int gmin = (int)ceil_div<size_t>(red_bytes, per_img);   // the reduction tile reuses the staging area
   if (G < gmin) return NGB_OK;
+  // register-prefetched staging (kernel comment): whole groups must fit the per-thread prefetch registers
+  bool pf = false;
+  if (pidx && (W & 3) == 0 && (g.Hp & 3) == 0 && !getenv("NGB_WGRAD_NO_PF") &&
+      (((uintptr_t)x | (uintptr_t)ug) & 15u) == 0 && ((uintptr_t)pidx & 3u) == 0) {
+    const int nthr = nwarps * 32;
+    const int gx = kPFX * nthr * 4 / (C * H * W), gu = kPFU * nthr * 4 / (O * g.Fp);
+    const int gp = gx < gu ? gx : gu;
+    if (gp >= gmin && gp >= 1) {
+      pf = true;
+      if (G > gp) G = gp;
+    }
+  }
+  if (const char* e = getenv("NGB_WGRAD_G")) {   // experiments: cap the images per group
+    const int ge = atoi(e);
+    if (ge >= gmin && ge >= 1 && ge < G) G = ge;
+  }
   int rc = ensure_init();
   if (rc) return rc;
   const int64_t nw = (int64_t)O * g.CKK;
   if (nw * 4 * kNumSMs * 4 > scratch_bytes()) return NGB_OK;
   int grid = 0;
   float* part = scratch_ptr();
-#define NGB_WGRAD(M_, N_) rc = launch_wgrad<M_, N_>(ug, x, pidx, ypool, zmask, part, g, nwarps, gmin, G, fixed, per_img, &grid, st)
+#define NGB_WGRAD(M_, N_)                                                                                                  \
+  rc = pf ? launch_wgrad<M_, N_, true>(ug, x, pidx, ypool, zmask, part, g, nwarps, gmin, G, fixed, per_img, &grid, st)     \
+          : launch_wgrad<M_, N_, false>(ug, x, pidx, ypool, zmask, part, g, nwarps, gmin, G, fixed, per_img, &grid, st)
   if (NT == 1) {
     switch (MTW) { case 1: NGB_WGRAD(1, 1); break; case 2: NGB_WGRAD(2, 1); break; case 3: NGB_WGRAD(3, 1); break;
                    case 4: NGB_WGRAD(4, 1); break; default: NGB_WGRAD(5, 1); break; }
@@ -1112,6 +1302,225 @@ int conv_mma_wgrad(const float* ug, const float* x, float* dw, int N, int C, int
   if (rc) return rc;
   *done = true;
   return launch_sum_partials(part, grid, nw, dw, accumulate, st);
+}
+
+// ------------------------------------------------------------------------------------------------ sparse pooled wgrad + bgrad
+// First-layer weight AND bias gradient of conv -> ReLU -> MaxPool(2x2, s2) straight from the pooled upstream gradient, on the
+// CUDA cores in full fp32.  Of the four cells of a pooling window only the argmax cell carries gradient, so
+//   dw[o][c][kh][kw] = sum over windows of gm * x[c][pc*stride + kh][qc*stride + kw],   db[o] = sum of gm,
+// gm = ug_pool * relu'(z at the argmax) (bit 2 of the argmax byte, written by ngb_maxpool_relu_fwd), (pc, qc) = the argmax
+// cell's conv position: C*KH*KW FMAs per (window, o) -- a quarter of the dense product, no scattered tile, no TF32 rounding,
+// and two coalesced loads (gradient, argmax byte) per item.  With few input channels the filter fits the registers of ONE
+// thread: every lane keeps all C*KH*KW (+1 bias) sums of one output channel.
+// Lane = (o, window): the O lanes of a window read x patches that differ only by the argmax offset (<= 4 distinct words per
+// load, mostly broadcasts) and a warp spans 32/O neighbouring windows.  (One window column per lane -- every lane its own
+// patch -- cost 2.9 shared-memory wavefronts per load and ran as slow as the tensor-core kernel, which pads 25 x 6 to 32 x 8,
+// gathers every A fragment and spends as many instructions staging the scattered gradient as on the MMAs.)
+// x images arrive through cp.async into a double buffer; one barrier per group of images.
+struct SparseGeo {
+  int N, O, H, W, Ho, Wo, Hp, Wp, Fp, stride;
+  int G, wpw;          // images per group, windows per warp iteration (32 / O)
+  int ximg;            // C*H*W (global)
+  int S, simg;         // staged row pitch and image size (C*H*S): S puts the two argmax rows of a window on disjoint banks
+  int w4;              // 16-byte chunks per x row (W / 4), 0: rows are not 16-byte multiples, the image is copied flat (S == W)
+  int square;          // Ho == Wo: conv position of the stored cell (r, c) is (c, r) without a division
+  int d_il, d_q, d_p;  // one warp-iteration step (kSparseWarps * wpw windows) as (images, pooled columns, pooled rows)
+};
+
+constexpr int kSparseWarps = 12;
+
+template <int C, int KH, int KW>
+__global__ void __launch_bounds__(kSparseWarps * 32, 3) conv_wbgrad_pooled_sparse_kernel(const float* __restrict__ ug,
+                                                                                    const uint8_t* __restrict__ pidx,
+                                                                                    const float* __restrict__ x,
+                                                                                    float* __restrict__ part, float* __restrict__ partb,
+                                                                                    SparseGeo g, FastDiv d_fp, FastDiv d_hp,
+                                                                                    FastDiv d_ho, FastDiv d_wpw, FastDiv d_w4) {
+  constexpr int CKK = C * KH * KW;
+  extern __shared__ __align__(16) float smem_f[];
+  const int tid = threadIdx.x, nthr = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  uint32_t o, wl;
+  d_wpw.divmod((uint32_t)lane, o, wl);
+  const bool active = (int)o < g.O;              // 32 % O spare lanes idle
+  const int gimg = g.G * g.simg;                 // floats per buffer
+  float* bufs = smem_f;                          // [2][G][simg]
+
+  float acc[CKK], accb = 0.f;
+#pragma unroll
+  for (int i = 0; i < CKK; ++i) acc[i] = 0.f;
+
+  int img_lo, img_cnt;
+  cta_image_range(g.N, img_lo, img_cnt);
+  auto stage = [&](int n0, int ng, int b) {      // 16-byte cp.async: images are 16-byte multiples (host-checked)
+    const float* src = x + (int64_t)n0 * g.ximg;
+    const uint32_t dst = smem_u32(bufs + b * gimg);
+    const int n16 = (ng * g.ximg) >> 2;
+    for (int e = tid; e < n16; e += nthr) {
+      uint32_t d = (uint32_t)e * 16u;
+      if (g.w4) {                                // row r of the group (images are C*H rows back to back), chunk k
+        uint32_t r, k;
+        d_w4.divmod((uint32_t)e, r, k);
+        d = (r * (uint32_t)g.S + 4u * k) * 4u;
+      }
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + d), "l"(src + 4 * (int64_t)e) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (img_cnt > 0) stage(img_lo, min(g.G, img_cnt), 0);
+  int cur = 0;
+  const int wstep = kSparseWarps * g.wpw;
+  const uint32_t ofp = o * (uint32_t)g.Fp, img_fp = (uint32_t)(g.O * g.Fp);
+  for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.G) {
+    const int ng = min(g.G, img_lo + img_cnt - n0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                             // buffer `cur` is complete; everyone is done reading the other one
+    const int nn = n0 + g.G;
+    if (nn < img_lo + img_cnt) stage(nn, min(g.G, img_lo + img_cnt - nn), cur ^ 1);
+    const float* xb = bufs + cur * gimg;
+    const int nwin = active ? ng * g.Fp : 0;     // windows in the group (every one has O lanes)
+    const float* ugb = ug + (int64_t)n0 * img_fp;
+    const uint8_t* idb = pidx + (int64_t)n0 * img_fp;
+    // operands of one item, loaded one iteration ahead
+    // (image, pooled column q', pooled row p') of this lane's window: decoded once per group, then stepped
+    int w = warp * g.wpw + (int)wl;
+    uint32_t il, fe0, qq, pp;
+    d_fp.divmod((uint32_t)w, il, fe0);
+    d_hp.divmod(fe0, qq, pp);
+    float gv = 0.f, gv_n = 0.f;
+    uint32_t av = 0, av_n = 0;
+    auto fetch = [&](bool ok, uint32_t i, uint32_t q, uint32_t p_, float& gout, uint32_t& aout) {
+      if (ok) {
+        const uint32_t off = i * img_fp + ofp + q * (uint32_t)g.Hp + p_;
+        gout = __ldg(ugb + off);
+        aout = __ldg(idb + off);
+      }
+    };
+    fetch(w < nwin, il, qq, pp, gv, av);
+    for (; w < nwin; w += wstep) {
+      // the next window of this lane
+      uint32_t pn = pp + (uint32_t)g.d_p, qn = qq + (uint32_t)g.d_q, in_ = il + (uint32_t)g.d_il;
+      if (pn >= (uint32_t)g.Hp) { pn -= (uint32_t)g.Hp; ++qn; }
+      if (qn >= (uint32_t)g.Wp) { qn -= (uint32_t)g.Wp; ++in_; }
+      fetch(w + wstep < nwin, in_, qn, pn, gv_n, av_n);
+      const float gm = (av & 4u) ? gv : 0.f;
+      // argmax cell in the conv output plane as stored: (r, c) = (2p' + kh_a, 2q' + kw_a), flat r*Wo + c -> the convolution
+      // produced it at position (flat % Ho, flat / Ho)
+      const uint32_t r = 2 * pp + ((av >> 1) & 1u), cc = 2 * qq + (av & 1u);
+      uint32_t pc, qc;
+      if (g.square) { pc = cc; qc = r; } else d_ho.divmod(r * (uint32_t)g.Wo + cc, qc, pc);
+      const float* xw = xb + il * (uint32_t)g.simg + (pc * (uint32_t)g.stride) * (uint32_t)g.S + qc * (uint32_t)g.stride;
+      pp = pn; qq = qn; il = in_; gv = gv_n; av = av_n;
+      accb += gm;
+#pragma unroll
+      for (int c = 0; c < C; ++c)
+#pragma unroll
+        for (int kh = 0; kh < KH; ++kh) {
+          const float* xr = xw + c * g.H * g.S + kh * g.S;
+#pragma unroll
+          for (int kw = 0; kw < KW; ++kw) acc[(c * KH + kh) * KW + kw] = fmaf(gm, xr[kw], acc[(c * KH + kh) * KW + kw]);
+        }
+    }
+    cur ^= 1;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+
+  // ---- every lane's sums to shared memory, then one thread per (o, filter element) adds warps and lanes in a fixed order
+  __syncthreads();
+  float* red = smem_f;                           // [threads][CKK + 1]
+#pragma unroll
+  for (int i = 0; i < CKK; ++i) red[tid * (CKK + 1) + i] = acc[i];
+  red[tid * (CKK + 1) + CKK] = accb;
+  __syncthreads();
+  for (int e = tid; e < g.O * (CKK + 1); e += nthr) {
+    const int oo = e / (CKK + 1), k = e % (CKK + 1);
+    float v = 0.f;
+    for (int wi = 0; wi < kSparseWarps; ++wi)
+      for (int l = 0; l < g.wpw; ++l) v += red[(wi * 32 + oo * g.wpw + l) * (CKK + 1) + k];
+    if (k < CKK) part[(int64_t)blockIdx.x * (g.O * CKK) + oo * CKK + k] = v;
+    else partb[(int64_t)blockIdx.x * g.O + oo] = v;
+  }
+}
+
+template <int C, int KH, int KW>
+static int launch_sparse(const float* ug, const uint8_t* pidx, const float* x, float* dw, float* db, SparseGeo g, int acc_w,
+                         int acc_b, cudaStream_t st) {
+  constexpr int CKK = C * KH * KW;
+  auto kern = conv_wbgrad_pooled_sparse_kernel<C, KH, KW>;
+  static bool attr = false;
+  if (!attr) {
+    NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
+    attr = true;
+  }
+  const int threads = kSparseWarps * 32;
+  const size_t per_img = (size_t)2 * g.simg * 4;              // double buffer
+  const size_t red_bytes = (size_t)threads * (CKK + 1) * 4;   // the reduction reuses the buffers
+  int gmax = 6;
+  if (const char* e = getenv("NGB_SPARSE_G")) gmax = atoi(e) > 0 ? atoi(e) : gmax;
+  const int gmin = (int)ceil_div<size_t>(red_bytes, per_img);
+  if (gmax < gmin) gmax = gmin;
+  if (gmax * per_img > 96 * 1024) return -1;
+  int grid = 1;
+  int rc = balance_images(kern, threads, 0, per_img, g.N, gmin, gmax, corun_hint() != 0, &g.G, &grid);
+  if (rc) return rc;
+  const int64_t nw = (int64_t)g.O * CKK;
+  if ((int64_t)grid * (nw + g.O) * 4 > scratch_bytes()) return -1;
+  float* part = scratch_ptr();
+  float* partb = part + (int64_t)grid * nw;
+  const int wstep = kSparseWarps * g.wpw;                     // windows per CTA iteration, as (images, columns, rows)
+  g.d_il = wstep / g.Fp;
+  g.d_q = (wstep % g.Fp) / g.Hp;
+  g.d_p = (wstep % g.Fp) % g.Hp;
+  kern<<<grid, threads, (size_t)g.G * per_img, st>>>(ug, pidx, x, part, partb, g, FastDiv((uint32_t)g.Fp), FastDiv((uint32_t)g.Hp),
+                                                     FastDiv((uint32_t)g.Ho), FastDiv((uint32_t)g.wpw),
+                                                     FastDiv((uint32_t)(g.w4 > 0 ? g.w4 : 1)));
+  NGB_LAUNCH_CHECK();
+  rc = launch_sum_partials(part, grid, nw, dw, acc_w, st);
+  if (rc) return rc;
+  if (db) rc = launch_sum_partials(partb, grid, g.O, db, acc_b, st);
+  return rc;
+}
+
+bool conv_sparse_serves(int C, int H, int W, int O, int KH, int KW, int pad, int Ho, int Wo) {
+  if (getenv("NGB_NO_SPARSE_WGRAD")) return false;
+  if (pad != 0 || (Ho & 1) || (Wo & 1) || O < 1 || O > 12 || ((C * H * W) & 3)) return false;
+  return (C == 1 && KH == 5 && KW == 5) || (C == 1 && KH == 3 && KW == 3) || (C == 3 && KH == 3 && KW == 3);
+}
+
+// *done = false: geometry not served (the caller uses the tensor-core kernel / the separate bias kernel).
+int conv_sparse_wbgrad_pooled(const float* ug, const float* ypool, const uint8_t* pidx, const float* z, const float* x, float* dw,
+                              float* db, int N, int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo,
+                              int acc_w, int acc_b, cudaStream_t st, bool* done) {
+  *done = false;
+  if (N < 1 || !conv_sparse_serves(C, H, W, O, KH, KW, pad, Ho, Wo) || ((uintptr_t)x & 15u)) return NGB_OK;
+  (void)ypool; (void)z;                // the ReLU mask travels in bit 2 of the argmax bytes
+  SparseGeo g;
+  g.N = N; g.O = O; g.H = H; g.W = W; g.Ho = Ho; g.Wo = Wo; g.Hp = Ho / 2; g.Fp = (Ho / 2) * (Wo / 2);
+  g.Wp = Wo / 2;
+  g.stride = stride; g.ximg = C * H * W; g.G = 1; g.wpw = 32 / O; g.square = (Ho == Wo) ? 1 : 0;
+  // Staged row pitch.  The lanes of a warp read words 2*wl*stride + {0, stride} (argmax column) + {0, S*stride} (argmax row), wl <
+  // wpw: the two rows of a window land on disjoint banks when S*stride mod 32 lies in [2*wpw*stride, 32 - 2*wpw*stride].
+  g.S = W; g.w4 = 0;
+  if ((W & 3) == 0) {
+    g.w4 = W / 4;
+    const int span = 2 * g.wpw * stride;
+    for (int Sx = W; Sx < W + 32; Sx += 4) {
+      const int m = (Sx * stride) & 31;
+      if (m >= span && m <= 32 - span) { g.S = Sx; break; }
+    }
+  }
+  g.simg = C * H * g.S;
+  int rc = ensure_init();
+  if (rc) return rc;
+  rc = -1;
+  if (C == 1 && KH == 5 && KW == 5) rc = launch_sparse<1, 5, 5>(ug, pidx, x, dw, db, g, acc_w, acc_b, st);
+  else if (C == 1 && KH == 3 && KW == 3) rc = launch_sparse<1, 3, 3>(ug, pidx, x, dw, db, g, acc_w, acc_b, st);
+  else if (C == 3 && KH == 3 && KW == 3) rc = launch_sparse<3, 3, 3>(ug, pidx, x, dw, db, g, acc_w, acc_b, st);
+  else return NGB_OK;
+  if (rc == -1) return NGB_OK;
+  if (rc) return rc;
+  *done = true;
+  return NGB_OK;
 }
 
 }  // namespace ngb

@@ -18,6 +18,9 @@
 
 namespace ngb {
 
+// 2x2 pools: bit 2 of an argmax byte written by ngb_maxpool_relu_fwd says whether the ReLU gradient at the argmax is 1
+constexpr int kPoolReluFlag = 4;
+
 struct PoolGeo {
   int H, W, Ho, Wo, KH, KW, pad, stride;
   int TP;       // output rows per strip
@@ -113,6 +116,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const float* __r
   extern __shared__ float sm[];
   // strip of input rows [h0, h1) <-> output rows that can be "the last window covering" those rows
   const int TPp = g.TP | 1;
+  const int imask = (g.KH * g.KW <= 4) ? 3 : 255;                     // 2x2 pools: drop ngb_maxpool_relu_fwd's flag bit
   float* sug = sm;                                                    // [G][Wo][TPp]
   uint8_t* sidx = reinterpret_cast<uint8_t*>(sm + g.G * g.Wo * TPp);   // [G][Wo][TPp]
   const int64_t groups = ceil_div<int64_t>(outer, g.G);
@@ -136,7 +140,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_tiled_kernel(const float* __r
       if (lp >= tp) continue;
       const int64_t f = (o0 + gi) * (int64_t)g.Ho * g.Wo + (int64_t)q * g.Ho + p0 + lp;
       sug[(gi * g.Wo + q) * TPp + lp] = __ldg(ug + f);
-      sidx[(gi * g.Wo + q) * TPp + lp] = idx[f];
+      sidx[(gi * g.Wo + q) * TPp + lp] = idx[f] & imask;
     }
     __syncthreads();
     // padded rows hp = h + pad handled by this strip
@@ -212,6 +216,7 @@ __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __rest
       if ((int)lp >= tp) continue;
       const float* r0 = x + ((o0 + gi) * g.H + 2 * (p0 + (int)lp)) * (int64_t)g.W + 4 * c4;
       float4 a = ld_stream4(r0), b = ld_stream4(r0 + g.W);
+      const float first0 = a.x, first1 = a.z;      // first cell of each window before the clamp
       if (RELU) {   // same expression as the elementwise ReLU kernel (elementwise.cu): fmaxf(0, x)
         a.x = fmaxf(0.f, a.x); a.y = fmaxf(0.f, a.y); a.z = fmaxf(0.f, a.z); a.w = fmaxf(0.f, a.w);
         b.x = fmaxf(0.f, b.x); b.y = fmaxf(0.f, b.y); b.z = fmaxf(0.f, b.z); b.w = fmaxf(0.f, b.w);
@@ -220,6 +225,13 @@ __global__ void __launch_bounds__(256) maxpool2x2_fwd_kernel(const float* __rest
       int a0, a1;
       max4(a.x, a.y, b.x, b.y, v0, a0);
       max4(a.z, a.w, b.z, b.w, v1, a1);
+      if (RELU) {
+        // bit 2 of the index byte = relu'(x at the argmax) (activations.py:31: x >= 0).  A positive maximum passed the ReLU;
+        // a zero maximum means every cell was clamped, the argmax is the first cell and the gradient flows iff that cell
+        // is exactly zero or above.  The pooled backward kernels read ug and this byte and nothing else.
+        if (v0 > 0.f || first0 >= 0.f) a0 |= kPoolReluFlag;
+        if (v1 > 0.f || first1 >= 0.f) a1 |= kPoolReluFlag;
+      }
       const int q = 2 * (int)c4;
       const int s0 = ((int)gi * g.Wo + q) * TPp + (int)lp;
       if (q < g.Wo) { sy[s0] = v0; si[s0] = (uint8_t)a0; }
@@ -280,7 +292,7 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __rest
           const uchar4 a = *reinterpret_cast<const uchar4*>(idx + f);
           const int s0 = ((int)gi * g.Wo + (int)q) * TPp + lp;
           sg[s0] = v.x; sg[s0 + 1] = v.y; sg[s0 + 2] = v.z; sg[s0 + 3] = v.w;
-          si[s0] = a.x; si[s0 + 1] = a.y; si[s0 + 2] = a.z; si[s0 + 3] = a.w;
+          si[s0] = a.x & 3; si[s0 + 1] = a.y & 3; si[s0 + 2] = a.z & 3; si[s0 + 3] = a.w & 3;   // bit 2: ReLU flag
         }
       }
     } else {
@@ -294,7 +306,7 @@ __global__ void __launch_bounds__(256) maxpool2x2_bwd_kernel(const float* __rest
           const int64_t f = (o0 + gi) * (int64_t)g.Ho * g.Wo + (int64_t)q * g.Ho + p0 + (int)lp;
           const int s0 = ((int)gi * g.Wo + (int)q) * TPp + (int)lp;
           sg[s0] = __ldg(ug + f);
-          si[s0] = idx[f];
+          si[s0] = idx[f] & 3;                   // 2x2 windows: bit 2 is ngb_maxpool_relu_fwd's ReLU flag
         }
       }
     }
@@ -401,6 +413,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_simple_kernel(const float* __
                                                                  float* __restrict__ dx, int64_t outer, int H, int W, int Ho,
                                                                  int Wo, int KH, int KW, int pad, int stride, int accumulate) {
   const int64_t hw_in = (int64_t)H * W, total = outer * hw_in, hw_out = (int64_t)Ho * Wo;
+  const int imask = (KH * KW <= 4) ? 3 : 255;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t o = i / hw_in;
     const int r = (int)(i - o * hw_in);
@@ -413,7 +426,7 @@ __global__ void __launch_bounds__(256) maxpool_bwd_simple_kernel(const float* __
     if (q * stride + KW > wp && p * stride + KH > hp) {
       const int64_t f = o * hw_out + (int64_t)q * Ho + p;
       const int local = (hp - p * stride) * KW + (wp - q * stride);
-      if ((int)idx[f] == local) g = ug[f];
+      if ((int)(idx[f] & imask) == local) g = ug[f];
     }
     dx[i] = accumulate ? dx[i] + g : g;
   }

@@ -174,6 +174,31 @@ def conv_bgrad_pooled(ug_pool, y_pool, z):
   return host(db)
 
 
+def conv_wbgrad_pooled(ug_pool, y_pool, idx, z, x, wshape, pad, stride, dw0=None, db0=None):
+  """(dw, db, fused) from ngb_conv_wbgrad_pooled; dw0 / db0: accumulate into these; None when the geometry is unsupported"""
+  N, C, H, W = x.shape
+  O, _, KH, KW = wshape
+  dw = torch.full(tuple(wshape), float('nan'), device='cuda') if dw0 is None else dev(dw0)
+  db = torch.full((O,), float('nan'), device='cuda') if db0 is None else dev(db0)
+  G, Y, I, Z, X = dev(ug_pool), dev(y_pool), dev(idx, torch.uint8), dev(z), dev(x)
+  B.ensure_runtime()
+  fused = lib.ngb_conv_wbgrad_pooled_is_fused(N, C, H, W, O, KH, KW, pad, stride) == 1
+  rc = lib.ngb_conv_wbgrad_pooled(ptr(G), ptr(Y), ptr(I), ptr(Z), ptr(X), ptr(dw), ptr(db), N, C, H, W, O, KH, KW, pad, stride,
+                                  int(dw0 is not None), int(db0 is not None), st())
+  if rc == B.ERR_UNSUPPORTED:
+    return None
+  B.check(rc)
+  return host(dw), host(db), fused
+
+
+def conv_bgrad_pooled_idx(ug_pool, idx):
+  N, O, Hp, Wp = ug_pool.shape
+  db = torch.full((O,), float('nan'), device='cuda')
+  G, I = dev(ug_pool), dev(idx, torch.uint8)
+  call('ngb_conv_bgrad_pooled_idx', ptr(G), ptr(I), ptr(db), N, O, Hp * Wp, 0, st())
+  return host(db)
+
+
 def conv_dgrad_pooled(ug_pool, y_pool, idx, z, w, xshape, pad, stride):
   """returns None when the geometry is not served by the pooled-gradient kernel"""
   N, C, H, W = xshape

@@ -350,7 +350,14 @@ def test_maxpool_relu_fused_is_bit_exact(U, shape):
   assert got is not None
   y, idx = got
   yr, idxr = U.maxpool_fwd(np.maximum(x, 0.0), (2, 2), 0, 2)
-  assert np.array_equal(y, yr) and np.array_equal(idx, idxr)
+  assert np.array_equal(y, yr) and np.array_equal(idx & 3, idxr)
+  # bit 2 of the fused kernel's index bytes: relu'(x at the argmax) = (x_argmax >= 0); windows are stored (p', q') at q'*Hp + p'
+  H2, W2 = x.shape[-2] // 2, x.shape[-1] // 2
+  win = x.reshape(x.shape[:-2] + (H2, 2, W2, 2)).swapaxes(-3, -2).reshape(x.shape[:-2] + (H2, W2, 4))
+  arg = (idx & 3).reshape(x.shape[:-2] + (W2, H2)).swapaxes(-1, -2).astype(int)
+  x_arg = np.take_along_axis(win, arg[..., None], axis=-1)[..., 0]
+  flag = (idx >> 2).reshape(x.shape[:-2] + (W2, H2)).swapaxes(-1, -2)
+  assert np.array_equal(flag, (x_arg >= 0).astype(flag.dtype))
   yo = ops.maxpool_fwd(np.maximum(x, 0.0), (2, 2), 0, 2)
   yo = yo[0] if isinstance(yo, tuple) else yo
   assert np.array_equal(y, yo.astype(np.float32))
@@ -383,7 +390,7 @@ def test_conv_wgrad_from_pooled_gradient(U, N, C, H, W, O, K):
   scat = np.zeros((N, O, Ho, Wo), np.float32)
   for qq in range(Wp):
     for pp in range(Hp):
-      a = idr[:, :, qq, pp].astype(int)
+      a = (idr[:, :, qq, pp] & 3).astype(int)
       for kh in range(2):
         for kw in range(2):
           m = a == kh * 2 + kw
@@ -391,16 +398,59 @@ def test_conv_wgrad_from_pooled_gradient(U, N, C, H, W, O, K):
   assert np.array_equal(scat, full)
   dw = U.conv_wgrad_pooled(ugp, y, idx, z, xin, (O, C, K, K), 0, 1)
   assert dw is not None
-  ref = U.conv_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1)
-  assert np.array_equal(dw, ref)
-  close(dw, ops.conv3d_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1), TOLTF32)
+  got = U.conv_wbgrad_pooled(ugp, y, idx, z, xin, (O, C, K, K), 0, 1)
+  assert got is not None
+  dw2, db2, fused = got
+  assert np.array_equal(dw, dw2)                           # same kernel behind both entry points
+  oracle_dw = ops.conv3d_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1)
+  if fused:                                                # first layers: sparse fp32 kernel (no TF32 rounding)
+    close(dw, oracle_dw, 4 * TOL32)
+  else:
+    ref = U.conv_wgrad(full.astype(np.float64), xin, (O, C, K, K), 0, 1)
+    assert np.array_equal(dw, ref)
+    close(dw, oracle_dw, TOLTF32)
+  close(db2, full.astype(np.float64).sum(axis=(0, 2, 3)), 4 * TOL32)
   close(U.conv_bgrad(gm.astype(np.float64)), U.conv_bgrad(full.astype(np.float64)), 4 * TOL32)
   close(U.conv_bgrad_pooled(ugp, y, z), full.astype(np.float64).sum(axis=(0, 2, 3)), 4 * TOL32)
+  close(U.conv_bgrad_pooled_idx(ugp, idx), full.astype(np.float64).sum(axis=(0, 2, 3)), 4 * TOL32)
   if C >= 3:                                               # data gradient: the row-decomposed kernel serves 3 <= C <= 8
     wt = f32(rng.standard_normal((O, C, K, K)) / np.sqrt(C * K * K))
     dxp = U.conv_dgrad_pooled(ugp, y, idx, z, wt, xin.shape, 0, 1)
     assert dxp is not None
     assert np.array_equal(dxp, U.conv_dgrad(full.astype(np.float64), wt, xin.shape, 0, 1))
+
+
+@pytest.mark.parametrize('N,C,H,W,O,K,stride', [(700, 1, 28, 28, 6, 5, 1), (333, 1, 12, 14, 4, 3, 1), (129, 3, 10, 14, 8, 3, 1),
+                                                 (65, 1, 14, 18, 12, 3, 2), (9, 1, 28, 28, 7, 5, 1)])
+def test_conv_wbgrad_pooled_single_pass(U, N, C, H, W, O, K, stride):
+  """ngb_conv_wbgrad_pooled on first-layer geometries (one fp32 kernel for dw and db: only the argmax cell of a pooling window
+  carries gradient) against the float64 oracle on the materialised gradient; several image groups per CTA, every argmax
+  position, clamped windows, exact zeros, accumulate on and off."""
+  rng = np.random.default_rng(N + C + H + O + K)
+  xin = f32(rng.standard_normal((N, C, H, W)))
+  Ho, Wo = (H - K) // stride + 1, (W - K) // stride + 1
+  assert Ho % 2 == 0 and Wo % 2 == 0
+  z = f32(rng.standard_normal((N, O, Ho, Wo)))
+  z[0] = -np.abs(z[0]) - 0.5
+  z[1, :, ::2, ::2] = 0.0
+  y, idx = U.maxpool_relu_fwd(z, (2, 2), 0, 2)
+  assert set(np.unique(idx & 3)) == {0, 1, 2, 3}
+  ugp = f32(rng.standard_normal(y.shape))
+  full = U.maxpool_relu_bwd(ugp, idx, z, (2, 2), 0, 2).astype(np.float64)
+  got = U.conv_wbgrad_pooled(ugp, y, idx, z, xin, (O, C, K, K), 0, stride)
+  assert got is not None
+  dw, db, fused = got
+  assert fused
+  ref_w = ops.conv3d_wgrad(full, xin, (O, C, K, K), 0, stride)
+  ref_b = full.sum(axis=(0, 2, 3))
+  close(dw, ref_w, 4 * TOL32)
+  close(db, ref_b, 4 * TOL32)
+  dw0, db0 = f32(rng.standard_normal(dw.shape)), f32(rng.standard_normal(db.shape))
+  dwa, dba, _ = U.conv_wbgrad_pooled(ugp, y, idx, z, xin, (O, C, K, K), 0, stride, dw0=dw0, db0=db0)
+  close(dwa, ref_w + dw0, 4 * TOL32)
+  close(dba, ref_b + db0, 4 * TOL32)
+  again = U.conv_wbgrad_pooled(ugp, y, idx, z, xin, (O, C, K, K), 0, stride)
+  assert np.array_equal(again[0], dw) and np.array_equal(again[1], db)       # fixed summation order
 
 
 def test_maxpool_relu_fused_rejects_other_geometries(U):

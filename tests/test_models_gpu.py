@@ -292,13 +292,17 @@ def test_backward_lanes_change_nothing(ng, captured):
 def test_lazy_relu_pool_fusion_changes_nothing(ng):
   """ReLU -> MaxPool pairs run as fused kernels (the ReLU output and the pool's input gradient are never written) and the
   first convolution's weight / bias gradients are taken from the pooled gradient; products and summation orders are
-  unchanged except in the conv1 bias gradient (sum over the pooled map instead of the 4x larger one with zeros), so a
-  LeNet-B trajectory agrees to fp32 rounding with the fusion switched off."""
+  unchanged except in the bias gradients (sum over the pooled map instead of the 4x larger one with zeros), so a LeNet-B
+  trajectory agrees to fp32 rounding with the fusion switched off -- as long as the first layer's weight gradient also goes
+  through the TF32 tensor-core kernel (NGB_NO_SPARSE_WGRAD); its single-pass fp32 kernel differs from that by TF32 rounding."""
+  import os
   from neograd_b200 import device as D
   from neograd_b200.configs import lenet_synthetic, train_step
   results = []
-  for fused in (False, True):
+  for fused, sparse in ((False, True), (True, False), (True, True)):
     prev, D.LAZY_FUSION = D.LAZY_FUSION, fused
+    if not sparse:
+      os.environ['NGB_NO_SPARSE_WGRAD'] = '1'
     try:
       np.random.seed(0)
       model, Xh, Yh = lenet_synthetic('b', 256)
@@ -310,9 +314,11 @@ def test_lazy_relu_pool_fusion_changes_nothing(ng):
       results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
     finally:
       D.LAZY_FUSION = prev
-  assert abs(results[0][0] - results[1][0]) <= 1e-6 * abs(results[0][0])
-  for a, b in zip(results[0][1:], results[1][1:]):
-    assert dist(a, b) < 1e-6, dist(a, b)
+      os.environ.pop('NGB_NO_SPARSE_WGRAD', None)
+  for other, tol in ((1, 1e-6), (2, 2e-3)):
+    assert abs(results[0][0] - results[other][0]) <= tol * abs(results[0][0])
+    for a, b in zip(results[0][1:], results[other][1:]):
+      assert dist(a, b) < tol, dist(a, b)
   # a lazily produced activation is an ordinary array for everything else
   x = ng.tensor(np.array([[-1.0, 2.0], [0.0, -3.0]]), requires_grad=True)
   r = ng.nn.ReLU()(x)
