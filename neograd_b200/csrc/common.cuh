@@ -51,6 +51,8 @@ inline void count_launch(int n = 1) { g_launches.fetch_add(n, std::memory_order_
 
 // out[k] (+)= sum_j part[j*K + k]; deterministic second pass of every split reduction (elementwise.cu).
 int launch_sum_partials(const float* part, int splits, int64_t K, float* out, int accumulate, cudaStream_t st);
+int launch_sum_partials2(const float* part, int splits, int64_t K1, float* out1, int acc1, int64_t K2, float* out2, int acc2,
+                         cudaStream_t st);
 
 inline cudaStream_t as_stream(ngb_stream_t s) { return reinterpret_cast<cudaStream_t>(s); }
 

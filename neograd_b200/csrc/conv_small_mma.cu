@@ -524,7 +524,32 @@ __global__ void __launch_bounds__(384) conv_dgrad_rows_mma_kernel(const float* _
   cta_image_range(g.N, img_lo, img_cnt);
   for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.IP) {
     const int ng = min(g.IP, img_lo + img_cnt - n0);
-    if (g.pooled) {
+    if (g.pooled == 2) {
+      // ---- POOLED gradient, square plane, four pooled rows per 128-bit load: the thread that owns a window writes its whole
+      // 2x2 cell block (masked value at the argmax, zeros elsewhere) -- no zeroing pass, no barrier, one index decomposition
+      // per four windows.  Stored cell (r, c) = (2p' + kh, 2q' + kw) is conv position (p, q) = (c, r): staged row c, column r.
+      const int64_t base = (int64_t)n0 * g.O * g.Fp;
+      const int raw4 = (ng * g.O * g.Fp) >> 2;
+#pragma unroll 2
+      for (int e4 = tid; e4 < raw4; e4 += nthr) {
+        uint32_t pl, fe, qq, pp, img, o;
+        d_fp.divmod((uint32_t)e4 * 4u, pl, fe);
+        d_hp.divmod(fe, qq, pp);
+        d_o.divmod(pl, img, o);
+        const float4 gv = ld_stream4(ug + base + 4 * (int64_t)e4);
+        const uint32_t a4 = __ldg(reinterpret_cast<const uint32_t*>(pidx + base + 4 * (int64_t)e4));
+        uint32_t* row0 = us + img * g.uimg + o * g.plane + (2 * qq) * g.P + g.hl + 2 * pp;     // staged row 2q', column 2p'
+        const float gs[4] = {gv.x, gv.y, gv.z, gv.w};
+#pragma unroll
+        for (int j2 = 0; j2 < 4; ++j2) {
+          const uint32_t ab = (a4 >> (8 * j2)) & 0xFFu, a = ab & 3u;
+          const uint32_t tv = to_tf32((ab & 4u) ? gs[j2] : 0.f);
+          // argmax cell a = kh*2 + kw sits at staged (row 2q' + kw, column 2p' + kh)
+          *reinterpret_cast<uint2*>(row0 + 2 * j2) = make_uint2(a == 0u ? tv : 0u, a == 2u ? tv : 0u);
+          *reinterpret_cast<uint2*>(row0 + g.P + 2 * j2) = make_uint2(a == 1u ? tv : 0u, a == 3u ? tv : 0u);
+        }
+      }
+    } else if (g.pooled) {
       // ---- ug arrives as the POOLED gradient of a ReLU + 2x2/s2 MaxPool behind this convolution: zero the interiors, then
       // every pooled element is masked (relu') and dropped at its window's argmax cell; the full gradient never exists in HBM
       for (int e = tid; e < ng * g.O * g.Ho; e += nthr) {          // interior rows [hl, hl + Wo) of every (img, o, p)
@@ -729,6 +754,10 @@ int conv_mma_dgrad_rows(const float* ug, const float* w, float* dx, int N, int C
   g.N = N; g.C = C; g.O = O; g.H = H; g.W = W; g.Ho = Ho; g.Wo = Wo; g.KH = KH; g.pad = pad;
   g.pooled = pidx ? 1 : 0; g.Hp = Ho / 2; g.Fp = (Ho / 2) * (Wo / 2);
   g.hl = KW - 1 - pad;
+  // whole-window staging (kernel comment): square plane, four pooled rows per 128-bit load, 8-byte aligned cell pairs
+  if (pidx && Ho == Wo && (g.Hp & 3) == 0 && (g.hl & 1) == 0 && ((uintptr_t)ug & 15u) == 0 && ((uintptr_t)pidx & 3u) == 0 &&
+      !getenv("NGB_DGRAD_NO_CELL"))
+    g.pooled = 2;
   g.P = round_up_mod(Wo + 2 * g.hl, 8, 4);
   g.plane = round_up_mod(Ho * g.P, 32, 8);
   g.uimg = OB * 8 * g.plane;
@@ -1436,8 +1465,9 @@ __global__ void __launch_bounds__(kSparseWarps * 32, 3) conv_wbgrad_pooled_spars
     float v = 0.f;
     for (int wi = 0; wi < kSparseWarps; ++wi)
       for (int l = 0; l < g.wpw; ++l) v += red[(wi * 32 + oo * g.wpw + l) * (CKK + 1) + k];
-    if (k < CKK) part[(int64_t)blockIdx.x * (g.O * CKK) + oo * CKK + k] = v;
-    else partb[(int64_t)blockIdx.x * g.O + oo] = v;
+    // one row of O*CKK weight sums followed by O bias sums per CTA
+    if (k < CKK) part[(int64_t)blockIdx.x * (g.O * (CKK + 1)) + oo * CKK + k] = v;
+    else part[(int64_t)blockIdx.x * (g.O * (CKK + 1)) + g.O * CKK + oo] = v;
   }
 }
 
@@ -1464,9 +1494,9 @@ static int launch_sparse(const float* ug, const uint8_t* pidx, const float* x, f
   int rc = balance_images(kern, threads, 0, per_img, g.N, gmin, gmax, corun_hint() != 0, &g.G, &grid);
   if (rc) return rc;
   const int64_t nw = (int64_t)g.O * CKK;
-  if ((int64_t)grid * (nw + g.O) * 4 > scratch_bytes()) return -1;
+  if (((int64_t)grid * (nw + g.O) + g.O) * 4 > scratch_bytes()) return -1;
   float* part = scratch_ptr();
-  float* partb = part + (int64_t)grid * nw;
+  float* partb = nullptr;
   const int wstep = kSparseWarps * g.wpw;                     // windows per CTA iteration, as (images, columns, rows)
   g.d_il = wstep / g.Fp;
   g.d_q = (wstep % g.Fp) / g.Hp;
@@ -1475,10 +1505,8 @@ static int launch_sparse(const float* ug, const uint8_t* pidx, const float* x, f
                                                      FastDiv((uint32_t)g.Ho), FastDiv((uint32_t)g.wpw),
                                                      FastDiv((uint32_t)(g.w4 > 0 ? g.w4 : 1)));
   NGB_LAUNCH_CHECK();
-  rc = launch_sum_partials(part, grid, nw, dw, acc_w, st);
-  if (rc) return rc;
-  if (db) rc = launch_sum_partials(partb, grid, g.O, db, acc_b, st);
-  return rc;
+  // the bias columns are summed into db, or dropped (out2 == nullptr keeps them inside the row: sum them into the scratch row)
+  return launch_sum_partials2(part, grid, nw, dw, acc_w, g.O, db ? db : part + (int64_t)grid * (nw + g.O), db ? acc_b : 0, st);
 }
 
 bool conv_sparse_serves(int C, int H, int W, int O, int KH, int KW, int pad, int Ho, int Wo) {

@@ -255,7 +255,8 @@ __global__ void __launch_bounds__(256) ew_bwd_fullreduce_kernel(int op, int side
 // Sum `splits` partial rows of length K into out (deterministic second pass).  CTA = 32 columns x 8 split lanes: lane j
 // adds splits j, j+8, ... and the eight lane sums are combined in a fixed order, so the result does not depend on timing.
 __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restrict__ part, int splits, int64_t K,
-                                                           float* __restrict__ out, int accumulate) {
+                                                           float* __restrict__ out, int accumulate,
+    float* __restrict__ out2 = nullptr, int64_t K1 = 0, int accumulate2 = 0) {   // out2: columns >= K1 go to out2[k - K1]
   __shared__ float tile[8][33];
   const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
   for (int64_t k0 = (int64_t)blockIdx.x * 32; k0 < K; k0 += (int64_t)gridDim.x * 32) {
@@ -276,7 +277,9 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
       float r = tile[0][tx];
 #pragma unroll
       for (int j = 1; j < 8; ++j) r += tile[j][tx];
-      out[k] = accumulate ? out[k] + r : r;
+      float* dst = (out2 && k >= K1) ? out2 + (k - K1) : out + k;
+      const int ac = (out2 && k >= K1) ? accumulate2 : accumulate;
+      *dst = ac ? *dst + r : r;
     }
     __syncthreads();
   }
@@ -286,7 +289,8 @@ __global__ void __launch_bounds__(256) sum_partials_kernel(const float* __restri
 // 8 columns x 32 split lanes per CTA, so a thread walks splits/32 rows instead of splits/8 -- the kernel is a chain of
 // dependent L2 round trips, its time is the length of that chain.  Lane sums are combined in a fixed order.
 __global__ void __launch_bounds__(256) sum_partials_tall_kernel(const float* __restrict__ part, int splits, int64_t K,
-                                                                float* __restrict__ out, int accumulate) {
+                                                                float* __restrict__ out, int accumulate,
+    float* __restrict__ out2 = nullptr, int64_t K1 = 0, int accumulate2 = 0) {   // out2: columns >= K1 go to out2[k - K1]
   __shared__ float tile[32][9];
   const int tx = threadIdx.x & 7, ty = threadIdx.x >> 3;
   for (int64_t k0 = (int64_t)blockIdx.x * 8; k0 < K; k0 += (int64_t)gridDim.x * 8) {
@@ -307,7 +311,9 @@ __global__ void __launch_bounds__(256) sum_partials_tall_kernel(const float* __r
       float r = tile[0][tx];
 #pragma unroll
       for (int j = 1; j < 32; ++j) r += tile[j][tx];
-      out[k] = accumulate ? out[k] + r : r;
+      float* dst = (out2 && k >= K1) ? out2 + (k - K1) : out + k;
+      const int ac = (out2 && k >= K1) ? accumulate2 : accumulate;
+      *dst = ac ? *dst + r : r;
     }
     __syncthreads();
   }
@@ -637,6 +643,18 @@ static int reduce_dispatch(int op, int side, const BDims& d, int64_t total, cons
   }
   int grid = (int)(K < (int64_t)kNumSMs * 8 ? K : (int64_t)kNumSMs * 8);
   ew_bwd_general_kernel<<<grid, 256, 0, st>>>(op, side, d, ug, a, as, b, bs, grad, accumulate, K, R);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+// rows of K1 + K2 columns: the first K1 sums go to out1, the rest to out2 (weight + bias gradient partials in one launch)
+int launch_sum_partials2(const float* part, int splits, int64_t K1, float* out1, int acc1, int64_t K2, float* out2, int acc2,
+                         cudaStream_t st) {
+  const int64_t K = K1 + K2;
+  if (splits >= 128 && K <= 8192)
+    sum_partials_tall_kernel<<<grid_for(K * 32, 256), 256, 0, st>>>(part, splits, K, out1, acc1, out2, K1, acc2);
+  else
+    sum_partials_kernel<<<grid_for(K * 8, 256), 256, 0, st>>>(part, splits, K, out1, acc1, out2, K1, acc2);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
