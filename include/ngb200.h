@@ -100,6 +100,17 @@ int ngb_conv_wgrad(const float* ug, const float* x, float* dw,
 int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoWo,
                    int accumulate, ngb_stream_t stream);                                    /* conv.py:323-327, 198-199 */
 
+/* Conv -> ReLU -> MaxPool(2x2, stride 2) blocks, forward in ONE kernel (conv.py:266-297 + activations.py:20 + conv.py:384-402):
+ * y_pool / idx as ngb_maxpool_relu_fwd would produce them from ngb_conv_fprop's output, which is never written.  fp32 FMAs.
+ * First-layer geometries only (C = 1, pad 0, stride 1, square even output); otherwise NGB_ERR_UNSUPPORTED. */
+int ngb_conv_relu_pool_fwd(const float* x, const float* w, const float* b, float* y_pool, uint8_t* idx, int64_t N, int64_t C,
+                           int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW, int64_t pad, int64_t stride,
+                           ngb_stream_t stream);
+
+/* 1 when ngb_conv_relu_pool_fwd serves the geometry (a caller that defers the convolution until its consumer is known asks first) */
+int ngb_conv_relu_pool_fwd_serves(int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                                  int64_t pad, int64_t stride);
+
 /* Conv -> ReLU -> MaxPool(2x2, stride 2) blocks, backward: the gradient of the convolution's output is three quarters
  * zeros (one cell per pooling window) and never has to exist in HBM.  ngb_conv_wgrad_pooled computes conv.py:311-321 from
  * the pool's upstream gradient ug_pool, the pool's output y_pool, its argmax indices idx and the conv output z (= the ReLU's
@@ -108,7 +119,7 @@ int ngb_conv_bgrad(const float* ug, float* db, int64_t N, int64_t O, int64_t HoW
  * writing it by ngb_conv_bgrad_pooled (Ho x Wo = the conv output plane).
  * idx must be the bytes ngb_maxpool_relu_fwd wrote: bits 0-1 = argmax cell (kh*2 + kw), bit 2 = relu'(z at the argmax);
  * the conv-gradient kernels take the mask from those bytes (y_pool and z are read by ngb_maxpool_relu_mask and
- * ngb_conv_bgrad_pooled only).
+ * ngb_conv_bgrad_pooled only, and may be NULL everywhere else).
  * NGB_ERR_UNSUPPORTED -> materialise the gradient with ngb_maxpool_relu_bwd and use ngb_conv_wgrad. */
 int ngb_maxpool_relu_mask(const float* ug_pool, const float* y_pool, const float* z, float* gm, int64_t outer, int64_t H,
                           int64_t W, ngb_stream_t stream);

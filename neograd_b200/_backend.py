@@ -75,6 +75,8 @@ SIGNATURES = {
   'ngb_conv_wgrad_pooled': ([_P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
   'ngb_conv_wbgrad_pooled': ([_P, _P, _P, _P, _P, _P, _P] + [c_int64] * 9 + [c_int, c_int, _S], c_int),
   'ngb_conv_wbgrad_pooled_is_fused': ([c_int64] * 9, c_int),
+  'ngb_conv_relu_pool_fwd': ([_P, _P, _P, _P, _P] + [c_int64] * 9 + [_S], c_int),
+  'ngb_conv_relu_pool_fwd_serves': ([c_int64] * 9, c_int),
   'ngb_conv_bgrad_pooled_idx': ([_P, _P, _P, c_int64, c_int64, c_int64, c_int, _S], c_int),
   'ngb_ew_binary_fwd': ([c_int, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, _S], c_int),
   'ngb_ew_binary_bwd': ([c_int, c_int, _P, _P, c_float, _i64p, c_int, _P, c_float, _i64p, c_int, _P, c_int, _S], c_int),

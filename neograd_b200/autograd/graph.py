@@ -28,13 +28,21 @@ class Graph:
     self.nodes_dict[tens] = Node(tens)
 
   def remove_tensor(self, tens):
-    self.nodes_dict.pop(tens)   # KeyError on double removal, as in the reference
+    node = self.nodes_dict.pop(tens)   # KeyError on double removal, as in the reference
+    # a node is removed once all its parents were visited: nothing walks its edges again.  Dropping them breaks the
+    # parent <-> child reference cycles, so the pass's intermediate tensors (and deferred arrays) die by reference count
+    # right here instead of waiting for the garbage collector.
+    node.parents = []
+    node.children = []
 
   def reset_visited(self):
     for node in self.nodes_dict.values():
       node.visited = False
 
   def reset_graph(self):
+    for node in self.nodes_dict.values():
+      node.parents = []
+      node.children = []
     self.nodes_dict = {}
 
   def zero_grad(self):

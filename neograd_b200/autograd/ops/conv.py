@@ -32,9 +32,21 @@ class Conv:
 def _conv_forward(op, x4, w4, b1, out_shape):
   N, C, H, W = x4.shape
   O, _, KH, KW = w4.shape
-  y = D.DeviceArray.empty(out_shape)
-  B.check(B.lib.ngb_conv_fprop(x4.ptr, w4.ptr, b1.ptr, y.ptr, N, C, H, W, O, KH, KW, op.padding, op.stride, D._st()))
-  return y
+  pad, stride = op.padding, op.stride
+
+  def run():
+    y = D.DeviceArray.empty(out_shape)
+    B.check(B.lib.ngb_conv_fprop(x4.ptr, w4.ptr, b1.ptr, y.ptr, N, C, H, W, O, KH, KW, pad, stride, D._st()))
+    return y
+
+  if (D.LAZY_FUSION and D.FUSED_CONV_POOL and len(out_shape) == 4 and
+      B.lib.ngb_conv_relu_pool_fwd_serves(N, C, H, W, O, KH, KW, pad, stride) == 1):
+    # a ReLU -> MaxPool(2x2, s2) behind this convolution runs with it as ONE kernel (_MaxPool.forward) and this output is
+    # never written; anything else that reads it produces it here
+    out = D.LazyArray(out_shape, run, 'conv', (x4, w4, b1, (N, C, H, W, O, KH, KW, pad, stride)))
+    D.register_lazy(out)
+    return out
+  return run()
 
 
 def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
@@ -43,6 +55,7 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
   O, _, KH, KW = w4shape
   pad, stride = op.padding, op.stride
   x, w = inputs.data, kernel.data
+  in_shape, k_shape, b_shape = inputs.shape, kernel.shape, bias.shape   # (closures must not hold the tensors: cycles)
 
   def pooled(ug):
     """The upstream gradient as (masked pooled gradient, argmax indices) if it is a still-deferred ReLU+MaxPool backward
@@ -53,10 +66,10 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
 
   def dgrad(ug, dst, acc):
     if dst is None:
-      dst, acc = D.DeviceArray.empty(inputs.shape), False
+      dst, acc = D.DeviceArray.empty(in_shape), False
     pg = pooled(ug) if D.POOLED_CONV_DGRAD else None
     if pg is not None:
-      rc = B.lib.ngb_conv_dgrad_pooled(pg.pug.ptr, pg.ypool.ptr, ctypes.c_void_p(pg.idx.data_ptr()), pg.x.ptr, w.ptr, dst.ptr,
+      rc = B.lib.ngb_conv_dgrad_pooled(pg.pug.ptr, None, ctypes.c_void_p(pg.idx.data_ptr()), None, w.ptr, dst.ptr,
                                        N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st())
       if rc == 0:
         return dst
@@ -67,10 +80,10 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
 
   def wgrad(ug, dst, acc):
     if dst is None:
-      dst, acc = D.DeviceArray.empty(kernel.shape), False
+      dst, acc = D.DeviceArray.empty(k_shape), False
     pg = pooled(ug)
     if pg is not None:
-      rc = B.lib.ngb_conv_wgrad_pooled(pg.pug.ptr, pg.ypool.ptr, ctypes.c_void_p(pg.idx.data_ptr()), pg.x.ptr, x.ptr, dst.ptr,
+      rc = B.lib.ngb_conv_wgrad_pooled(pg.pug.ptr, None, ctypes.c_void_p(pg.idx.data_ptr()), None, x.ptr, dst.ptr,
                                        N, C, H, W, O, KH, KW, pad, stride, int(acc), D._st())
       if rc == 0:
         return dst
@@ -81,7 +94,7 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
 
   def bgrad(ug, dst, acc):
     if dst is None:
-      dst, acc = D.DeviceArray.empty(bias.shape), False
+      dst, acc = D.DeviceArray.empty(b_shape), False
     pg = pooled(ug)
     if pg is not None:      # the sum over a plane of the scattered gradient is the sum over its masked pooled form
       B.check(B.lib.ngb_conv_bgrad_pooled_idx(pg.pug.ptr, ctypes.c_void_p(pg.idx.data_ptr()), dst.ptr, N, O,
@@ -95,7 +108,7 @@ def _conv_grad_fns(op, inputs, kernel, bias, x4shape, w4shape):
     kernels above, one after the other."""
     pg = pooled(ug)
     if pg is not None:
-      rc = B.lib.ngb_conv_wbgrad_pooled(pg.pug.ptr, pg.ypool.ptr, ctypes.c_void_p(pg.idx.data_ptr()), pg.x.ptr, x.ptr, dst_w.ptr,
+      rc = B.lib.ngb_conv_wbgrad_pooled(pg.pug.ptr, None, ctypes.c_void_p(pg.idx.data_ptr()), None, x.ptr, dst_w.ptr,
                                         dst_b.ptr, N, C, H, W, O, KH, KW, pad, stride, int(acc_w), int(acc_b), D._st())
       if rc == 0:
         return
@@ -203,6 +216,16 @@ class _MaxPool(Operation, Conv):
     idx = D.torch().empty(lead + (ho, wo), device='cuda', dtype=D.torch().uint8)
     xin, rc = inputs.data, -1
     if isinstance(xin, D.LazyArray) and xin.pending and xin.tag == 'relu':
+      src = xin.args
+      if (isinstance(src, D.LazyArray) and src.pending and src.tag == 'conv' and tuple(self.kernel_shape) == (2, 2)
+          and self.stride == 2 and self.padding == 0):
+        # ... and the ReLU's input is a convolution output nobody has read either: conv + bias + ReLU + pool in one kernel
+        x4, w4, b1, (cN, cC, cH, cW, cO, cKH, cKW, cpad, cstride) = src.args
+        rc = B.lib.ngb_conv_relu_pool_fwd(x4.ptr, w4.ptr, b1.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), cN, cC, cH, cW, cO,
+                                          cKH, cKW, cpad, cstride, D._st())
+        if rc not in (0, B.ERR_UNSUPPORTED):
+          B.check(rc)
+    if rc != 0 and isinstance(xin, D.LazyArray) and xin.pending and xin.tag == 'relu':
       # the input is a ReLU output nobody has read yet: pool max(0, x) of the ReLU's own input, relu(x) is never written
       rc = B.lib.ngb_maxpool_relu_fwd(xin.args.ptr, y.ptr, ctypes.c_void_p(idx.data_ptr()), outer, H, W,
                                       self.kernel_shape[0], self.kernel_shape[1], self.padding, self.stride, D._st())
@@ -217,13 +240,14 @@ class _MaxPool(Operation, Conv):
 
   def backward(self, inputs):
     idx, ypool, (KH, KW), pad, stride = self._idx, self._y, self.kernel_shape, self.padding, self.stride
+    in_shape = inputs.shape          # (the closures below must not hold `inputs`: tensor <-> grad_fn cycles outlive the pass)
     lead = inputs.shape[:-2]
     H, W = inputs.shape[-2:]
     outer = int(np.prod(lead))
 
     def into(ug, dst, acc):
       if dst is None:
-        dst, acc = D.DeviceArray.empty(inputs.shape), False
+        dst, acc = D.DeviceArray.empty(in_shape), False
       B.check(B.lib.ngb_maxpool_bwd(ug.ptr, ctypes.c_void_p(idx.data_ptr()), dst.ptr, outer, H, W, KH, KW, pad, stride,
                                     int(acc), D._st()))
       return dst
@@ -232,8 +256,7 @@ class _MaxPool(Operation, Conv):
       # the input gradient as a deferred array: a ReLU backward that consumes it fuses the routing with its mask
       if not D.LAZY_FUSION:
         return None
-      shape = inputs.shape
-      return D.LazyArray(shape, lambda: into(ug, None, False), 'maxpool_bwd', (ug, idx, outer, H, W, KH, KW, pad, stride, ypool))
+      return D.LazyArray(in_shape, lambda: into(ug, None, False), 'maxpool_bwd', (ug, idx, outer, H, W, KH, KW, pad, stride, ypool))
     inputs.set_grad_fn(GradFn(into, None, lazy))
 
   def validate_inputs(self, inputs):

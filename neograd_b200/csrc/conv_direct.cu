@@ -25,6 +25,9 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
 int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
                     int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done);
 bool conv_sparse_serves(int C, int H, int W, int O, int KH, int KW, int pad, int Ho, int Wo);
+bool conv_fused_fwd_serves(int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo);
+int conv_fused_relu_pool_fwd(const float* x, const float* w, const float* bias, float* y, uint8_t* idx, int N, int C, int H, int W,
+                             int O, int KH, int KW, int pad, int stride, int Ho, int Wo, cudaStream_t st, bool* done);
 int conv_sparse_wbgrad_pooled(const float* ug, const float* ypool, const uint8_t* pidx, const float* z, const float* x, float* dw,
                               float* db, int N, int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo,
                               int acc_w, int acc_b, cudaStream_t st, bool* done);
@@ -953,7 +956,7 @@ extern "C" int ngb_conv_wgrad_pooled(const float* ug_pool, const float* y_pool, 
   ConvGeo g;
   int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
   if (rc) return rc;
-  NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr && z != nullptr, "ngb_conv_wgrad_pooled needs the pool output, its argmax indices and the conv output");
+  NGB_CHECK_ARG(idx != nullptr, "ngb_conv_wgrad_pooled needs the argmax bytes of ngb_maxpool_relu_fwd");
   if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wgrad_pooled: empty batch");
   bool done = false;
   rc = conv_sparse_wbgrad_pooled(ug_pool, y_pool, idx, z, x, dw, nullptr, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho,
@@ -1016,7 +1019,7 @@ extern "C" int ngb_conv_wbgrad_pooled(const float* ug_pool, const float* y_pool,
   ConvGeo g;
   int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
   if (rc) return rc;
-  NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr && z != nullptr, "ngb_conv_wbgrad_pooled needs the pool output, its argmax indices and the conv output");
+  NGB_CHECK_ARG(idx != nullptr, "ngb_conv_wbgrad_pooled needs the argmax bytes of ngb_maxpool_relu_fwd");
   if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wbgrad_pooled: empty batch");
   if ((g.Ho & 1) || (g.Wo & 1)) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wbgrad_pooled: odd conv output plane");
   bool done = false;
@@ -1029,6 +1032,33 @@ extern "C" int ngb_conv_wbgrad_pooled(const float* ug_pool, const float* y_pool,
   if (!done) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_wbgrad_pooled: geometry not served by the pooled weight-gradient kernels");
   if (db) return conv_bgrad_impl(ug_pool, db, g.N, g.O, (g.Ho / 2) * (g.Wo / 2), accumulate_b, nullptr, nullptr, 0, 0, stream, idx);
   return NGB_OK;
+}
+
+// y_pool / idx = maxpool2x2s2(relu(conv(x, w) + b)) in one kernel; the convolution's output is never written (first-layer
+// geometries only: NGB_ERR_UNSUPPORTED -> ngb_conv_fprop + ngb_maxpool_relu_fwd).  idx carries the ReLU flag in bit 2.
+extern "C" int ngb_conv_relu_pool_fwd(const float* x, const float* w, const float* b, float* y_pool, uint8_t* idx, int64_t N,
+                                      int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW, int64_t pad,
+                                      int64_t stride, ngb_stream_t stream) {
+  ConvGeo g;
+  int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
+  if (rc) return rc;
+  NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr, "ngb_conv_relu_pool_fwd: NULL output");
+  if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_relu_pool_fwd: empty batch");
+  bool done = false;
+  rc = conv_fused_relu_pool_fwd(x, w, b, y_pool, idx, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo,
+                                as_stream(stream), &done);
+  if (rc) return rc;
+  if (!done) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_relu_pool_fwd: geometry not served by the fused first-layer kernel");
+  return NGB_OK;
+}
+
+extern "C" int ngb_conv_relu_pool_fwd_serves(int64_t N, int64_t C, int64_t H, int64_t W, int64_t O, int64_t KH, int64_t KW,
+                                             int64_t pad, int64_t stride) {
+  if (stride < 1 || pad < 0 || N < 1 || C < 1 || O < 1 || KH < 1 || KW < 1 || H + 2 * pad < KH || W + 2 * pad < KW ||
+      N * C * H * W >= (int64_t(1) << 40))
+    return 0;
+  const int Ho = (int)((H + 2 * pad - KH) / stride + 1), Wo = (int)((W + 2 * pad - KW) / stride + 1);
+  return conv_fused_fwd_serves((int)C, (int)H, (int)W, (int)O, (int)KH, (int)KW, (int)pad, (int)stride, Ho, Wo) ? 1 : 0;
 }
 
 // 1 when ngb_conv_wbgrad_pooled serves this geometry with ONE kernel (callers that would otherwise overlap the weight and
@@ -1050,7 +1080,7 @@ extern "C" int ngb_conv_dgrad_pooled(const float* ug_pool, const float* y_pool, 
   ConvGeo g;
   int rc = make_geo(&g, N, C, H, W, O, KH, KW, pad, stride);
   if (rc) return rc;
-  NGB_CHECK_ARG(idx != nullptr && y_pool != nullptr && z != nullptr, "ngb_conv_dgrad_pooled needs the pool output, its argmax indices and the conv output");
+  NGB_CHECK_ARG(idx != nullptr, "ngb_conv_dgrad_pooled needs the argmax bytes of ngb_maxpool_relu_fwd");
   if (N == 0) return fail(NGB_ERR_UNSUPPORTED, "ngb_conv_dgrad_pooled: empty batch");
   bool done = false;
   rc = conv_mma_dgrad_rows(ug_pool, w, dx, g.N, g.C, g.H, g.W, g.O, g.KH, g.KW, g.pad, g.stride, g.Ho, g.Wo, accumulate,

@@ -1551,4 +1551,190 @@ int conv_sparse_wbgrad_pooled(const float* ug, const float* ypool, const uint8_t
   return NGB_OK;
 }
 
+// ------------------------------------------------------------------------------------------------ conv + bias + ReLU + MaxPool(2x2, s2) forward
+// First-layer block in ONE kernel: y_pool / idx = maxpool2x2(relu(conv(x, w) + b)) (conv.py:266-297, activations.py:20,
+// conv.py:384-402).  The convolution's own output (4x the pooled map; for LeNet-B conv1 57 MB written and read back by the
+// pool) never exists: the backward kernels of such a block read the pooled gradient and the argmax bytes only.  CUDA cores,
+// full fp32: a thread owns one pooling window of every output channel -- conv positions p in 2q'..2q'+1 (image rows), q in
+// 2p'..2p'+1 (image columns) -- i.e. 4*O accumulators fed from a 6 x 6 input patch in registers (64-bit shared-memory loads,
+// conflict-free for the searched row pitch) and the filter bank in shared memory (128-bit broadcast loads): 25 taps x 4
+// positions x O FMAs per 18 + 50 loads.  Bias, ReLU, the window maximum (first maximum wins, as maxpool2x2_fwd_kernel) and
+// the ReLU-gradient flag (bit 2 of the argmax byte) finish in registers.  Square outputs with Ho % 4 == 0, pad 0, stride 1.
+struct FusedFwdGeo {
+  int N, H, W, Ho, Hp, Fp;
+  int G, S, simg, ximg, tpi;     // images per group, staged row pitch / image size, raw image size, thread tiles per image
+};
+
+template <int C, int KH, int KW, int O>
+__global__ void __launch_bounds__(256, 3) conv_relu_pool_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                   const float* __restrict__ bias, float* __restrict__ y,
+                                                                   uint8_t* __restrict__ idx, FusedFwdGeo g, FastDiv d_tpi,
+                                                                   FastDiv d_hp, FastDiv d_w2) {
+  constexpr int CKK = C * KH * KW, OP = (O + 3) & ~3, PR = 2 + KH - 1, PC = 2 + KW - 1;
+  static_assert((PC & 1) == 0, "odd filter widths only: the patch rows are read as 64-bit pairs");
+  extern __shared__ __align__(16) float smem_f[];
+  float* ws = smem_f;                            // [CKK][OP]
+  float* bs = ws + CKK * OP;                     // [OP]
+  float* bufs = bs + OP;                         // [2][G][simg]   (CKK*OP + OP is a multiple of 4)
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  for (int e = tid; e < CKK * OP; e += nthr) {
+    const int k = e / OP, o = e % OP;
+    ws[e] = o < O ? __ldg(w + (int64_t)o * CKK + k) : 0.f;
+  }
+  for (int e = tid; e < OP; e += nthr) bs[e] = e < O ? __ldg(bias + e) : 0.f;
+
+  const int gimg = g.G * g.simg;
+  int img_lo, img_cnt;
+  cta_image_range(g.N, img_lo, img_cnt);
+  auto stage = [&](int n0, int ng, int b) {      // 8-byte cp.async: the staged pitch is even, not a multiple of 4
+    const float* src = x + (int64_t)n0 * g.ximg;
+    const uint32_t dst = smem_u32(bufs + b * gimg);
+    const int n8 = (ng * g.ximg) >> 1;
+    for (int e = tid; e < n8; e += nthr) {
+      uint32_t r, k;
+      d_w2.divmod((uint32_t)e, r, k);            // row r of the group (images are C*H rows back to back), pair k
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + (r * (uint32_t)g.S + 2u * k) * 4u), "l"(src + 2 * (int64_t)e)
+                   : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  if (img_cnt > 0) stage(img_lo, min(g.G, img_cnt), 0);
+  int cur = 0;
+  for (int n0 = img_lo; n0 < img_lo + img_cnt; n0 += g.G) {
+    const int ng = min(g.G, img_lo + img_cnt - n0);
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();                             // buffer `cur` (and, the first time, the filter bank) is complete
+    const int nn = n0 + g.G;
+    if (nn < img_lo + img_cnt) stage(nn, min(g.G, img_lo + img_cnt - nn), cur ^ 1);
+    const float* xb = bufs + cur * gimg;
+    for (int ti = tid; ti < ng * g.tpi; ti += nthr) {
+      uint32_t il, rem, qp, pq;
+      d_tpi.divmod((uint32_t)ti, il, rem);
+      d_hp.divmod(rem, qp, pq);                  // window (p' = pq, q' = qp): p' fastest over lanes
+      float acc[2][2][O];
+#pragma unroll
+      for (int a = 0; a < 2; ++a)
+#pragma unroll
+        for (int b2 = 0; b2 < 2; ++b2)
+#pragma unroll
+          for (int o = 0; o < O; ++o) acc[a][b2][o] = 0.f;
+#pragma unroll
+      for (int c = 0; c < C; ++c) {
+        const float* xp = xb + il * (uint32_t)g.simg + (c * g.H + 2 * qp) * (uint32_t)g.S + 2 * pq;
+        // one patch row at a time (6 values live instead of 36): row r feeds output row a through filter row kh = r - a
+#pragma unroll
+        for (int r = 0; r < PR; ++r) {
+          float row[PC];
+#pragma unroll
+          for (int k = 0; k < PC; k += 2) {
+            const float2 t2 = *reinterpret_cast<const float2*>(xp + r * g.S + k);
+            row[k] = t2.x; row[k + 1] = t2.y;
+          }
+#pragma unroll
+          for (int a = 0; a < 2; ++a) {
+            const int kh = r - a;
+            if (kh < 0 || kh >= KH) continue;
+#pragma unroll
+            for (int kw = 0; kw < KW; ++kw) {
+              // keep the scheduler from hoisting every filter load of the (fully unrolled) tile to the top: it then needs
+              // ~230 registers and spills; with the loads pinned per tap pair the tile fits 2-3 CTAs per SM
+              if ((kw & 1) == 0) asm volatile("" ::: "memory");
+              float wv[OP];
+#pragma unroll
+              for (int o4 = 0; o4 < OP; o4 += 4) {
+                const float4 t4 = *reinterpret_cast<const float4*>(ws + ((c * KH + kh) * KW + kw) * OP + o4);
+                wv[o4] = t4.x; wv[o4 + 1] = t4.y; wv[o4 + 2] = t4.z; wv[o4 + 3] = t4.w;
+              }
+#pragma unroll
+              for (int b2 = 0; b2 < 2; ++b2)
+#pragma unroll
+                for (int o = 0; o < O; ++o) acc[a][b2][o] = fmaf(row[b2 + kw], wv[o], acc[a][b2][o]);
+            }
+          }
+        }
+      }
+      // stored cell (kh2, kw2) of the window is conv position (p, q) = (2q' + kw2, 2p' + kh2) = acc[kw2][kh2]
+      const int64_t f = ((int64_t)(n0 + (int)il) * O) * g.Fp + (int64_t)qp * g.Hp + pq;
+#pragma unroll
+      for (int o = 0; o < O; ++o) {
+        const float b0 = bs[o];
+        const float z0 = acc[0][0][o] + b0, z1 = acc[1][0][o] + b0, z2 = acc[0][1][o] + b0, z3 = acc[1][1][o] + b0;
+        float best = fmaxf(0.f, z0);
+        int arg = 0;
+        const float r1 = fmaxf(0.f, z1), r2 = fmaxf(0.f, z2), r3 = fmaxf(0.f, z3);
+        if (r1 > best) { best = r1; arg = 1; }
+        if (r2 > best) { best = r2; arg = 2; }
+        if (r3 > best) { best = r3; arg = 3; }
+        if (best > 0.f || z0 >= 0.f) arg |= 4;     // relu'(z at the argmax), as maxpool2x2_fwd_kernel<true>
+        y[f + (int64_t)o * g.Fp] = best;
+        idx[f + (int64_t)o * g.Fp] = (uint8_t)arg;
+      }
+    }
+    cur ^= 1;
+  }
+  asm volatile("cp.async.wait_all;" ::: "memory");
+}
+
+template <int C, int KH, int KW, int O>
+static int launch_fused_fwd(const float* x, const float* w, const float* bias, float* y, uint8_t* idx, FusedFwdGeo g, cudaStream_t st) {
+  constexpr int CKK = C * KH * KW, OP = (O + 3) & ~3;
+  auto kern = conv_relu_pool_fwd_kernel<C, KH, KW, O>;
+  static bool attr = false;
+  if (!attr) {
+    NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
+    attr = true;
+  }
+  const size_t fixed = (size_t)(CKK * OP + OP) * 4;
+  const size_t per_img = (size_t)2 * g.simg * 4;
+  // images per group: fill the 256 threads' tile slots as evenly as possible
+  int best_g = 1;
+  double best_eff = 0;
+  for (int G = 1; G <= 12 && fixed + G * per_img <= 72 * 1024; ++G) {
+    const int tiles = G * g.tpi;
+    const double eff = (double)tiles / (double)(ceil_div(tiles, 256) * 256);
+    if (eff > best_eff + 1e-9) { best_eff = eff; best_g = G; }
+  }
+  if (fixed + best_g * per_img > 96 * 1024) return -1;
+  int grid = 1;
+  int rc = balance_images(kern, 256, fixed, per_img, g.N, best_g, best_g, corun_hint() != 0, &g.G, &grid);
+  if (rc) return rc;
+  kern<<<grid, 256, fixed + (size_t)g.G * per_img, st>>>(x, w, bias, y, idx, g, FastDiv((uint32_t)g.tpi), FastDiv((uint32_t)g.Hp),
+                                                        FastDiv((uint32_t)(g.W / 2)));
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+bool conv_fused_fwd_serves(int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo) {
+  if (getenv("NGB_NO_FUSED_CONV_POOL")) return false;
+  if (pad != 0 || stride != 1 || Ho != Wo || (Ho & 1) || (W & 1)) return false;
+  return (C == 1 && KH == 5 && KW == 5 && O == 6) || (C == 1 && KH == 3 && KW == 3 && (O == 4 || O == 8));
+}
+
+// *done = false: geometry not served (the caller runs the convolution and the fused ReLU + pool kernel separately).
+int conv_fused_relu_pool_fwd(const float* x, const float* w, const float* bias, float* y, uint8_t* idx, int N, int C, int H, int W,
+                             int O, int KH, int KW, int pad, int stride, int Ho, int Wo, cudaStream_t st, bool* done) {
+  *done = false;
+  if (N < 1 || !conv_fused_fwd_serves(C, H, W, O, KH, KW, pad, stride, Ho, Wo) || ((uintptr_t)x & 7u)) return NGB_OK;
+  FusedFwdGeo g;
+  g.N = N; g.H = H; g.W = W; g.Ho = Ho; g.Hp = Ho / 2; g.Fp = (Ho / 2) * (Wo / 2);
+  g.ximg = C * H * W; g.tpi = g.Fp; g.G = 1;
+  // staged row pitch: even (64-bit patch loads); lanes walk p' first, then q', and read pair (S*q' + p') mod 16 of the 16
+  // bank pairs: S = Hp (mod 16) lets a half-warp cover all of them once
+  g.S = W + (W & 1);
+  for (int Sx = W + (W & 1); Sx < W + 16; Sx += 2)
+    if ((Sx & 15) == (g.Hp & 15)) { g.S = Sx; break; }
+  g.simg = C * H * g.S;
+  int rc = ensure_init();
+  if (rc) return rc;
+  rc = -1;
+  if (C == 1 && KH == 5 && KW == 5 && O == 6) rc = launch_fused_fwd<1, 5, 5, 6>(x, w, bias, y, idx, g, st);
+  else if (C == 1 && KH == 3 && KW == 3 && O == 4) rc = launch_fused_fwd<1, 3, 3, 4>(x, w, bias, y, idx, g, st);
+  else if (C == 1 && KH == 3 && KW == 3 && O == 8) rc = launch_fused_fwd<1, 3, 3, 8>(x, w, bias, y, idx, g, st);
+  if (rc == -1) return NGB_OK;
+  if (rc) return rc;
+  *done = true;
+  return NGB_OK;
+}
+
 }  // namespace ngb

@@ -295,7 +295,7 @@ class LazyArray(DeviceArray):
   backward).  `tag` / `args` tell such a consumer what the array stands for; anything else that touches `.t` / `.ptr`
   simply triggers the producing kernel, so the rest of the engine treats it as an ordinary array.  Metadata (shape,
   ndim, size) never materialises it."""
-  __slots__ = ('_shape', '_thunk', 'tag', 'args')
+  __slots__ = ('_shape', '_thunk', 'tag', 'args', '__weakref__')
 
   def __init__(self, shape, thunk, tag, args):
     self._shape = tuple(int(s) for s in shape)
@@ -341,6 +341,33 @@ class LazyArray(DeviceArray):
     return self._shape[0]
 
 
+# Deferred convolution outputs (tag 'conv') read their weights when they are finally produced: the optimizers flush the
+# ones somebody still holds before they touch the parameters (flush_lazy), so a late reader sees the forward-time values.
+_pending_convs = []
+
+
+def register_lazy(arr):
+  import weakref
+  _pending_convs.append(weakref.ref(arr))
+
+
+def flush_lazy():
+  if not _pending_convs:
+    return
+  refs, _pending_convs[:] = list(_pending_convs), []
+  for r in refs:
+    arr = r()
+    if arr is not None and arr.pending:
+      arr.t
+
+
+def opt_ptr(arr):
+  """Pointer argument for an operand the kernel does not read: NULL instead of producing a still-deferred array."""
+  if arr is None or (isinstance(arr, LazyArray) and arr.pending):
+    return None
+  return arr.ptr
+
+
 class PoolReluGrad:
   """What a deferred ReLU+MaxPool(2x2, stride 2) backward stands for: the pooled upstream gradient `pug`, the pooling
   argmax indices `idx`, the pool's output `ypool` and the ReLU's input `x`.  The convolution's weight gradient consumes
@@ -367,6 +394,7 @@ import os as _os
 POOLED_CONV_GRADS = _os.environ.get('NGB_NO_POOLED') != '1'   # conv weight / bias gradients straight from a pooled gradient
 POOLED_CONV_DGRAD = _os.environ.get('NGB_NO_POOLED_DGRAD') != '1'
 LAZY_FUSION = True   # ReLU -> MaxPool pairs run as fused kernels (set False to materialise every op's output eagerly)
+FUSED_CONV_POOL = _os.environ.get('NGB_NO_FUSED_CONV_POOL') != '1'   # first-layer conv -> ReLU -> MaxPool blocks in one kernel
 
 
 def unary(op, x, alpha=0.0):

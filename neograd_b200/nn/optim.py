@@ -15,6 +15,7 @@ import ctypes
 
 from ..autograd.utils import get_graph
 from ..device import DeviceArray, torch, _st
+from .. import device as D
 from .. import _backend as B
 from .. import distributed as dist
 
@@ -118,6 +119,7 @@ class Optimizer:
     """Data parallel: sum the flat gradient buffer over ranks -- peer-memory exchange over NVLink (the summed gradient is
     then `arena.grad_sum`), or one NCCL allreduce in place when peer memory is unavailable; returns grad_scale."""
     a = self.arena
+    D.flush_lazy()           # deferred conv outputs somebody still holds are produced before the weights change
     a.prepare_grads()
     if dist.is_initialized() and dist.world_size() > 1:
       if a.exchange is not None:

@@ -191,6 +191,22 @@ def conv_wbgrad_pooled(ug_pool, y_pool, idx, z, x, wshape, pad, stride, dw0=None
   return host(dw), host(db), fused
 
 
+def conv_relu_pool_fwd(x, w, b, pad, stride):
+  """(y_pool, idx) of the one-kernel conv + ReLU + MaxPool(2x2, s2) forward; None when the geometry is not served"""
+  N, C, H, W = x.shape
+  O, _, KH, KW = w.shape
+  Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+  X, Wt, Bs = dev(x), dev(w), dev(b)
+  y = torch.full((N, O, Ho // 2, Wo // 2), float('nan'), device='cuda')
+  idx = torch.full((N, O, Ho // 2, Wo // 2), 255, device='cuda', dtype=torch.uint8)
+  B.ensure_runtime()
+  rc = lib.ngb_conv_relu_pool_fwd(ptr(X), ptr(Wt), ptr(Bs), ptr(y), ptr(idx), N, C, H, W, O, KH, KW, pad, stride, st())
+  if rc == B.ERR_UNSUPPORTED:
+    return None
+  B.check(rc)
+  return host(y), host(idx)
+
+
 def conv_bgrad_pooled_idx(ug_pool, idx):
   N, O, Hp, Wp = ug_pool.shape
   db = torch.full((O,), float('nan'), device='cuda')

@@ -453,6 +453,42 @@ def test_conv_wbgrad_pooled_single_pass(U, N, C, H, W, O, K, stride):
   assert np.array_equal(again[0], dw) and np.array_equal(again[1], db)       # fixed summation order
 
 
+@pytest.mark.parametrize('N,H,O,K', [(300, 28, 6, 5), (37, 12, 6, 5), (130, 10, 4, 3), (77, 18, 8, 3), (3, 28, 6, 5)])
+def test_conv_relu_pool_forward_in_one_kernel(U, N, H, O, K):
+  """ngb_conv_relu_pool_fwd (first-layer block, the conv output is never written) against the separate kernels.  Small
+  integer operands make every product and sum exact in fp32, so pooled values, argmax bytes (ties between clamped zeros
+  included) and the ReLU flag in bit 2 must be IDENTICAL to ngb_conv_fprop (fp32 mode) -> ngb_maxpool_relu_fwd; real-valued
+  operands agree with the float64 oracle to fp32 rounding."""
+  rng = np.random.default_rng(N + H + O + K)
+  xi = rng.integers(-3, 4, (N, 1, H, H)).astype(np.float64)
+  wi = rng.integers(-2, 3, (O, 1, K, K)).astype(np.float64)
+  bi = rng.integers(-2, 3, (O,)).astype(np.float64)
+  xi[0] = 0.0                                             # z == bias everywhere: all-equal windows, exact zeros for bias 0
+  got = U.conv_relu_pool_fwd(xi, wi, bi, 0, 1)
+  assert got is not None
+  y, idx = got
+  with U.precision('fp32'):
+    z = U.conv_fprop(xi, wi, bi, 0, 1)
+  yr, idxr = U.maxpool_relu_fwd(z, (2, 2), 0, 2)
+  assert np.array_equal(y, yr) and np.array_equal(idx, idxr)
+  zo = ops.conv3d_fwd(xi, wi, bi, 0, 1)
+  yo = ops.maxpool_fwd(np.maximum(zo, 0.0), (2, 2), 0, 2)
+  yo = yo[0] if isinstance(yo, tuple) else yo
+  assert np.array_equal(y, yo.astype(np.float32))
+  xr, wr, br = f32(rng.standard_normal(xi.shape)), f32(rng.standard_normal(wi.shape) / K), f32(rng.standard_normal(O))
+  y2, _ = U.conv_relu_pool_fwd(xr, wr, br, 0, 1)
+  yo2 = ops.maxpool_fwd(np.maximum(ops.conv3d_fwd(xr, wr, br, 0, 1), 0.0), (2, 2), 0, 2)
+  yo2 = yo2[0] if isinstance(yo2, tuple) else yo2
+  close(y2, yo2, 4 * TOL32)
+
+
+def test_conv_relu_pool_forward_rejects_other_geometries(U):
+  x, w, b = np.zeros((2, 1, 12, 12)), np.zeros((6, 1, 5, 5)), np.zeros(6)
+  assert U.conv_relu_pool_fwd(x, w, b, 1, 1) is None                                   # padding
+  assert U.conv_relu_pool_fwd(np.zeros((2, 1, 13, 13)), w, b, 0, 1) is None            # odd output plane
+  assert U.conv_relu_pool_fwd(np.zeros((2, 3, 12, 12)), np.zeros((6, 3, 5, 5)), b, 0, 1) is None
+
+
 def test_maxpool_relu_fused_rejects_other_geometries(U):
   x = np.zeros((2, 3, 9, 9))
   assert U.maxpool_relu_fwd(x, (3, 3), 0, 3) is None

@@ -262,7 +262,7 @@ def test_backward_lanes_change_nothing(ng, captured):
   (kernels that co-run with the data-gradient chain use half of each SM), i.e. fp32 re-association."""
   from neograd_b200.capture import CapturedStep
   from neograd_b200.configs import lenet_synthetic, train_step
-  results = []
+  results, grads = [], []
   for n_lanes in (0, 3, 3):
     prev = ng.set_backward_lanes(n_lanes)
     try:
@@ -271,6 +271,9 @@ def test_backward_lanes_change_nothing(ng, captured):
       X, Y = ng.tensor(Xh), ng.tensor(Yh)
       optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
       loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+      loss_fn(model(X), Y).backward()                       # the gradients themselves, before Adam normalises them
+      grads.append([p.grad.numpy() for p in model.parameters()])
+      optim.zero_grad()
       if captured:
         step = CapturedStep(lambda: train_step(model, optim, loss_fn, X, Y), warmup=2)
         for _ in range(3):
@@ -281,9 +284,13 @@ def test_backward_lanes_change_nothing(ng, captured):
       results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
     finally:
       ng.set_backward_lanes(prev)
-  assert abs(results[0][0] - results[1][0]) <= 1e-6 * abs(results[0][0])
-  for a, b in zip(results[0][1:], results[1][1:]):
-    assert dist(a, b) < 1e-6, dist(a, b)
+  for i, (a, b) in enumerate(zip(grads[0], grads[1])):
+    assert dist(a, b) < 2e-6, (i, dist(a, b))
+  # Adam divides by sqrt(v): an entry whose gradient is at rounding-noise level can move by lr in either direction, so
+  # the trajectories agree to a few lr, not to fp32 rounding (same bound as test_c3_lenet_vs_oracle_at_size)
+  assert abs(results[0][0] - results[1][0]) <= 1e-4 * abs(results[0][0])
+  for i, (a, b) in enumerate(zip(results[0][1:], results[1][1:])):
+    assert np.max(np.abs(a - b)) < 5 * 1e-3, (i, np.max(np.abs(a - b)))
   assert results[1][0] == results[2][0]                     # same configuration twice: bit-identical
   for a, b in zip(results[1][1:], results[2][1:]):
     assert np.array_equal(a, b)
@@ -301,6 +308,7 @@ def test_lazy_relu_pool_fusion_changes_nothing(ng):
   results = []
   for fused, sparse in ((False, True), (True, False), (True, True)):
     prev, D.LAZY_FUSION = D.LAZY_FUSION, fused
+    prev_cp, D.FUSED_CONV_POOL = D.FUSED_CONV_POOL, sparse     # (the one-kernel fp32 conv+ReLU+pool forward likewise)
     if not sparse:
       os.environ['NGB_NO_SPARSE_WGRAD'] = '1'
     try:
@@ -313,7 +321,7 @@ def test_lazy_relu_pool_fusion_changes_nothing(ng):
         loss = train_step(model, optim, loss_fn, X, Y)
       results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
     finally:
-      D.LAZY_FUSION = prev
+      D.LAZY_FUSION, D.FUSED_CONV_POOL = prev, prev_cp
       os.environ.pop('NGB_NO_SPARSE_WGRAD', None)
   for other, tol in ((1, 1e-6), (2, 2e-3)):
     assert abs(results[0][0] - results[other][0]) <= tol * abs(results[0][0])
