@@ -148,12 +148,18 @@ def call_work(name, a):
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
     return 4 * (N * C * H * W + O * C * KH * KW + N * O * Ho * Wo), 2 * N * O * C * KH * KW * Ho * Wo
   if name in ('ngb_conv_dgrad_pooled', 'ngb_conv_wgrad_pooled'):
-    # the conv gradient taken from the 2x2-pooled upstream gradient: per pooling window the kernel needs ug_pool, y_pool
-    # (4 B each), idx (1 B) and ONE z value (4 B) instead of the 4 full-resolution gradient values (16 B)
+    # the conv gradient taken from the 2x2-pooled upstream gradient: per pooling window the kernel needs ug_pool (4 B) and
+    # the argmax byte (cell + ReLU flag) instead of the 4 full-resolution gradient values (16 B)
     N, C, H, W, O, KH, KW, pad, stride = a[6:15]
     Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
     win = N * O * (Ho // 2) * (Wo // 2)
-    return 4 * (N * C * H * W + O * C * KH * KW) + 13 * win, 2 * N * O * C * KH * KW * Ho * Wo
+    return 4 * (N * C * H * W + O * C * KH * KW) + 5 * win, 2 * N * O * C * KH * KW * Ho * Wo
+  if name == 'ngb_conv_relu_pool_fwd':
+    # conv + bias + ReLU + 2x2 pool in one pass: reads x and the filter bank, writes the pooled map and one argmax byte per window
+    N, C, H, W, O, KH, KW, pad, stride = a[5:14]
+    Ho, Wo = (H + 2 * pad - KH) // stride + 1, (W + 2 * pad - KW) // stride + 1
+    win = N * O * (Ho // 2) * (Wo // 2)
+    return 4 * (N * C * H * W + O * C * KH * KW + O) + 5 * win, 2 * N * O * C * KH * KW * Ho * Wo
   if name == 'ngb_conv_wbgrad_pooled':
     # weight + bias gradient in one pass: reads x, the pooled gradient and the argmax bytes; one window cell carries gradient
     N, C, H, W, O, KH, KW, pad, stride = a[7:16]

@@ -305,7 +305,7 @@ def test_lazy_relu_pool_fusion_changes_nothing(ng):
   import os
   from neograd_b200 import device as D
   from neograd_b200.configs import lenet_synthetic, train_step
-  results = []
+  results, grads = [], []
   for fused, sparse in ((False, True), (True, False), (True, True)):
     prev, D.LAZY_FUSION = D.LAZY_FUSION, fused
     prev_cp, D.FUSED_CONV_POOL = D.FUSED_CONV_POOL, sparse     # (the one-kernel fp32 conv+ReLU+pool forward likewise)
@@ -317,16 +317,25 @@ def test_lazy_relu_pool_fusion_changes_nothing(ng):
       X, Y = ng.tensor(Xh), ng.tensor(Yh)
       optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
       loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
+      first = loss_fn(model(X), Y)
+      first.backward()                                      # loss and gradients, before Adam normalises them
+      grads.append([float(first.data)] + [p.grad.numpy() for p in model.parameters()])
+      optim.zero_grad()
       for _ in range(4):
         loss = train_step(model, optim, loss_fn, X, Y)
       results.append([float(loss.data)] + [p.data.numpy() for p in model.parameters()])
     finally:
       D.LAZY_FUSION, D.FUSED_CONV_POOL = prev, prev_cp
       os.environ.pop('NGB_NO_SPARSE_WGRAD', None)
-  for other, tol in ((1, 1e-6), (2, 2e-3)):
-    assert abs(results[0][0] - results[other][0]) <= tol * abs(results[0][0])
-    for a, b in zip(results[0][1:], results[other][1:]):
-      assert dist(a, b) < tol, dist(a, b)
+  for other, tol in ((1, 2e-6), (2, 2e-3)):
+    assert abs(grads[0][0] - grads[other][0]) <= tol * abs(grads[0][0])
+    for i, (a, b) in enumerate(zip(grads[0][1:], grads[other][1:])):
+      assert dist(a, b) < tol, (other, i, dist(a, b))
+    # trajectories: Adam moves an entry whose gradient is at rounding-noise level by lr in either direction, so parameters
+    # agree to a few lr (same bound as test_c3_lenet_vs_oracle_at_size), not to the gradients' tolerance
+    assert abs(results[0][0] - results[other][0]) <= max(tol, 1e-4) * abs(results[0][0])
+    for i, (a, b) in enumerate(zip(results[0][1:], results[other][1:])):
+      assert np.max(np.abs(a - b)) < 5e-3, (other, i, np.max(np.abs(a - b)))
   # a lazily produced activation is an ordinary array for everything else
   x = ng.tensor(np.array([[-1.0, 2.0], [0.0, -3.0]]), requires_grad=True)
   r = ng.nn.ReLU()(x)
