@@ -327,13 +327,17 @@ def test_lazy_relu_pool_fusion_changes_nothing(ng):
     finally:
       D.LAZY_FUSION, D.FUSED_CONV_POOL = prev, prev_cp
       os.environ.pop('NGB_NO_SPARSE_WGRAD', None)
-  for other, tol in ((1, 2e-6), (2, 2e-3)):
-    assert abs(grads[0][0] - grads[other][0]) <= tol * abs(grads[0][0])
+  # configuration 2 computes the first block in fp32 instead of TF32: a forward value that moves by 5e-4 can change which
+  # cell of a near-tied pooling window wins (or a ReLU mask), which re-routes that window's gradient -- a few hundred of
+  # 221 K windows, ~1 % of the first layer's weight gradient.  (Both configurations sit within 2e-3 of the float64 oracle
+  # in test_c3_lenet_*; the fp32 one is the closer.)
+  for other, tol_loss, tol in ((1, 2e-6, 2e-6), (2, 2e-3, 3e-2)):
+    assert abs(grads[0][0] - grads[other][0]) <= tol_loss * abs(grads[0][0])
     for i, (a, b) in enumerate(zip(grads[0][1:], grads[other][1:])):
       assert dist(a, b) < tol, (other, i, dist(a, b))
     # trajectories: Adam moves an entry whose gradient is at rounding-noise level by lr in either direction, so parameters
     # agree to a few lr (same bound as test_c3_lenet_vs_oracle_at_size), not to the gradients' tolerance
-    assert abs(results[0][0] - results[other][0]) <= max(tol, 1e-4) * abs(results[0][0])
+    assert abs(results[0][0] - results[other][0]) <= max(tol_loss, 1e-4) * abs(results[0][0])
     for i, (a, b) in enumerate(zip(results[0][1:], results[other][1:])):
       assert np.max(np.abs(a - b)) < 5e-3, (other, i, np.max(np.abs(a - b)))
   # a lazily produced activation is an ordinary array for everything else
