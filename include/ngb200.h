@@ -56,6 +56,10 @@ int ngb_shutdown(void);
 /* Debug aid: synchronises the device and reports (NGB_ERR_CUDA + ngb_last_error) if a tcgen05 producer / MMA / epilogue
  * warp gave up waiting on a pipeline barrier since the last call (such waits are bounded so a bug cannot hang the GPU). */
 int ngb_debug_check_pipelines(void);
+/* Host only (no GPU): the bank-conflict-searched shared-memory layout of the small-channel conv weight-gradient tile for a
+ * layer: out[0..5] = row stride, column stride, plane pitch, taps-kh-fastest flag, wavefronts per gather load x 1000 with
+ * that layout and with the natural one. */
+int ngb_debug_wgrad_layout(int64_t C, int64_t H, int64_t W, int64_t KH, int64_t KW, int64_t pad, int64_t stride, int* out);
 /* Pre-sizes the grow-on-demand workspace the tensor-core convolutions stage their channels-last operand copies in
  * (N*C*H*W*4 bytes of the largest staged tensor).  Only needed before CUDA-graph capture, where growing is not allowed. */
 int ngb_workspace_reserve(int64_t bytes);

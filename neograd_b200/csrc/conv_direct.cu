@@ -24,6 +24,7 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
 // conv_small_mma.cu: TF32 mma.sync kernels for small-channel layers (fprop mode 0 / dgrad mode 1, wgrad)
 int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
                     int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done);
+int wgrad_layout_for_tests(int C, int H, int W, int KH, int KW, int pad, int stride, int* out);
 bool conv_sparse_serves(int C, int H, int W, int O, int KH, int KW, int pad, int Ho, int Wo);
 bool conv_fused_fwd_serves(int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo);
 int conv_fused_relu_pool_fwd(const float* x, const float* w, const float* bias, float* y, uint8_t* idx, int N, int C, int H, int W,
@@ -1059,6 +1060,17 @@ extern "C" int ngb_conv_relu_pool_fwd_serves(int64_t N, int64_t C, int64_t H, in
     return 0;
   const int Ho = (int)((H + 2 * pad - KH) / stride + 1), Wo = (int)((W + 2 * pad - KW) / stride + 1);
   return conv_fused_fwd_serves((int)C, (int)H, (int)W, (int)O, (int)KH, (int)KW, (int)pad, (int)stride, Ho, Wo) ? 1 : 0;
+}
+
+// Debug aid (host only, no GPU needed): the shared-memory layout the small-channel weight-gradient kernel would use for a
+// layer -- out[0..5] = row stride, column stride, plane pitch, taps-kh-fastest flag, wavefronts per gather load x 1000 for
+// that layout and for the natural one.
+extern "C" int ngb_debug_wgrad_layout(int64_t C, int64_t H, int64_t W, int64_t KH, int64_t KW, int64_t pad, int64_t stride,
+                                      int* out) {
+  NGB_CHECK_ARG(out != nullptr && C >= 1 && KH >= 1 && KW >= 1 && stride >= 1 && pad >= 0 && H + 2 * pad >= KH && W + 2 * pad >= KW &&
+                    C * KH * KW <= 4096 && H <= 4096 && W <= 4096,
+                "ngb_debug_wgrad_layout: bad geometry");
+  return wgrad_layout_for_tests((int)C, (int)H, (int)W, (int)KH, (int)KW, (int)pad, (int)stride, out);
 }
 
 // 1 when ngb_conv_wbgrad_pooled serves this geometry with ONE kernel (callers that would otherwise overlap the weight and

@@ -1217,6 +1217,20 @@ static XLayout search_x_layout(int C, int H, int W, int KH, int KW, int pad, int
   return best;
 }
 
+// Host-only view of the search for tests: out = {row stride, column stride, plane pitch, taps kh-fastest, wavefronts per
+// A-gather load x 1000} for the weight-gradient tile of the given layer.
+int wgrad_layout_for_tests(int C, int H, int W, int KH, int KW, int pad, int stride, int* out) {
+  const int Ho = (H + 2 * pad - KH) / stride + 1, Wo = (W + 2 * pad - KW) / stride + 1;
+  const int mt_total = ceil_div(C * KH * KW, 16), MS = ceil_div(mt_total, 5), MTW = ceil_div(mt_total, MS);
+  const int Mrows = MS * MTW * 16;
+  const XLayout L = search_x_layout(C, H, W, KH, KW, pad, stride, Ho, Wo, Mrows);
+  out[0] = L.sr; out[1] = L.sc; out[2] = L.splane; out[3] = L.khfast; out[4] = (int)(L.wavefronts * 1000.f + 0.5f);
+  const float natural = layout_cost(C, KH, KW, Ho, Ho * Wo, stride, Mrows, round_up_mod(W + 2 * pad, 8, 4), 1,
+                                    (H + 2 * pad) * round_up_mod(W + 2 * pad, 8, 4), 0);
+  out[5] = (int)(natural * 1000.f + 0.5f);
+  return NGB_OK;
+}
+
 template <int MTW, int NT, bool PF>
 static int launch_wgrad(const float* ug, const float* x, const uint8_t* pidx, const float* ypool, const float* zmask, float* part,
                         WgradGeo g, int nwarps, int gmin, int gmax, size_t fixed, size_t per_img, int* grid_out, cudaStream_t st) {

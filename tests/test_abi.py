@@ -71,3 +71,21 @@ def test_neograd_alias_package():
   for name in ('Model', 'Sequential', 'Dropout', 'Linear', 'Conv2D', 'Conv3D', 'MaxPool2D', 'MaxPool3D', 'ReLU', 'Sigmoid', 'Tanh',
                'Softmax', 'LeakyReLU', 'Checkpoint', 'save_model', 'load_model'):       # neograd/nn/__init__.py:1-5
     assert hasattr(nn, name), name
+
+
+def test_wgrad_tile_layout_search_is_conflict_free_for_lenet():
+  """Host-side logic of the small-channel weight-gradient kernel (csrc/conv_small_mma.cu:search_x_layout): lane (gq, t) of
+  an A-gather load reads word moff[tap gq] + poff[position t]; the searched strides / plane pitch / tap order must bring
+  both LeNet-B layers to ONE shared-memory wavefront per load (the natural pitch needs ~2), keep images 16-byte multiples
+  and leave the tile large enough for every tap of every position."""
+  import ctypes
+  from neograd_b200 import _backend as B
+  for (C, H, W, K) in ((1, 28, 28, 5), (6, 12, 12, 5), (3, 10, 14, 3), (4, 9, 11, 3)):
+    out = (ctypes.c_int * 6)()
+    B.check(B.lib.ngb_debug_wgrad_layout(C, H, W, K, K, 0, 1, ctypes.cast(out, ctypes.c_void_p)))
+    sr, sc, plane, khfast, cost, natural = list(out)
+    assert (C * plane) % 4 == 0 and khfast in (0, 1) and 1 in (sr, sc)
+    assert (H - 1) * sr + (W - 1) * sc < plane                      # every pixel of a plane fits
+    assert cost <= natural, (C, H, W, K, cost, natural)
+    if (C, H) in ((1, 28), (6, 12)):
+      assert cost == 1000 and natural >= 1700, (cost, natural)
