@@ -348,6 +348,8 @@ _pending_convs = []
 
 def register_lazy(arr):
   import weakref
+  if len(_pending_convs) >= 256:     # forward-only loops never reach an optimizer: keep the list to the live ones
+    _pending_convs[:] = [r for r in _pending_convs if r() is not None and r().pending]
   _pending_convs.append(weakref.ref(arr))
 
 
