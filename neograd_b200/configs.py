@@ -1,96 +1,26 @@
-"""The BASELINE.json configurations written against the public API exactly as a neograd user would write them
-(README.md:95-106, examples/digits.ipynb cell 7, SURVEY 8d C3A / C3B, examples/gans/basic.ipynb cells 7-11).
-Used by bench.py, the parity tests and smoke(); nothing here is special-cased by the backend."""
-import numpy as np
+"""The BASELINE.json configurations bound to this package (definitions: workload_defs.py, shared with the reference arm
+of bench.py).  Used by bench.py, the parity tests and smoke(); nothing here is special-cased by the backend."""
+import numpy as np  # noqa: F401
 
-import neograd_b200 as ng
-from neograd_b200 import nn
+from . import nn
+from .workload_defs import (model_classes, set_params, synthetic_params, lenet_data, gan_data, train_step,  # noqa: F401
+                            gan_iteration)
 
-
-class MLPCircles(nn.Model):
-  """C1: Linear(2,100) ReLU Linear(100,1) Sigmoid."""
-
-  def __init__(self):
-    self.stack = nn.Sequential(nn.Linear(2, 100), nn.ReLU(), nn.Linear(100, 1), nn.Sigmoid())
-
-  def forward(self, inputs):
-    return self.stack(inputs)
-
-
-class DigitsCNN(nn.Model):
-  """C2: Conv2D((3,3)) ReLU reshape(B,36) Linear(36,10)."""
-
-  def __init__(self):
-    self.conv = nn.Sequential(nn.Conv2D((3, 3)), nn.ReLU())
-    self.stack = nn.Sequential(nn.Linear(36, 10))
-
-  def forward(self, inputs):
-    conv_outputs = self.conv(inputs)
-    return self.stack(conv_outputs.reshape((inputs.shape[0], 36)))
-
-
-class LeNetA(nn.Model):
-  """C3A: neograd's single-channel Conv2D / MaxPool2D on (B,28,28); 13 106 parameters."""
-
-  def __init__(self):
-    self.conv = nn.Sequential(nn.Conv2D((5, 5)), nn.ReLU(), nn.MaxPool2D((2, 2), stride=2),
-                              nn.Conv2D((5, 5)), nn.ReLU(), nn.MaxPool2D((2, 2), stride=2))
-    self.stack = nn.Sequential(nn.Linear(16, 120), nn.ReLU(), nn.Linear(120, 84), nn.ReLU(), nn.Linear(84, 10))
-
-  def forward(self, inputs):
-    return self.stack(self.conv(inputs).reshape((inputs.shape[0], 16)))
-
-
-class LeNetB(nn.Model):
-  """C3B: LeNet-5 channels with Conv3D(1,6,5x5) / MaxPool3D / Conv3D(6,16,5x5) on (B,1,28,28); 44 426 parameters."""
-
-  def __init__(self):
-    self.conv = nn.Sequential(nn.Conv3D(1, 6, (5, 5)), nn.ReLU(), nn.MaxPool3D((2, 2), stride=2),
-                              nn.Conv3D(6, 16, (5, 5)), nn.ReLU(), nn.MaxPool3D((2, 2), stride=2))
-    self.stack = nn.Sequential(nn.Linear(256, 120), nn.ReLU(), nn.Linear(120, 84), nn.ReLU(), nn.Linear(84, 10))
-
-  def forward(self, inputs):
-    return self.stack(self.conv(inputs).reshape((inputs.shape[0], 256)))
-
-
-class GAN(nn.Model):
-  """C4: MLP generator + discriminator (examples/gans/basic.ipynb cell 7 with the dims of SURVEY 8d)."""
-
-  def __init__(self, data_dim=784, h1=512, h2=256):
-    self.data_dim = data_dim
-    self.generator = nn.Sequential(nn.Linear(data_dim, h1), nn.LeakyReLU(), nn.Linear(h1, h2), nn.LeakyReLU(),
-                                   nn.Linear(h2, data_dim))
-    self.discriminator = nn.Sequential(nn.Linear(data_dim, h1), nn.LeakyReLU(), nn.Linear(h1, h2), nn.LeakyReLU(),
-                                       nn.Linear(h2, 1), nn.Sigmoid())
-
-  def forward(self, noise):
-    return self.discriminator(self.generator(noise))
-
-
-def set_params(model, arrays):
-  """Assign host arrays to model.parameters() in order, through the Param.data setter."""
-  params = model.parameters()
-  assert len(params) == len(arrays), (len(params), len(arrays))
-  for p, a in zip(params, arrays):
-    p.data = np.asarray(a, dtype=np.float64).reshape(p.shape)
+_C = model_classes(nn)
+MLPCircles, DigitsCNN, LeNetA, LeNetB, GAN = _C['MLPCircles'], _C['DigitsCNN'], _C['LeNetA'], _C['LeNetB'], _C['GAN']
 
 
 def lenet_synthetic(kind, batch, seed=0, scale=0.1):
-  """SURVEY 8d C3 inputs: X ~ N(0,1), one-hot labels, weights 0.1*randn (seed+1), biases 0."""
-  rng = np.random.default_rng(seed)
-  x = rng.standard_normal((batch, 28, 28) if kind == 'a' else (batch, 1, 28, 28)).astype(np.float32)
-  y = np.eye(10, dtype=np.float32)[rng.integers(0, 10, batch)]
+  """X ~ N(0,1), one-hot labels, weights 0.1*randn (seed+1), biases 0."""
+  x, y = lenet_data(kind, batch, seed)
   model = (LeNetA if kind == 'a' else LeNetB)()
-  wrng = np.random.default_rng(seed + 1)
-  set_params(model, [scale * wrng.standard_normal(p.shape) if i % 2 == 0 else np.zeros(p.shape)
-                     for i, p in enumerate(model.parameters())])
+  set_params(model, synthetic_params([p.shape for p in model.parameters()], seed + 1, scale))
   return model, x, y
 
 
-def train_step(model, optim, loss_fn, X, Y):
-  """README.md:109-115."""
-  optim.zero_grad()
-  loss = loss_fn(model(X), Y)
-  loss.backward()
-  optim.step()
-  return loss
+def gan_synthetic(batch, data_dim=784, h1=512, h2=256, seed=0, scale=0.05):
+  """real rows ~ N(0,1), two noise batches, weights 0.05*randn (seed+1), biases 0."""
+  real, noise_g, noise_d = gan_data(batch, data_dim, seed)
+  model = GAN(data_dim, h1, h2)
+  set_params(model, synthetic_params([p.shape for p in model.parameters()], seed + 1, scale))
+  return model, real, noise_g, noise_d

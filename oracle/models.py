@@ -197,3 +197,70 @@ def digits_cnn(rng):
   """examples/digits.ipynb cell 7: Conv2D((3,3)) ReLU reshape(B,36) Linear(36,10)."""
   return SeqNet([('conv2d', rng.standard_normal((3, 3)), np.array(0.0), 0, 1), ('relu',), ('reshape', (36,)),
                  ('linear', rng.standard_normal((36, 10)), np.zeros((1, 10)))])
+
+
+# ----------------------------------------------------------------------------- config C4: the MLP GAN
+def gan_nets(rng, data_dim=784, h1=512, h2=256, scale=0.05, leak=0.01):
+  """examples/gans/basic.ipynb cell 7 with the dims of SURVEY 8d C4: generator data_dim-h1-h2-data_dim, discriminator
+  data_dim-h1-h2-1-Sigmoid, LeakyReLU between the Linears.  Draw order = Model.parameters() order (generator first)."""
+  r = lambda *s: scale * rng.standard_normal(s)
+  def stack(dims, tail):
+    layers = []
+    for i, (a, b) in enumerate(zip(dims[:-1], dims[1:])):
+      layers.append(('linear', r(a, b), np.zeros((1, b))))
+      if i + 2 < len(dims):
+        layers.append(('leaky_relu', leak))
+    return SeqNet(layers + tail)
+  gen = stack([data_dim, h1, h2, data_dim], [])
+  disc = stack([data_dim, h1, h2, 1], [('sigmoid',)])
+  return gen, disc
+
+
+def gan_iteration(gen, disc, opt_g, opt_d, noise_g, noise_d, real, return_grads=False):
+  """One iteration of basic.ipynb cells 9-10: generator step (discriminator frozen, BCE(D(G(z)), 1)), then
+  discriminator step (generator frozen, BCE(D(real), 1) + BCE(D(G(z')), 0)).  BCE keeps the reference's swapped
+  argument roles (loss.py:83).  A frozen sub-model's parameters have requires_grad=False, so its Adam moments and
+  values are untouched by the other optimizer's step (optim.py:173-174): two independent Adam states, each with its
+  own `iter`.  Returns (loss_g, loss_d[, generator grads, discriminator grads])."""
+  n = noise_g.shape[0]
+  ones, zeros = np.ones((n, 1)), np.zeros((n, 1))
+  out = disc.forward(gen.forward(noise_g))
+  loss_g, dout = bce(out, ones)
+  disc.backward(dout)
+  g_gen = gen.backward(disc.input_grad)
+  opt_g.step(g_gen)
+  fake = gen.forward(noise_d)
+  l_real, d_real = bce(disc.forward(real), np.ones((real.shape[0], 1)))
+  g_real = disc.backward(d_real)
+  l_fake, d_fake = bce(disc.forward(fake), zeros)
+  g_fake = disc.backward(d_fake)
+  g_disc = [a + b for a, b in zip(g_real, g_fake)]
+  opt_d.step(g_disc)
+  if return_grads:
+    return float(loss_g), float(l_real + l_fake), g_gen, g_disc
+  return float(loss_g), float(l_real + l_fake)
+
+
+GAN784_DIMS = (784, 512, 256)
+GAN784_STRIDE = 97
+
+
+def _f32(x):
+  return np.asarray(x, np.float32).astype(np.float64)
+
+
+def gan784_inputs(batch, iters, seed=7):
+  """Seeded, float32-representable parameters and data shared by the generator script and the tests."""
+  d, h1, h2 = GAN784_DIMS
+  rng = np.random.default_rng(seed)
+  shapes = [(d, h1), (1, h1), (h1, h2), (1, h2), (h2, d), (1, d), (d, h1), (1, h1), (h1, h2), (1, h2), (h2, 1), (1, 1)]
+  params = [_f32(0.05 * rng.standard_normal(s)) for s in shapes]
+  real = _f32(rng.standard_normal((batch, d)))
+  noise_g = _f32(rng.standard_normal((iters, batch, d)))
+  noise_d = _f32(rng.standard_normal((iters, batch, d)))
+  return params, real, noise_g, noise_d
+
+
+def sample(a):
+  a = np.asarray(a, dtype=np.float64).reshape(-1)
+  return np.concatenate([[np.sqrt(np.sum(a * a))], a[::GAN784_STRIDE]])

@@ -90,12 +90,13 @@ def conv_dgrad(ug, w, xshape, pad, stride):
   return host(dx)
 
 
-def conv_wgrad(ug, x, wshape, pad, stride):
+def conv_wgrad(ug, x, wshape, pad, stride, into=None):
+  """`into`: an existing gradient the kernel must accumulate onto (accumulate = 1)"""
   N, C, H, W = x.shape
   O, _, KH, KW = wshape
-  dw = torch.full(tuple(wshape), float('nan'), device='cuda')
+  dw = torch.full(tuple(wshape), float('nan'), device='cuda') if into is None else dev(into)
   U, X = dev(ug), dev(x)
-  call('ngb_conv_wgrad', ptr(U), ptr(X), ptr(dw), N, C, H, W, O, KH, KW, pad, stride, 0, st())
+  call('ngb_conv_wgrad', ptr(U), ptr(X), ptr(dw), N, C, H, W, O, KH, KW, pad, stride, 0 if into is None else 1, st())
   return host(dw)
 
 

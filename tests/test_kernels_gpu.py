@@ -304,6 +304,7 @@ IGEMM_CASES = [   # N, C, H, W, O, KH, KW, pad  (stride 1, C % 32 == O % 32 == 0
   (2, 128, 32, 32, 128, 3, 3, 1),      # C5 family
   (1, 64, 64, 64, 256, 3, 3, 1),       # BN = 256
   (3, 32, 16, 20, 32, 3, 2, 1),        # rectangular filter
+  (256, 64, 32, 32, 64, 3, 3, 1),      # a full BASELINE C5 sweep point (N = 256, C = O = 64, H = W = 32)
 ]
 
 
@@ -331,6 +332,13 @@ def test_conv_igemm_exact_on_small_integers(U):
   assert np.array_equal(U.conv_fprop(x, w, b, 1, 1), y.astype(np.float32))
   ug = rng.integers(-3, 4, y.shape).astype(np.float64)
   assert np.array_equal(U.conv_dgrad(ug, w, x.shape, 1, 1), ops.conv3d_dgrad(ug, w, x.shape, 1, 1).astype(np.float32))
+  # weight gradient (conv_wgrad_igemm_kernel, split over positions + deterministic reduce): |sum| <= 9 * 4096 < 2^24, so
+  # any summation order is exact in fp32
+  assert np.array_equal(U.conv_wgrad(ug, x, w.shape, 1, 1), ops.conv3d_wgrad(ug, x, w.shape, 1, 1).astype(np.float32))
+  # ... and accumulating into an existing gradient buffer
+  dw0 = rng.integers(-4, 5, w.shape).astype(np.float64)
+  assert np.array_equal(U.conv_wgrad(ug, x, w.shape, 1, 1, into=dw0),
+                        (dw0 + ops.conv3d_wgrad(ug, x, w.shape, 1, 1)).astype(np.float32))
 
 
 def test_no_pipeline_timeouts(U):

@@ -97,7 +97,7 @@ def test_c3_lenet_grads_and_steps(ng, kind):
 
 
 @pytest.mark.parametrize('precision', ['fp32', 'tf32'])
-@pytest.mark.parametrize('kind,batch', [('a', 4096), ('b', 512)])
+@pytest.mark.parametrize('kind,batch', [('a', 4096), ('b', 512), ('b', 4096)])
 def test_c3_lenet_vs_oracle_at_size(ng, kind, batch, precision):
   """Same seeded inputs through the device path and the float64 oracle at (close to) the BASELINE batch size, in both
   precision modes.  Zero-initialised biases move by exactly lr*sign(g) in the first Adam steps, so entries whose
@@ -202,6 +202,114 @@ def test_c4_gan_matches_reference_trajectory(ng):
   for i, p in enumerate(model.parameters()):
     d = dist(p.data.numpy(), g[f'final_{i}'])
     assert d < 2e-3, (i, d)
+
+
+def _gan784(ng, params):
+  from neograd_b200.configs import GAN, set_params
+  np.random.seed(0)
+  model = GAN(*models.GAN784_DIMS)
+  set_params(model, params)
+  return model
+
+
+def test_c4_gan784_matches_reference_trajectory(ng):
+  """Config C4 at the BASELINE dims (784-512-256), batch 512, against the UNMODIFIED reference's recorded run
+  (tests/golden/step_c4_gan784.npz, oracle/gen_golden_gan784.py): first-step gradients of all twelve parameters, three
+  generator + discriminator iterations of losses, final parameters (each on its L2 norm and every 97th element).
+  Every Dot here is tcgen05 TF32 (three passes behind the first generator weight gradient): gradients 2e-3, losses 1e-3."""
+  g = load_golden('step_c4_gan784')
+  B, iters, lr = int(g['batch']), int(g['iters']), float(g['lr'])
+  params, real, noise_g, noise_d = models.gan784_inputs(B, iters)
+  model = _gan784(ng, params)
+  nn = ng.nn
+  optim_g, optim_d = nn.optim.Adam(model.parameters(), lr), nn.optim.Adam(model.parameters(), lr)
+  loss_fn = nn.loss.BCE()
+  ones, zeros, realT = ng.tensor(np.ones((B, 1))), ng.tensor(np.zeros((B, 1))), ng.tensor(real)
+  lg, ld = [], []
+  for it in range(iters):      # examples/gans/basic.ipynb cells 9-10 (same statements as configs.gan_iteration)
+    model.discriminator.freeze()
+    optim_g.zero_grad(all_members=True)
+    loss_g = loss_fn(model(ng.tensor(noise_g[it])), ones)
+    loss_g.backward()
+    if it == 0:
+      for i, p in enumerate(model.parameters()[:6]):
+        d = dist(models.sample(p.grad.numpy()), g[f'grad_{i}'])
+        assert d < 2e-3, (i, d)
+    optim_g.step()
+    model.discriminator.unfreeze()
+    model.generator.freeze()
+    optim_d.zero_grad(all_members=True)
+    fake = model.generator(ng.tensor(noise_d[it]))
+    loss_d = loss_fn(model.discriminator(realT), ones) + loss_fn(model.discriminator(fake), zeros)
+    loss_d.backward()
+    if it == 0:
+      for i, p in enumerate(model.parameters()[6:]):
+        d = dist(models.sample(p.grad.numpy()), g[f'grad_{i + 6}'])
+        assert d < 2e-3, (i + 6, d)
+    optim_d.step()
+    model.generator.unfreeze()
+    lg.append(float(loss_g.data))
+    ld.append(float(loss_d.data))
+  assert dist(lg, g['losses_g']) < 1e-3, (lg, g['losses_g'])
+  assert dist(ld, g['losses_d']) < 1e-3, (ld, g['losses_d'])
+  for i, p in enumerate(model.parameters()):
+    got, want = models.sample(p.data.numpy()), g[f'final_{i}']
+    if i % 2 == 0:
+      assert dist(got, want) < 2e-3, (i, dist(got, want))
+    else:   # zero-initialised bias: Adam moves each entry by ~lr per step whatever the gradient's size (see test_c3_*)
+      assert np.mean(np.abs(got[1:] - want[1:])) < 0.1 * lr * iters, (i, np.mean(np.abs(got[1:] - want[1:])) / (lr * iters))
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'fp32'])
+def test_c4_gan784_vs_oracle_at_size(ng, precision):
+  """The BASELINE C4 configuration itself -- 784-512-256, batch 8192 -- through the device path and the float64 oracle on
+  the same seeded inputs: one generator + discriminator iteration; losses, the first-step gradients of all twelve
+  parameters and the parameters after the two Adam updates."""
+  from neograd_b200.configs import gan_iteration
+  B, lr = 8192, 3e-4
+  params, real, noise_g, noise_d = models.gan784_inputs(B, 1)
+  prev = ng.set_precision(precision)
+  try:
+    model = _gan784(ng, params)
+    gen, disc = models.gan_nets(np.random.default_rng(0))
+    gen.set_params(params[:6])
+    disc.set_params(params[6:])
+    og, od = models.Adam(gen, lr), models.Adam(disc, lr)
+    olg, old, ogg, ogd = models.gan_iteration(gen, disc, og, od, noise_g[0], noise_d[0], real, return_grads=True)
+    nn = ng.nn
+    optim_g, optim_d = nn.optim.Adam(model.parameters(), lr), nn.optim.Adam(model.parameters(), lr)
+    loss_fn = nn.loss.BCE()
+    ones, zeros = ng.tensor(np.ones((B, 1))), ng.tensor(np.zeros((B, 1)))
+    tol = 2e-3 if precision == 'tf32' else 2e-5
+    # generator half
+    model.discriminator.freeze()
+    optim_g.zero_grad(all_members=True)
+    loss_g = loss_fn(model(ng.tensor(noise_g[0])), ones)
+    loss_g.backward()
+    for i, (p, r) in enumerate(zip(model.parameters()[:6], ogg)):
+      assert dist(p.grad.numpy(), r) < tol, ('gen', i, dist(p.grad.numpy(), r))
+    optim_g.step()
+    model.discriminator.unfreeze()
+    # discriminator half
+    model.generator.freeze()
+    optim_d.zero_grad(all_members=True)
+    fake = model.generator(ng.tensor(noise_d[0]))
+    loss_d = loss_fn(model.discriminator(ng.tensor(real)), ones) + loss_fn(model.discriminator(fake), zeros)
+    loss_d.backward()
+    for i, (p, r) in enumerate(zip(model.parameters()[6:], ogd)):
+      assert dist(p.grad.numpy(), r) < tol, ('disc', i, dist(p.grad.numpy(), r))
+    optim_d.step()
+    model.generator.unfreeze()
+    assert abs(float(loss_g.data) - olg) < tol * abs(olg), (float(loss_g.data), olg)
+    assert abs(float(loss_d.data) - old) < tol * abs(old), (float(loss_d.data), old)
+    for i, (p, r) in enumerate(zip(model.parameters(), gen.params() + disc.params())):
+      got = p.data.numpy()
+      if i % 2 == 0:
+        assert dist(got, r) < tol, (i, dist(got, r))
+      else:
+        assert np.max(np.abs(got - r)) <= 2.001 * lr, (i, np.max(np.abs(got - r)))   # one Adam step moves an entry by <= lr
+  finally:
+    ng.set_precision(prev)
 
 
 def test_grad_check_passes_on_device(ng):

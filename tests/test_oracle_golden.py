@@ -177,6 +177,31 @@ def test_step_c3_lenet(kind):
     close(net.params()[i], g[f'final_{i}'], 1e-7)
 
 
+def test_step_c4_gan784():
+  """Config C4 at the BASELINE dims (784-512-256), batch 512: the oracle's GAN iteration against the unmodified reference's
+  recorded run (oracle/gen_golden_gan784.py): first-step gradients of all twelve parameters, three iterations of losses,
+  final parameters (each compared on its L2 norm and every 97th element)."""
+  g = load_golden('step_c4_gan784')
+  B, iters, lr = int(g['batch']), int(g['iters']), float(g['lr'])
+  params, real, noise_g, noise_d = models.gan784_inputs(B, iters)
+  gen, disc = models.gan_nets(np.random.default_rng(0))
+  gen.set_params(params[:6])
+  disc.set_params(params[6:])
+  opt_g, opt_d = models.Adam(gen, lr), models.Adam(disc, lr)
+  lg, ld = [], []
+  for it in range(iters):
+    a, b, gg, gd = models.gan_iteration(gen, disc, opt_g, opt_d, noise_g[it], noise_d[it], real, return_grads=True)
+    lg.append(a)
+    ld.append(b)
+    if it == 0:
+      for i, gr in enumerate(gg + gd):
+        close(models.sample(gr), g[f'grad_{i}'], 1e-11)
+  close(lg, g['losses_g'], 1e-10)
+  close(ld, g['losses_d'], 1e-10)
+  for i, p in enumerate(gen.params() + disc.params()):
+    close(models.sample(p), g[f'final_{i}'], 1e-8)
+
+
 def test_geometry_and_errors():
   assert ops.out_hw(12, 15, 4, 4, 0, 2) == (5, 6)
   assert ops.out_hw(12, 15, 2, 2, 2, 1) == (15, 18)

@@ -11,7 +11,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
   ap = argparse.ArgumentParser()
   ap.add_argument('--workload', default='lenet_b')
-  ap.add_argument('--batch', type=int, default=4096)
+  ap.add_argument('--batch', type=int, default=0)
   ap.add_argument('--lanes', type=int, default=3)
   ap.add_argument('--flush', type=int, default=1)
   args = ap.parse_args()
@@ -19,13 +19,11 @@ def main():
   from torch.profiler import ProfilerActivity, profile
   import neograd_b200 as ng
   from neograd_b200.capture import CapturedStep
-  from neograd_b200.configs import lenet_synthetic, train_step
+  import bench
   ng.set_backward_lanes(args.lanes)
-  model, x, y = lenet_synthetic(args.workload[-1], args.batch, seed=100)
-  X, Y = ng.tensor(x), ng.tensor(y)
-  optim = ng.nn.optim.Adam(model.parameters(), 1e-3)
-  loss_fn = ng.nn.loss.SoftmaxCE(axis=1)
-  step = CapturedStep(lambda: train_step(model, optim, loss_fn, X, Y), warmup=3)
+  wl = bench.make_workload(ng, args.workload, args.batch or bench.BATCH[args.workload], 0)
+  wl.setup_optim()
+  step = CapturedStep(wl.make_step([ng.tensor(a) for a in wl.host_inputs]), warmup=3)
   flush = torch.empty(256 << 20, device='cuda', dtype=torch.uint8)
   for _ in range(3):
     step()
