@@ -89,6 +89,29 @@ int ngb_gemm(int engine, int transA, int transB, int64_t M, int64_t N, int64_t K
              const float* A, int64_t lda, const float* B, int64_t ldb, float* C, int64_t ldc,
              int accumulate, ngb_stream_t stream);
 
+/* ---- Linear layers in one kernel per pass: neograd/nn/layers/misc.py:63 (+ the activation layer that follows) ------ */
+/* `act` is an ngb_unary_op (NGB_RELU, NGB_LEAKY_RELU with slope `alpha`, NGB_SIGMOID, NGB_TANH) or -1 for none.
+ * x (batch, n_in), W (n_in, n_out), b (n_out) or NULL, all row-major and dense.
+ * forward: z = x.W + b (misc.py:63: dot basics.py:194 + broadcast add basics.py:20) and a = act(z) (activations.py:20, 205,
+ * 55, 87) from the same accumulators; either output pointer may be NULL (not both). */
+int ngb_linear_fwd(const float* x, const float* W, const float* b, float* z, float* a, int act, float alpha,
+                   int64_t batch, int64_t n_in, int64_t n_out, ngb_stream_t stream);
+/* data gradient: dx (+)= (ug . W^T) * act'(zprev)  -- basics.py:206 followed by the backward of the activation that
+ * produced this layer's input from zprev (activations.py:31, 216, 63, 99); zprev (batch, n_in) may be NULL (no mask). */
+int ngb_linear_dgrad(const float* ug, const float* W, const float* zprev, float* dx, int act, float alpha,
+                     int64_t batch, int64_t n_in, int64_t n_out, int accumulate, ngb_stream_t stream);
+/* weight and bias gradient from one pass over ug: dW (+)= x^T . ug (basics.py:207), db (+)= column sums of ug (the
+ * `unbroadcast` of the bias add: autograd/utils.py:75 via tensor.py:93-100); db may be NULL. */
+int ngb_linear_wgrad(const float* x, const float* ug, float* dW, float* db, int64_t batch, int64_t n_in, int64_t n_out,
+                     int accumulate_w, int accumulate_b, ngb_stream_t stream);
+/* classifier head: z = x.W + b, loss = SoftmaxCE(z, targets) along the class axis (nn/loss.py:153-157) and
+ * dz = (softmax(z) - targets) * inv_num_examples (loss.py:170 with upstream gradient 1) in one kernel; z may be NULL.
+ * Layers with at most 32 outputs (ngb_linear_softmax_ce_serves tells; NGB_ERR_UNSUPPORTED otherwise). */
+int ngb_linear_softmax_ce(const float* x, const float* W, const float* b, const float* targets, float* z, float* loss,
+                          float* dz, int64_t batch, int64_t n_in, int64_t n_out, float inv_num_examples, float epsilon,
+                          ngb_stream_t stream);
+int ngb_linear_softmax_ce_serves(int64_t batch, int64_t n_in, int64_t n_out);
+
 /* ---- Conv3D / Conv2D: neograd/autograd/ops/conv.py:121-343 ------------------------------------------------- */
 /* x (N,C,H,W), w (O,C,KH,KW), b (O) -> y (N,O,Ho,Wo) in neograd order.  neograd's single-channel Conv2D
  * (conv.py:131-152) is the C=O=1 case with a one-element bias. */
@@ -219,9 +242,11 @@ int ngb_softmax_bwd(const float* x, const float* ug, int64_t outer, int64_t L, i
  * double on the host and only then rounded to fp32.  `t` is the iteration count AFTER the increment of optim.py:169. */
 int ngb_adam_step(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                   double epsilon, int64_t t, double grad_scale, ngb_stream_t stream);       /* optim.py:168-179, 191-197 */
-/* CUDA-graph friendly variant: the iteration count lives in device memory.  With tick != 0, *t_dev is incremented (by a
- * one-thread launch ahead of the update) before use, so a captured training step replays with the right bias
- * correction; an optimizer that updates several ranges of one arena ticks on the first range only. */
+/* CUDA-graph friendly variant: the iteration count lives in device memory, so a captured training step replays with the
+ * right bias correction.  t_dev points to TWO int32: [0] = steps taken so far, [1] = scratch counter (0 between calls).
+ * tick = 1: this launch is step t_dev[0] + 1 and stores it when it completes (optim.py:169 folded into the update);
+ * tick = 2: same step number, nothing stored (an optimizer that updates several ranges of one arena passes 2 on all but
+ * the last range); tick = 0: the step number is t_dev[0] as it stands. */
 int ngb_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n, double lr, double beta1, double beta2,
                       double epsilon, int32_t* t_dev, int tick, double grad_scale, ngb_stream_t stream);
 int ngb_sgd_step(float* p, const float* g, int64_t n, double lr, double grad_scale, ngb_stream_t stream);  /* optim.py:42-47 */

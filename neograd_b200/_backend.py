@@ -62,6 +62,11 @@ SIGNATURES = {
   'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
   'ngb_launch_count': ([], c_int64),
   'ngb_gemm': ([c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _S], c_int),
+  'ngb_linear_fwd': ([_P, _P, _P, _P, _P, c_int, c_float, c_int64, c_int64, c_int64, _S], c_int),
+  'ngb_linear_dgrad': ([_P, _P, _P, _P, c_int, c_float, c_int64, c_int64, c_int64, c_int, _S], c_int),
+  'ngb_linear_wgrad': ([_P, _P, _P, _P, c_int64, c_int64, c_int64, c_int, c_int, _S], c_int),
+  'ngb_linear_softmax_ce': ([_P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64, c_float, c_float, _S], c_int),
+  'ngb_linear_softmax_ce_serves': ([c_int64, c_int64, c_int64], c_int),
   'ngb_conv_fprop': ([_P, _P, _P, _P] + [c_int64] * 9 + [_S], c_int),
   'ngb_conv_dgrad': ([_P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
   'ngb_conv_wgrad': ([_P, _P, _P] + [c_int64] * 9 + [c_int, _S], c_int),
@@ -259,7 +264,7 @@ class profile_calls:
   Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
   SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
           'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane', 'ngb_set_corun', 'ngb_xgpu_check',
-          'ngb_debug_wgrad_layout', 'ngb_conv_relu_pool_fwd_serves', 'ngb_conv_wbgrad_pooled_is_fused')
+          'ngb_debug_wgrad_layout', 'ngb_conv_relu_pool_fwd_serves', 'ngb_conv_wbgrad_pooled_is_fused', 'ngb_linear_softmax_ce_serves')
 
   def __enter__(self):
     import torch

@@ -99,9 +99,16 @@ class _Unary(Operation):
   def forward(self, tens):
     tens = self.get_tensors(tens)
     x, op, alpha = tens.data, self.OP, self.alpha
-    if op == B.RELU and D.LAZY_FUSION:
+    if (op in _LINEAR_ACTS and D.LAZY_FUSION and D.FUSED_LINEAR and isinstance(x, D.LazyArray) and x.pending
+        and x.tag == 'linear'):
+      # the input is a Linear layer's output nobody has read yet: z = x.W + b and act(z) come out of ONE kernel (the GEMM's
+      # epilogue writes both) when this activation is first used
+      out = D.LazyArray(x.shape, x.args.act_thunk(x, op, alpha), 'linear_act', None)
+      D.register_lazy(out, x.args.sources())
+    elif op == B.RELU and D.LAZY_FUSION:
       # produced on first use: a MaxPool that follows reads x itself (maxpool(relu(x)) in one kernel, conv.py here)
       out = D.LazyArray(x.shape, lambda: D.unary(op, x, alpha), 'relu', x)
+      D.register_lazy(out, (x,))
     else:
       out = D.unary(op, x, alpha)
     return self.get_result_tensor(out, tens)
@@ -110,6 +117,13 @@ class _Unary(Operation):
     op, alpha, x = self.OP, self.alpha, tens.data
 
     def into(ug, dst, accumulate):
+      if op in _LINEAR_ACTS and isinstance(ug, D.LazyArray) and ug.pending and ug.tag == 'linear_dgrad':
+        # upstream gradient = data gradient of the Linear layer that consumed this activation, not computed yet:
+        # (ug0 . W^T) * act'(x) in one kernel (the mask rides in the GEMM's epilogue)
+        if dst is None:
+          dst, accumulate = D.DeviceArray.empty(x.shape), False
+        ug.args.run(dst, accumulate, x, op, alpha)
+        return dst
       if op == B.RELU and isinstance(ug, D.LazyArray) and ug.pending and ug.tag == 'maxpool_bwd':
         # upstream gradient = input gradient of a MaxPool that has not been written yet: route + mask in one kernel
         pug, idx, outer, H, W, KH, KW, pad, stride, _ = ug.args
@@ -138,6 +152,9 @@ class _Unary(Operation):
         return None
       return D.LazyArray(x.shape, lambda: into(ug, None, False), 'pool_relu_bwd', D.PoolReluGrad(pug, idx, ypool, x, outer, H, W))
     tens.set_grad_fn(GradFn(into, None, lazy))
+
+
+_LINEAR_ACTS = (B.RELU, B.LEAKY_RELU, B.SIGMOID, B.TANH)   # activations the Linear kernels' epilogues implement
 
 
 class Exp(_Unary):

@@ -44,7 +44,7 @@ def _conv_forward(op, x4, w4, b1, out_shape):
     # a ReLU -> MaxPool(2x2, s2) behind this convolution runs with it as ONE kernel (_MaxPool.forward) and this output is
     # never written; anything else that reads it produces it here
     out = D.LazyArray(out_shape, run, 'conv', (x4, w4, b1, (N, C, H, W, O, KH, KW, pad, stride)))
-    D.register_lazy(out)
+    D.register_lazy(out, (x4, w4, b1))
     return out
   return run()
 

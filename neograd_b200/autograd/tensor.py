@@ -13,7 +13,7 @@
 import numpy as np
 
 from .._backend import lanes as _lanes
-from ..device import DeviceArray
+from ..device import ConstScalar, DeviceArray
 from .utils import process_data, unbroadcast_data
 
 
@@ -141,7 +141,7 @@ class Tensor:
     if type(upper_grad) in (int, float):
       if self.shape != ():
         raise ValueError("Shapes of grad and Tensor data must match!")
-      upper_grad = DeviceArray.full((), upper_grad)
+      upper_grad = ConstScalar(upper_grad)      # stays a host-known immediate until a kernel needs it in memory
       if not self._grad_live and not self._grad_pinned:
         self._grad, self._grad_live, self._grad_shared = upper_grad, True, False   # our own fresh buffer: no copy needed
       else:

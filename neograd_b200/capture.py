@@ -44,4 +44,6 @@ class CapturedStep:
 
 def copy_from_host(dst_tensor, pinned_host_tensor):
   """Async H2D copy of a pinned torch host tensor into a neograd Tensor's device buffer (same element count)."""
+  from .device import flush_readers_of
+  flush_readers_of(dst_tensor.data)      # deferred arrays that still read the old batch are produced first
   dst_tensor.data.t.view(-1).copy_(pinned_host_tensor.view(-1), non_blocking=True)

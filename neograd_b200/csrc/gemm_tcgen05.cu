@@ -19,9 +19,11 @@
 namespace ngb {
 
 int gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
-              int64_t ldb, float* C, int64_t ldc, int accumulate, cudaStream_t st);
+              int64_t ldb, float* C, int64_t ldc, int accumulate, cudaStream_t st, const tc::Epilogue* epi = nullptr);
 int launch_splitk_reduce(const float* part, int splits, int64_t M, int64_t N, float* C, int64_t ldc, int accumulate,
                          cudaStream_t st);
+int launch_splitk_reduce2(const float* part, int splits, int64_t M, int64_t N, float* C, int64_t ldc, int accumulate,
+                          const float* cs_part, float* cs_out, int cs_accumulate, cudaStream_t st);
 
 namespace tc {
 
@@ -62,15 +64,22 @@ constexpr int UMMA_K = 8;             // tf32: 32 bytes per instruction
 constexpr int kThreads = 192;
 constexpr uint32_t kSpinNone = 0;
 
-template <int BLOCK_N>
+// COLSUM: the weight-gradient GEMM of a Linear layer also produces the bias gradient -- the column sums of its B operand
+// (the upstream gradient) -- by multiplying every B stage with an all-ones A tile into a second accumulator (every row of
+// which is the column sum).  Costs one more UMMA per k-step on the CTAs of the first row of output tiles, 16 KB of shared
+// memory for the ones tile and twice the TMEM columns.
+template <int BLOCK_N, bool COLSUM = false>
 struct Cfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;
   static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
-  static constexpr int kStages = (192 * 1024) / kStageBytes > 8 ? 8 : (192 * 1024) / kStageBytes;
-  static constexpr int kTmemCols = 2 * BLOCK_N < 32 ? 32 : 2 * BLOCK_N;  // 2 accumulator stages (power of two >= 32)
+  static constexpr int kOnesBytes = COLSUM ? kABytes : 0;
+  static constexpr int kRing = 192 * 1024 - kOnesBytes;
+  static constexpr int kStages = kRing / kStageBytes > 8 ? 8 : kRing / kStageBytes;
+  static constexpr int kAccCols = COLSUM ? 2 * BLOCK_N : BLOCK_N;        // TMEM columns per accumulator stage
+  static constexpr int kTmemCols = 2 * kAccCols < 32 ? 32 : 2 * kAccCols;  // 2 accumulator stages (power of two >= 32)
   static constexpr int kEpiBytes = 2 * 128 * 128;                        // two [128 rows][32 cols] staging tiles for TMA stores
-  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kEpiBytes + kOnesBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 struct GemmArgs {
@@ -85,21 +94,50 @@ struct GemmArgs {
   int accumulate;
   int a_3d, b_3d;      // MN-major operand described by a 3-D map {32, K, MN/32}: one TMA box per stage instead of MN/32
   int tma_store;       // epilogue goes registers -> swizzled smem -> TMA store (coalesced 128B lines); needs ldc % 4 == 0
+  // ---- fused epilogue (Linear layers; all optional)
+  const float* bias;   // [N]: added to every output row before anything else (layers/misc.py:63)
+  int act;             // NGB_EPI_*: activation applied to (acc + bias) for the SECOND output C2 (activations.py:20, 205, 55)
+  float alpha;         // LeakyReLU slope
+  float* C2;           // second output [M, N] (ld = ldc2): act(acc + bias); C itself may be null then (tma_store maps: tmap_c2)
+  int64_t ldc2;
+  int store_c;         // write C (0 when only the activation is wanted)
+  const float* mask_z; // [M, N] (ld = ldm): output is multiplied by act'(mask_z) (activations.py:31, 216) -- data-grad of a Linear
+  int64_t ldm;         //   whose input was act(mask_z)
+  float* colsum;       // COLSUM kernels: [N] column sums of the B operand (bias gradient), or the split partials [split][N]
+  int colsum_accumulate;
 };
 
+// activation ids of the fused epilogue (= ngb_unary_op of include/ngb200.h; -1 = none)
+__device__ __forceinline__ float epi_act(int act, float alpha, float v) {
+  if (act == NGB_RELU) return fmaxf(v, 0.f);
+  if (act == NGB_LEAKY_RELU) return v >= 0.f ? v : alpha * v;
+  if (act == NGB_SIGMOID) return 1.f / (1.f + __expf(-v));
+  if (act == NGB_TANH) return tanhf(v);
+  return v;
+}
+// d act(z) / dz from the pre-activation z (the reference's masks: relu / leaky use z >= 0)
+__device__ __forceinline__ float epi_act_grad(int act, float alpha, float z) {
+  if (act == NGB_RELU) return z >= 0.f ? 1.f : 0.f;
+  if (act == NGB_LEAKY_RELU) return z >= 0.f ? 1.f : alpha;
+  if (act == NGB_SIGMOID) { const float s = 1.f / (1.f + __expf(-z)); return s * (1.f - s); }
+  if (act == NGB_TANH) { const float t = tanhf(z); return 1.f - t * t; }
+  return 1.f;
+}
+
 // A_MN / B_MN: operand is MN-major in global memory (1) or K-major (0).
-template <int BLOCK_N, int A_MN, int B_MN>
+template <int BLOCK_N, int A_MN, int B_MN, bool COLSUM = false>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
-                 const __grid_constant__ CUtensorMap tmap_c, const GemmArgs g) {
-  using C_ = Cfg<BLOCK_N>;
+                 const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2, const GemmArgs g) {
+  using C_ = Cfg<BLOCK_N, COLSUM>;
   constexpr int kStages = C_::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* smem_a = smem;
   uint8_t* smem_b = smem + kStages * C_::kABytes;
   uint8_t* smem_epi = smem + kStages * C_::kStageBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes + C_::kEpiBytes);
+  uint8_t* smem_ones = smem_epi + C_::kEpiBytes;      // COLSUM: [128 x 32] tile of 1.0f (any operand layout of all-ones is all-ones)
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + kStages * C_::kStageBytes + C_::kEpiBytes + C_::kOnesBytes);
   uint64_t* full = bars;
   uint64_t* empty = bars + kStages;
   uint64_t* tmem_full = bars + 2 * kStages;
@@ -116,6 +154,11 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, C_::kTmemCols);
+  if (COLSUM) {
+    for (int i = threadIdx.x; i < C_::kOnesBytes / 16; i += kThreads)
+      reinterpret_cast<float4*>(smem_ones)[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+    fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -183,7 +226,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_ph ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        const uint32_t d_tmem = tmem_base + acc * C_::kAccCols;
+        const bool do_colsum = COLSUM && ((w / g.splits) % g.tiles_m) == 0;   // first row of output tiles only
+        const uint32_t ones_addr = smem_u32(smem_ones);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
@@ -195,6 +240,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
             umma_tf32(d_tmem, smem_desc(adesc_base, a_addr + k * a_kstep), smem_desc(bdesc_base, b_addr + k * b_kstep),
                       idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (COLSUM && do_colsum)
+              umma_tf32(d_tmem + BLOCK_N, smem_desc(adesc_base, ones_addr + k * a_kstep),
+                        smem_desc(bdesc_base, b_addr + k * b_kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
           umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
         }
@@ -221,21 +269,69 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       if (g.partial) { ld = g.N; out_row = g.partial + (int64_t)split * g.M * g.N + (int64_t)row * ld; }
       else { ld = g.ldc; out_row = g.C + (int64_t)row * ld; }
       const bool accum = !g.partial && g.accumulate;
+      const bool tile_colsum = COLSUM && (tile % g.tiles_m) == 0;
 #pragma unroll 1
       for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
         float v[32];
-        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * BLOCK_N + c0, v);
+        tmem_ld32(tmem_base + (uint32_t(quad * 32) << 16) + acc * C_::kAccCols + c0, v);
         tmem_ld_wait();
+        if (COLSUM && tile_colsum && quad == 0) {
+          // second accumulator: every row holds the column sums of the B operand; lane 0 (row 0) writes them
+          float cs[32];
+          tmem_ld32(tmem_base + acc * C_::kAccCols + BLOCK_N + c0, cs);
+          tmem_ld_wait();
+          if (lane == 0) {
+            float* dst = g.partial ? g.colsum + (int64_t)split * g.N : g.colsum;
+            const bool cacc = !g.partial && g.colsum_accumulate;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = n0 + c0 + j;
+              if (n < g.N) dst[n] = cacc ? dst[n] + cs[j] : cs[j];
+            }
+          }
+        }
         if (c0 + 32 >= BLOCK_N) {  // last chunk read: hand the accumulator back before the (slow) global stores
           tc_fence_before();
           __syncwarp();
           if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
-        if (g.tma_store) {
-          // registers -> smem tile [128 rows][32 cols] in the 128B-swizzle the store tensor map expects -> one TMA store
-          // (whole 128-byte lines, M / N tails clipped by the tensor map).  Two tiles alternate so the store of chunk i
-          // overlaps the TMEM reads of chunk i+1.
-          if (n0 + c0 < g.N) {
+        const int nbase = n0 + c0;
+        if (nbase >= g.N) continue;           // (uniform across the CTA)
+        // ---- fused epilogue on the registers: + bias, * act'(z_prev)
+        if (g.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] += (nbase + j < g.N) ? __ldg(g.bias + nbase + j) : 0.f;
+        }
+        if (g.mask_z && row < g.M) {
+          const float* zr = g.mask_z + (int64_t)row * g.ldm + nbase;
+          if (nbase + 32 <= g.N && (g.ldm % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.mask_z) & 15) == 0)) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              const float4 z4 = *reinterpret_cast<const float4*>(zr + j);
+              v[j] *= epi_act_grad(g.act, g.alpha, z4.x);
+              v[j + 1] *= epi_act_grad(g.act, g.alpha, z4.y);
+              v[j + 2] *= epi_act_grad(g.act, g.alpha, z4.z);
+              v[j + 3] *= epi_act_grad(g.act, g.alpha, z4.w);
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < g.N) v[j] *= epi_act_grad(g.act, g.alpha, zr[j]);
+          }
+        }
+        // ---- up to two outputs: C (the values themselves) and C2 = act(values)
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+          if (which == 0 && !g.store_c) continue;
+          if (which == 1) {
+            if (!g.C2) break;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = epi_act(g.act, g.alpha, v[j]);
+          }
+          if (g.tma_store) {
+            // registers -> smem tile [128 rows][32 cols] in the 128B-swizzle the store tensor map expects -> one TMA store
+            // (whole 128-byte lines, M / N tails clipped by the tensor map).  Two tiles alternate so the store of chunk i
+            // overlaps the TMEM reads of chunk i+1.
             uint8_t* tile_s = smem_epi + (chunk_it & 1) * (128 * 128);
             if (et == 0) tma_store_wait_read<1>();          // the store that last read this tile has drained it
             asm volatile("bar.sync 1, 128;" ::: "memory");
@@ -246,26 +342,29 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
             fence_proxy_async();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et == 0) {
-              if (g.partial) tma_store_3d(&tmap_c, tile_s, n0 + c0, m0, split);
-              else tma_store_2d(&tmap_c, tile_s, n0 + c0, m0, accum);
+              if (which == 1) tma_store_2d(&tmap_c2, tile_s, nbase, m0, false);
+              else if (g.partial) tma_store_3d(&tmap_c, tile_s, nbase, m0, split);
+              else tma_store_2d(&tmap_c, tile_s, nbase, m0, accum);
               tma_store_commit();
             }
             ++chunk_it;
-          }
-        } else if (row < g.M) {
-          const int nbase = n0 + c0;
-          if (vec_ok && nbase + 32 <= g.N) {
+          } else if (row < g.M) {
+            float* orow = which == 1 ? g.C2 + (int64_t)row * g.ldc2 : out_row;
+            const bool acc_here = which == 0 && accum;
+            const bool v_ok = which == 1 ? ((g.ldc2 % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C2) & 15) == 0)) : vec_ok;
+            if (v_ok && nbase + 32 <= g.N) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-              float4* p = reinterpret_cast<float4*>(out_row + nbase + j);
-              if (accum) { float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
-              *p = o;
-            }
-          } else {
+              for (int j = 0; j < 32; j += 4) {
+                float4 o = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                float4* p = reinterpret_cast<float4*>(orow + nbase + j);
+                if (acc_here) { float4 old = *p; o.x += old.x; o.y += old.y; o.z += old.z; o.w += old.w; }
+                *p = o;
+              }
+            } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              if (nbase + j < g.N) out_row[nbase + j] = accum ? out_row[nbase + j] + v[j] : v[j];
+              for (int j = 0; j < 32; ++j) {
+                if (nbase + j < g.N) orow[nbase + j] = acc_here ? orow[nbase + j] + v[j] : v[j];
+              }
             }
           }
         }
@@ -283,28 +382,31 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 }
 
 // ---------------------------------------------------------------------------------------------- host launch
-template <int BLOCK_N, int A_MN, int B_MN>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const GemmArgs& g, int grid,
-                  cudaStream_t st) {
-  using C_ = Cfg<BLOCK_N>;
-  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN>;
+template <int BLOCK_N, int A_MN, int B_MN, bool COLSUM>
+static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tc2, const GemmArgs& g,
+                  int grid, cudaStream_t st) {
+  using C_ = Cfg<BLOCK_N, COLSUM>;
+  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, COLSUM>;
   static bool attr_set = false;
   if (!attr_set) {
     NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(ta, tb, tc_, g);
+  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(ta, tb, tc_, tc2, g);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
 
 template <int BLOCK_N>
-static int launch_major(int a_mn, int b_mn, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const GemmArgs& g,
-                        int grid, cudaStream_t st) {
-  if (!a_mn && !b_mn) return launch<BLOCK_N, 0, 0>(ta, tb, tc_, g, grid, st);
-  if (!a_mn && b_mn) return launch<BLOCK_N, 0, 1>(ta, tb, tc_, g, grid, st);
-  if (a_mn && !b_mn) return launch<BLOCK_N, 1, 0>(ta, tb, tc_, g, grid, st);
-  return launch<BLOCK_N, 1, 1>(ta, tb, tc_, g, grid, st);
+static int launch_major(int a_mn, int b_mn, bool colsum, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_,
+                        const CUtensorMap& tc2, const GemmArgs& g, int grid, cudaStream_t st) {
+  if constexpr (BLOCK_N <= 128) {
+    if (colsum) return launch<BLOCK_N, 1, 1, true>(ta, tb, tc_, tc2, g, grid, st);   // (only the TN weight-gradient form)
+  }
+  if (!a_mn && !b_mn) return launch<BLOCK_N, 0, 0, false>(ta, tb, tc_, tc2, g, grid, st);
+  if (!a_mn && b_mn) return launch<BLOCK_N, 0, 1, false>(ta, tb, tc_, tc2, g, grid, st);
+  if (a_mn && !b_mn) return launch<BLOCK_N, 1, 0, false>(ta, tb, tc_, tc2, g, grid, st);
+  return launch<BLOCK_N, 1, 1, false>(ta, tb, tc_, tc2, g, grid, st);
 }
 
 bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc) {
@@ -316,18 +418,41 @@ bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, i
   return true;
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* v = getenv(name);
+  return v ? atoi(v) : dflt;
+}
+
 int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
-            int64_t ldb, float* C, int64_t ldc, int accumulate, cudaStream_t st) {
+            int64_t ldb, float* C, int64_t ldc, int accumulate, cudaStream_t st, const Epilogue* epi) {
   if (!aligned16(A) || !aligned16(B)) return fail(NGB_ERR_UNSUPPORTED, "tcgen05 GEMM needs 16-byte aligned operands");
   const int a_mn = transA ? 1 : 0;  // A stored [K,M] (M contiguous) -> MN-major
   const int b_mn = transB ? 0 : 1;  // B stored [K,N] (N contiguous) -> MN-major; stored [N,K] -> K-major
-  // widest tile that still gives the grid about a full wave of CTAs: a 256-wide tile on an 8192 x 256 output leaves
-  // 64 CTAs for 148 SMs (and needs split-K plus a reduce pass to fill them), two 128-wide tiles per row do not
+  Epilogue e;
+  if (epi) e = *epi;
+  const bool colsum = e.colsum != nullptr;
+  const bool fused = e.bias || e.mask_z || e.C2;     // needs the complete sums in the epilogue: no split-K
+  if (colsum && !(a_mn && b_mn)) return fail(NGB_ERR_UNSUPPORTED, "tcgen05 GEMM: column sums only in the TN (weight-gradient) form");
+
+  // Tile width and K-splits.  The kernel is bound by shared-memory fill (each k-block brings (128 + BN) x 128 B for
+  // 128 x BN x 32 MACs), so bytes per MAC fall with BN: prefer the widest tile, and when that leaves the grid short of
+  // CTAs cover the SMs with K-splits (deterministic second pass) rather than with narrower tiles.  A narrower tile is taken
+  // only while it gives more whole tiles without splitting (short K) -- see profiles/r02_gemm_tiles.md for the sweep.
+  const int64_t tm = ceil_div<int64_t>(M, BLOCK_M);
+  const int k_blocks = (int)ceil_div<int64_t>(K, BLOCK_K);
   int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  {
-    const int64_t tm = ceil_div<int64_t>(M, BLOCK_M);
+  if (colsum && BN > 128) BN = 128;                   // two accumulators per stage: 4 x BN TMEM columns <= 512
+  const bool can_split = !fused && k_blocks >= 16;
+  if (!can_split) {
     while (BN > 64 && tm * ceil_div<int64_t>(N, BN) < (3 * kNumSMs) / 4 && ceil_div<int64_t>(N, BN / 2) > ceil_div<int64_t>(N, BN))
       BN /= 2;
+  } else {
+    // with splitting available only drop to a narrower tile when the wide one wastes a large part of its columns
+    while (BN > 64 && ceil_div<int64_t>(N, BN) * BN >= N + BN / 2) BN /= 2;
+  }
+  {
+    const int f = env_int("NGB_GEMM_BN", 0);          // tuning / experiments
+    if (f == 64 || f == 128 || (f == 256 && !colsum)) BN = f;
   }
 
   CUtensorMap ta, tb;
@@ -363,18 +488,22 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   }
 
   GemmArgs g;
+  memset(&g, 0, sizeof(g));
   g.M = (int)M; g.N = (int)N;
-  g.k_blocks = (int)ceil_div<int64_t>(K, BLOCK_K);
-  g.tiles_m = (int)ceil_div<int64_t>(M, BLOCK_M);
+  g.k_blocks = k_blocks;
+  g.tiles_m = (int)tm;
   g.tiles_n = (int)ceil_div<int64_t>(N, BN);
   const int tiles = g.tiles_m * g.tiles_n;
   int splits = 1;
-  if (tiles < kNumSMs / 2 && g.k_blocks >= 16) {
-    splits = kNumSMs / tiles;
-    if (splits > g.k_blocks / 8) splits = g.k_blocks / 8;
+  if (can_split && tiles < (3 * kNumSMs) / 4) {
+    splits = ceil_div(kNumSMs, tiles);
+    // every split should still stream a few k-blocks: below ~4 the pipeline fill / drain and the partials dominate
+    if (splits > g.k_blocks / 4) splits = g.k_blocks / 4;
+    const int f = env_int("NGB_GEMM_SPLITS", 0);
+    if (f > 0) splits = f < g.k_blocks ? f : g.k_blocks;
     if (splits > 1) {
       if (ensure_init() != NGB_OK) return NGB_ERR_CUDA;
-      const int64_t cap = scratch_bytes() / (M * N * (int64_t)sizeof(float));
+      const int64_t cap = scratch_bytes() / ((M * N + N) * (int64_t)sizeof(float));
       if (splits > cap) splits = (int)cap;
     }
     if (splits < 1) splits = 1;
@@ -385,30 +514,48 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   g.partial = g.splits > 1 ? scratch_ptr() : nullptr;
   g.accumulate = accumulate;
   g.a_3d = a_3d; g.b_3d = b_3d;
+  g.bias = e.bias; g.act = e.act; g.alpha = e.alpha; g.C2 = e.C2; g.ldc2 = e.ldc2; g.store_c = (C != nullptr && e.store_c) ? 1 : 0;
+  g.mask_z = e.mask_z; g.ldm = e.ldm;
+  float* cs_part = g.partial ? g.partial + (int64_t)g.splits * M * N : nullptr;
+  g.colsum = colsum ? (g.partial ? cs_part : e.colsum) : nullptr;
+  g.colsum_accumulate = e.colsum_accumulate;
   const int work = tiles * g.splits;
   const int grid = work < kNumSMs ? work : kNumSMs;
 
-  // output tensor map for the TMA-store epilogue: C itself, or the split partials as {N, M, splits}
-  CUtensorMap tcm;
+  // output tensor maps for the TMA-store epilogue: C itself, or the split partials as {N, M, splits}; C2 likewise
+  CUtensorMap tcm, tcm2;
   memset(&tcm, 0, sizeof(tcm));
+  memset(&tcm2, 0, sizeof(tcm2));
   g.tma_store = 0;
   {
     const bool to_partial = g.splits > 1;
     const float* obase = to_partial ? g.partial : C;
     const int64_t old = to_partial ? N : ldc;
     static const bool no_tma_store = getenv("NGB_NO_TMA_STORE") != nullptr;
-    if (!no_tma_store && old % 4 == 0 && aligned16(obase)) {
+    bool ok = !no_tma_store;
+    if (g.store_c) ok = ok && old % 4 == 0 && aligned16(obase);
+    if (g.C2) ok = ok && g.ldc2 % 4 == 0 && aligned16(g.C2);
+    if (ok && g.store_c) {
       uint64_t dims[3] = {(uint64_t)N, (uint64_t)M, (uint64_t)g.splits}, str[2] = {(uint64_t)old * 4, (uint64_t)M * N * 4};
       uint32_t box[3] = {32, 128, 1};
-      if (make_tmap_f32(&tcm, obase, to_partial ? 3 : 2, dims, str, box, false, /*plain_f32=*/true) == NGB_OK) g.tma_store = 1;
+      ok = make_tmap_f32(&tcm, obase, to_partial ? 3 : 2, dims, str, box, false, /*plain_f32=*/true) == NGB_OK;
     }
+    if (ok && g.C2) {
+      uint64_t dims[2] = {(uint64_t)N, (uint64_t)M}, str[1] = {(uint64_t)g.ldc2 * 4};
+      uint32_t box[2] = {32, 128};
+      ok = make_tmap_f32(&tcm2, g.C2, 2, dims, str, box, false, /*plain_f32=*/true) == NGB_OK;
+    }
+    g.tma_store = ok ? 1 : 0;
   }
   int rc;
-  if (BN == 64) rc = launch_major<64>(a_mn, b_mn, ta, tb, tcm, g, grid, st);
-  else if (BN == 128) rc = launch_major<128>(a_mn, b_mn, ta, tb, tcm, g, grid, st);
-  else rc = launch_major<256>(a_mn, b_mn, ta, tb, tcm, g, grid, st);
+  if (BN == 64) rc = launch_major<64>(a_mn, b_mn, colsum, ta, tb, tcm, tcm2, g, grid, st);
+  else if (BN == 128) rc = launch_major<128>(a_mn, b_mn, colsum, ta, tb, tcm, tcm2, g, grid, st);
+  else rc = launch_major<256>(a_mn, b_mn, colsum, ta, tb, tcm, tcm2, g, grid, st);
   if (rc) return rc;
-  if (g.splits > 1) return launch_splitk_reduce(g.partial, g.splits, M, N, C, ldc, accumulate, st);
+  if (g.splits > 1) {
+    if (!colsum) return launch_splitk_reduce(g.partial, g.splits, M, N, C, ldc, accumulate, st);
+    return launch_splitk_reduce2(g.partial, g.splits, M, N, C, ldc, accumulate, cs_part, e.colsum, e.colsum_accumulate, st);
+  }
   return NGB_OK;
 }
 

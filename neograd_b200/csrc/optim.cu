@@ -18,13 +18,18 @@ __device__ __forceinline__ void adam1(float& p, float g, float& m, float& v, con
   p -= a.lr * (mh / (sqrtf(vh) + a.eps));   // optim.py:179
 }
 
-// T_DEV: the iteration count is read from device memory (already incremented by adam_tick_kernel).
+// T_DEV: the iteration count lives in device memory: t_dev[0] = steps taken so far, t_dev[1] = blocks-done counter (0 between
+// launches).  tick = 1: this launch is step t_dev[0] + 1 and records it when its last block finishes (every block has read
+// the old value by then); tick = 2: same step number, but further launches of the step follow (frozen parameters split the
+// arena into several ranges), nothing is recorded; tick = 0: use t_dev[0] as is.
 template <bool T_DEV>
 __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
-                                                   float* __restrict__ v, int64_t n, AdamP a, const int32_t* __restrict__ t_dev,
-                                                   double b1d, double b2d, int vec_ok) {
+                                                   float* __restrict__ v, int64_t n, AdamP a, int32_t* __restrict__ t_dev,
+                                                   double b1d, double b2d, int vec_ok, int tick) {
+  int32_t step = 0;
   if (T_DEV) {
-    const double t = (double)*t_dev;
+    step = *reinterpret_cast<volatile int32_t*>(t_dev) + (tick ? 1 : 0);
+    const double t = (double)step;
     a.ibc1 = (float)(1.0 / (1.0 - pow(b1d, t)));
     a.ibc2 = (float)(1.0 / (1.0 - pow(b2d, t)));
   }
@@ -44,9 +49,18 @@ __global__ void __launch_bounds__(256) adam_kernel(float* __restrict__ p, const 
     done = n4 << 2;
   }
   for (int64_t i = done + tid; i < n; i += nt) adam1(p[i], g[i], m[i], v[i], a);
+  if (T_DEV && tick == 1) {                                        // optim.py:169, recorded by the last block to finish
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();
+      unsigned int* cnt = reinterpret_cast<unsigned int*>(t_dev + 1);
+      if (atomicAdd(cnt, 1u) == gridDim.x - 1) {
+        t_dev[0] = step;
+        *cnt = 0;
+      }
+    }
+  }
 }
-
-__global__ void adam_tick_kernel(int32_t* t_dev) { *t_dev += 1; }   // optim.py:169
 
 __global__ void __launch_bounds__(256) sgd_kernel(float* __restrict__ p, const float* __restrict__ g, int64_t n, float lr,
                                                   float gs, int vec_ok) {
@@ -104,7 +118,7 @@ extern "C" int ngb_adam_step(float* p, const float* g, float* m, float* v, int64
   if (n == 0) return NGB_OK;
   const AdamP a = make_adam(lr, beta1, beta2, epsilon, (double)t, grad_scale);
   const int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
-  adam_kernel<false><<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, nullptr, 0, 0, vec);
+  adam_kernel<false><<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, as_stream(stream)>>>(p, g, m, v, n, a, nullptr, 0, 0, vec, 0);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
@@ -113,15 +127,13 @@ extern "C" int ngb_adam_step_dev(float* p, const float* g, float* m, float* v, i
                                  double beta2, double epsilon, int32_t* t_dev, int tick, double grad_scale,
                                  ngb_stream_t stream) {
   NGB_CHECK_ARG(t_dev != nullptr, "ngb_adam_step_dev: t_dev is NULL");
+  NGB_CHECK_ARG(tick >= 0 && tick <= 2, "ngb_adam_step_dev: tick must be 0, 1 or 2");
   cudaStream_t st = as_stream(stream);
-  if (tick) {
-    adam_tick_kernel<<<1, 1, 0, st>>>(t_dev);
-    NGB_LAUNCH_CHECK();
-  }
-  if (n == 0) return NGB_OK;
   const AdamP a = make_adam(lr, beta1, beta2, epsilon, 0, grad_scale);
   const int vec = aligned16(p) && aligned16(g) && aligned16(m) && aligned16(v);
-  adam_kernel<true><<<grid_for(ceil_div<int64_t>(n, 4), 256), 256, 0, st>>>(p, g, m, v, n, a, t_dev, beta1, beta2, vec);
+  // (n == 0 with tick == 1 still launches one block: the step must be counted)
+  if (n == 0 && tick != 1) return NGB_OK;
+  adam_kernel<true><<<grid_for(ceil_div<int64_t>(n > 0 ? n : 1, 4), 256), 256, 0, st>>>(p, g, m, v, n, a, t_dev, beta1, beta2, vec, tick);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }

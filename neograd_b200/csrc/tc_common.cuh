@@ -226,5 +226,23 @@ EncodeTiledFn get_encode_tiled();
 int make_tmap_f32(CUtensorMap* out, const float* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                   const uint32_t* box, bool atom32b = false, bool plain_f32 = false);
 
+// ---------------------------------------------------------------------------------------------- host: GEMM entry
+// Optional fused epilogue of the tcgen05 GEMM (Linear layers, linear.cu).  Everything defaults to "plain GEMM".
+struct Epilogue {
+  const float* bias = nullptr;   // [N] added to every row
+  int act = -1;                  // ngb_unary_op for C2 = act(acc + bias) and for the mask derivative; -1 = identity
+  float alpha = 0.f;             // LeakyReLU slope
+  float* C2 = nullptr;           // second output [M, N]
+  int64_t ldc2 = 0;
+  int store_c = 1;               // 0: only C2 is written (C may be null)
+  const float* mask_z = nullptr; // [M, N]: result is multiplied by act'(mask_z)
+  int64_t ldm = 0;
+  float* colsum = nullptr;       // [N]: column sums of the B operand (TN form only)
+  int colsum_accumulate = 0;
+};
+bool gemm_tc_eligible(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, int64_t ldc);
+int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B, int64_t ldb,
+            float* C, int64_t ldc, int accumulate, cudaStream_t st, const Epilogue* epi = nullptr);
+
 }  // namespace tc
 }  // namespace ngb

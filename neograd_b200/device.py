@@ -187,6 +187,7 @@ class DeviceArray:
   # ------------------------------------------------------------------ in-place kernels
   def fill(self, value):
     if self.size:
+      flush_readers_of(self)
       B.check(B.lib.ngb_fill(self.ptr, float(value), self.size, _st()))
     return self
 
@@ -197,12 +198,14 @@ class DeviceArray:
     if other.size != self.size:
       raise ValueError(f'could not assign array of shape {other.shape} to shape {self.shape}')
     if self.size and other.t.data_ptr() != self.t.data_ptr():
+      flush_readers_of(self)
       B.check(B.lib.ngb_copy(self.ptr, other.ptr, self.size, _st()))
     return self
 
   def add_(self, other, alpha=1.0):
     """self += alpha * other  (tensor.py:301 grad accumulation)."""
     if self.size:
+      flush_readers_of(self)
       B.check(B.lib.ngb_axpy(self.ptr, other.ptr, float(alpha), self.size, _st()))
     return self
 
@@ -341,26 +344,73 @@ class LazyArray(DeviceArray):
     return self._shape[0]
 
 
-# Deferred convolution outputs (tag 'conv') read their weights when they are finally produced: the optimizers flush the
-# ones somebody still holds before they touch the parameters (flush_lazy), so a late reader sees the forward-time values.
-_pending_convs = []
+# Deferred arrays read their producer's inputs when they are finally produced, not at forward time.  To keep that
+# invisible (the reference's results hold forward-time values) every deferred array is registered with the buffers it will
+# read: the optimizers flush all pending ones before they touch the parameters (flush_lazy), and every in-place write to a
+# DeviceArray first produces the pending arrays that read the written range (flush_readers_of).
+_pending = []          # [(weakref to the LazyArray, ((data_ptr, nbytes), ...))]
 
 
-def register_lazy(arr):
+def _extent(arr):
+  """(address, bytes) of a materialised DeviceArray; None for one that is itself still deferred (its own entry covers it)"""
+  if arr is None or (isinstance(arr, LazyArray) and arr.pending):
+    return None
+  t = arr.t
+  return (t.data_ptr(), t.numel() * 4)
+
+
+def register_lazy(arr, sources=()):
   import weakref
-  if len(_pending_convs) >= 256:     # forward-only loops never reach an optimizer: keep the list to the live ones
-    _pending_convs[:] = [r for r in _pending_convs if r() is not None and r().pending]
-  _pending_convs.append(weakref.ref(arr))
+  if len(_pending) >= 256:     # forward-only loops never reach an optimizer: keep the list to the live ones
+    _pending[:] = [e for e in _pending if e[0]() is not None and e[0]().pending]
+  _pending.append((weakref.ref(arr), tuple(x for x in (_extent(s) for s in sources) if x is not None)))
 
 
 def flush_lazy():
-  if not _pending_convs:
+  if not _pending:
     return
-  refs, _pending_convs[:] = list(_pending_convs), []
-  for r in refs:
+  entries, _pending[:] = list(_pending), []
+  for r, _ in entries:
     arr = r()
     if arr is not None and arr.pending:
       arr.t
+
+
+def flush_readers_of(dst):
+  """Produce the pending deferred arrays that will read any part of `dst`'s buffer (called before in-place writes)."""
+  if not _pending:
+    return
+  ext = _extent(dst)
+  if ext is None:
+    return
+  lo, hi = ext[0], ext[0] + ext[1]
+  hit = False
+  for r, srcs in _pending:
+    for (p, n) in srcs:
+      if p < hi and lo < p + n:
+        hit = True
+        arr = r()
+        if arr is not None and arr.pending:
+          arr.t
+        break
+  if hit:
+    _pending[:] = [e for e in _pending if e[0]() is not None and e[0]().pending]
+
+
+class ConstScalar(LazyArray):
+  """A 0-d array whose value the host knows (the `1.` that Tensor.backward() seeds, tensor.py:44): consumers that can use
+  the value as an immediate never make it exist on the device; anything else materialises it with one fill."""
+  __slots__ = ('value',)
+
+  def __init__(self, value):
+    value = float(value)
+    LazyArray.__init__(self, (), lambda: DeviceArray.full((), value), 'const', None)
+    self.value = value
+
+
+def const_value(arr):
+  """the host-known value of a ConstScalar, else None"""
+  return arr.value if isinstance(arr, ConstScalar) else None
 
 
 def opt_ptr(arr):
@@ -397,6 +447,7 @@ POOLED_CONV_GRADS = _os.environ.get('NGB_NO_POOLED') != '1'   # conv weight / bi
 POOLED_CONV_DGRAD = _os.environ.get('NGB_NO_POOLED_DGRAD') != '1'
 LAZY_FUSION = True   # ReLU -> MaxPool pairs run as fused kernels (set False to materialise every op's output eagerly)
 FUSED_CONV_POOL = _os.environ.get('NGB_NO_FUSED_CONV_POOL') != '1'   # first-layer conv -> ReLU -> MaxPool blocks in one kernel
+FUSED_LINEAR = _os.environ.get('NGB_NO_FUSED_LINEAR') != '1'   # Linear (+ activation / + SoftmaxCE) as one kernel per pass
 
 
 def unary(op, x, alpha=0.0):

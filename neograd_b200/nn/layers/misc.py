@@ -6,6 +6,7 @@ from ...autograd import dot
 from ...autograd.ops.operation import Operation
 from ...autograd.tensor import GradFn
 from ...autograd.ops.basics import _copy_into
+from ...autograd.ops import linear as _linear
 
 
 class Sequential(Container):
@@ -38,7 +39,9 @@ class Linear(Layer):
     self.bias = Param(np.zeros((1, num_out)), requires_grad=True)
 
   def forward(self, inputs):
-    return dot(inputs, self.weights) + self.bias
+    if _linear.fusable(inputs, self.weights, self.bias):
+      return _linear.linear(inputs, self.weights, self.bias)      # same arithmetic, one Operation (autograd/ops/linear.py)
+    return dot(inputs, self.weights) + self.bias                  # misc.py:63
 
   def __repr__(self):
     return f'Linear(num_in={self.num_in}, num_out={self.num_out})'

@@ -65,7 +65,22 @@ class SoftmaxCE(Operation, Loss):
     n = self.get_num_examples(outputs.shape)
     outer, L, inner = _split_axis(outputs.shape, self.axis)
     loss = D.DeviceArray.empty(())
-    B.check(B.lib.ngb_softmax_ce_fwd(outputs.data.ptr, targets.data.ptr, outer, L, inner, 1.0 / n, epsilon, loss.ptr, D._st()))
+    self._dz0 = None
+    z = outputs.data
+    if (D.LAZY_FUSION and D.FUSED_LINEAR and isinstance(z, D.LazyArray) and z.pending and z.tag == 'linear'
+        and len(outputs.shape) == 2 and inner == 1 and targets._data is not None
+        and B.lib.ngb_linear_softmax_ce_serves(outer, z.args.n_in, L) == 1):
+      # the logits are a Linear layer's output nobody has read yet (a classifier head): logits, loss and the loss gradient
+      # for an upstream gradient of 1 -- (softmax(z) - t) / n, loss.py:170 -- come out of ONE kernel
+      pend = z.args
+      zbuf = D.DeviceArray.empty(outputs.shape)
+      dz0 = D.DeviceArray.empty(outputs.shape)
+      B.check(B.lib.ngb_linear_softmax_ce(pend.x.ptr, pend.W.ptr, pend.b.ptr, targets.data.ptr, zbuf.ptr, loss.ptr, dz0.ptr,
+                                          pend.M, pend.n_in, pend.n_out, 1.0 / n, epsilon, D._st()))
+      z.t = zbuf.t
+      self._dz0 = dz0
+    else:
+      B.check(B.lib.ngb_softmax_ce_fwd(z.ptr, targets.data.ptr, outer, L, inner, 1.0 / n, epsilon, loss.ptr, D._st()))
     return self.get_result_tensor(loss, outputs, targets)
 
   def backward(self, outputs, targets):
@@ -73,12 +88,18 @@ class SoftmaxCE(Operation, Loss):
     n = self.get_num_examples(outputs.shape)
     outer, L, inner = _split_axis(outputs.shape, self.axis)
 
+    dz0 = getattr(self, '_dz0', None)
+
     def into(ug, dst, acc):
       if dst is None:
         dst, acc = D.DeviceArray.empty(z.shape), False
       B.check(B.lib.ngb_softmax_ce_bwd(z.ptr, t.ptr, ug.ptr, outer, L, inner, 1.0 / n, dst.ptr, int(acc), D._st()))
       return dst
-    outputs.set_grad_fn(GradFn(into))
+
+    def alias(ug):
+      # upstream gradient is the host-known 1. of loss.backward(): the gradient the forward kernel already wrote IS the result
+      return dz0 if (dz0 is not None and D.const_value(ug) == 1.0) else None
+    outputs.set_grad_fn(GradFn(into, alias))
     assert targets.requires_grad is False, 'Targets Tensor should have requires_grad=False'
 
   def __repr__(self): return f'SoftmaxCE(axis={self.axis})'

@@ -202,7 +202,7 @@ class Adam(Optimizer):
 
   def __init__(self, params, lr, beta1=0.9, beta2=0.999, epsilon=1e-8):
     super().__init__(params, lr)
-    self._t_dev = torch().zeros(1, device='cuda', dtype=torch().int32)
+    self._t_dev = torch().zeros(2, device='cuda', dtype=torch().int32)   # [steps taken, scratch counter of the update kernel]
     self.iter = 0
     self.beta1, self.beta2 = beta1, beta2
     self.epsilon = epsilon
@@ -216,12 +216,12 @@ class Adam(Optimizer):
     self.iter += 1
     gs = self._sync_grads()
     a = self.arena
-    tick = 1
     t_ptr = ctypes.c_void_p(self._t_dev.data_ptr())
-    for b, e in a.ranges():
+    ranges = a.ranges() or [[0, 0]]          # (nothing trainable: the step is still counted, optim.py:169)
+    for i, (b, e) in enumerate(ranges):
+      tick = 1 if i == len(ranges) - 1 else 2      # the last launch of the step records the new iteration count
       B.check(B.lib.ngb_adam_step_dev(_off(a.data, b), _off(a.grad_sum, b), _off(self._m, b), _off(self._v, b), e - b, self.lr,
                                       self.beta1, self.beta2, self.epsilon, t_ptr, tick, gs, _st()))
-      tick = 0
 
   def reset_iter(self):
     self.iter = 0

@@ -71,6 +71,53 @@ def gemm(a, b, ta=False, tb=False, engine=B.GEMM_AUTO, accumulate=None):
   return host(C)
 
 
+ACT = {None: -1, 'relu': B.RELU, 'leaky_relu': B.LEAKY_RELU, 'sigmoid': B.SIGMOID, 'tanh': B.TANH}
+
+
+def linear_fwd(x, w, b, act=None, alpha=0.0, want_z=True, want_a=True):
+  """(z, a) of ngb_linear_fwd; an output that is not requested comes back as None"""
+  M, K = x.shape
+  N = w.shape[1]
+  X, W, Bv = dev(x), dev(w), (dev(np.reshape(b, -1)) if b is not None else None)
+  z = torch.full((M, N), float('nan'), device='cuda') if want_z else None
+  a = torch.full((M, N), float('nan'), device='cuda') if want_a else None
+  call('ngb_linear_fwd', ptr(X), ptr(W), ptr(Bv), ptr(z), ptr(a), ACT[act], float(alpha), M, K, N, st())
+  return (host(z) if want_z else None), (host(a) if want_a else None)
+
+
+def linear_dgrad(ug, w, zprev=None, act=None, alpha=0.0, into=None):
+  M, N = ug.shape
+  K = w.shape[0]
+  U, W, Z = dev(ug), dev(w), (dev(zprev) if zprev is not None else None)
+  dx = torch.full((M, K), float('nan'), device='cuda') if into is None else dev(into)
+  call('ngb_linear_dgrad', ptr(U), ptr(W), ptr(Z), ptr(dx), ACT[act], float(alpha), M, K, N, 0 if into is None else 1, st())
+  return host(dx)
+
+
+def linear_wgrad(x, ug, want_db=True, into_w=None, into_b=None):
+  M, K = x.shape
+  N = ug.shape[1]
+  X, U = dev(x), dev(ug)
+  dw = torch.full((K, N), float('nan'), device='cuda') if into_w is None else dev(into_w)
+  db = None
+  if want_db:
+    db = torch.full((N,), float('nan'), device='cuda') if into_b is None else dev(np.reshape(into_b, -1))
+  call('ngb_linear_wgrad', ptr(X), ptr(U), ptr(dw), ptr(db), M, K, N, 0 if into_w is None else 1, 0 if into_b is None else 1, st())
+  return host(dw), (host(db) if want_db else None)
+
+
+def linear_softmax_ce(x, w, b, t, eps=1e-9):
+  """(z, loss, dz) of ngb_linear_softmax_ce"""
+  M, K = x.shape
+  N = w.shape[1]
+  X, W, Bv, T = dev(x), dev(w), dev(np.reshape(b, -1)), dev(t)
+  z = torch.full((M, N), float('nan'), device='cuda')
+  dz = torch.full((M, N), float('nan'), device='cuda')
+  loss = torch.full((1,), float('nan'), device='cuda')
+  call('ngb_linear_softmax_ce', ptr(X), ptr(W), ptr(Bv), ptr(T), ptr(z), ptr(loss), ptr(dz), M, K, N, 1.0 / M, eps, st())
+  return host(z), float(host(loss)[0]), host(dz)
+
+
 def conv_fprop(x, w, b, pad, stride):
   N, C, H, W = x.shape
   O, _, KH, KW = w.shape

@@ -7,6 +7,8 @@ Tolerances (dist = ||a-b||/(||a||+||b||), the reference's own metric, neograd/au
   * tcgen05 TF32 kernels (Dot / conv implicit GEMM): 5e-4 (TF32 operand rounding, fp32 accumulate; SURVEY A.8);
   * MaxPool values, argmax indices and pool backward: bit-exact.
 """
+import ctypes
+
 import numpy as np
 import pytest
 
@@ -341,6 +343,125 @@ def test_conv_igemm_exact_on_small_integers(U):
                         (dw0 + ops.conv3d_wgrad(ug, x, w.shape, 1, 1)).astype(np.float32))
 
 
+# ---------------------------------------------------------------------------------------------- Linear (fused) entry points
+LINEAR_CASES = [   # batch, n_in, n_out : which engine serves it in 'tf32' mode
+  (4096, 256, 120),    # LeNet FC1: tcgen05, ragged N tile (120 = 3 x 32 + 24), TMA-store epilogue
+  (4096, 120, 84),     # LeNet FC2: tcgen05, K = 120 (partial k-block), N = 84
+  (4096, 84, 10),      # LeNet FC3: small-N kernels
+  (8192, 784, 512),    # GAN: tcgen05 BN = 256
+  (1024, 256, 784),    # GAN last generator layer
+  (2048, 256, 1),      # GAN discriminator head: small-N, one output
+  (200, 36, 10),       # digits CNN head
+  (750, 2, 100),       # README MLP first layer: SIMT (K = 2)
+  (333, 50, 25),       # notebook-scale GAN layer: SIMT (unaligned leading dimensions)
+  (65, 33, 32),        # small-N with the widest tile
+]
+
+
+def _act_ref(name, z, alpha):
+  return z if name is None else ops.unary_fwd(name, z, alpha) if name == 'leaky_relu' else ops.unary_fwd(name, z)
+
+
+def _act_grad_ref(name, z, alpha):
+  one = np.ones_like(z)
+  return one if name is None else (ops.unary_bwd(name, z, one, alpha) if name == 'leaky_relu' else ops.unary_bwd(name, z, one))
+
+
+@pytest.mark.parametrize('precision', ['tf32', 'fp32'])
+@pytest.mark.parametrize('M,K,N', LINEAR_CASES)
+def test_linear_fused_vs_oracle(U, M, K, N, precision):
+  """ngb_linear_fwd / _dgrad / _wgrad against the float64 oracle of the two-node form (misc.py:63: dot + broadcast add;
+  basics.py:206-207; utils.py:75), with every activation the epilogues implement."""
+  rng = np.random.default_rng(M + 3 * K + 7 * N)
+  x, w = f32(rng.standard_normal((M, K))), f32(rng.standard_normal((K, N)) / np.sqrt(K))
+  b, ug = f32(rng.standard_normal((1, N))), f32(rng.standard_normal((M, N)))
+  zprev = f32(rng.standard_normal((M, K)))
+  zprev[0, : min(3, K)] = 0.0                      # exact zeros: relu' = 1 at 0 (activations.py:31)
+  tc = precision == 'tf32' and U.lib.ngb_gemm_query(0, 0, M, N, K, K, N, N) == 2 and N > 32
+  tol = TOLTF32 if tc else TOL32
+  zr = ops.dot_fwd(x, w) + b
+  with U.precision(precision):
+    for act, alpha in ((None, 0.0), ('relu', 0.0), ('leaky_relu', 0.01), ('sigmoid', 0.0), ('tanh', 0.0)):
+      z, a = U.linear_fwd(x, w, b, act, alpha)
+      close(z, zr, tol)
+      close(a, _act_ref(act, zr, alpha), tol)
+      dx = U.linear_dgrad(ug, w, zprev, act, alpha)
+      close(dx, ops.dot_dgrad(ug, w) * _act_grad_ref(act, zprev, alpha), tol)
+    z_only, none = U.linear_fwd(x, w, b, 'relu', want_a=False)
+    assert none is None
+    close(z_only, zr, tol)
+    none, a_only = U.linear_fwd(x, w, None, 'relu', want_z=False)
+    assert none is None
+    close(a_only, np.maximum(ops.dot_fwd(x, w), 0), tol)
+    close(U.linear_dgrad(ug, w), ops.dot_dgrad(ug, w), tol)
+    dx0 = f32(rng.standard_normal((M, K)))
+    close(U.linear_dgrad(ug, w, zprev, 'relu', into=dx0), dx0 + ops.dot_dgrad(ug, w) * (zprev >= 0), tol)
+    dw, db = U.linear_wgrad(x, ug)
+    close(dw, ops.dot_wgrad(x, ug), tol)
+    close(db, ug.sum(axis=0), tol)
+    dw2, none = U.linear_wgrad(x, ug, want_db=False)
+    assert none is None
+    close(dw2, ops.dot_wgrad(x, ug), tol)
+    dw0, db0 = f32(rng.standard_normal((K, N))), f32(rng.standard_normal(N))
+    dw3, db3 = U.linear_wgrad(x, ug, into_w=dw0, into_b=db0)
+    close(dw3, dw0 + ops.dot_wgrad(x, ug), tol)
+    close(db3, db0 + ug.sum(axis=0), tol)
+
+
+@pytest.mark.parametrize('M,K,N', [(4096, 256, 120), (512, 128, 256), (300, 64, 96)])
+def test_linear_fused_matches_unfused_kernels_bitwise(U, M, K, N):
+  """Same accumulators, same operations in the same order: the fused forward equals ngb_gemm followed by the bias add and
+  the activation kernel BIT FOR BIT; the masked data gradient equals ngb_gemm followed by the activation's backward kernel;
+  the weight gradient equals ngb_gemm's."""
+  rng = np.random.default_rng(M + K + N)
+  x, w = f32(rng.standard_normal((M, K))), f32(rng.standard_normal((K, N)) / np.sqrt(K))
+  b, ug = f32(rng.standard_normal((1, N))), f32(rng.standard_normal((M, N)))
+  zprev = f32(rng.standard_normal((M, K)))
+  z, a = U.linear_fwd(x, w, b, 'relu')
+  z2 = U.binary_fwd(BOPS['add'], U.gemm(x, w), b)
+  assert np.array_equal(z, z2)
+  assert np.array_equal(a, U.unary_fwd(UOPS['relu'], z2))
+  dx = U.linear_dgrad(ug, w, zprev, 'leaky_relu', 0.01)
+  assert np.array_equal(dx, U.unary_bwd(UOPS['leaky_relu'], zprev, U.gemm(ug, w, tb=True), 0.01))
+  dw, _ = U.linear_wgrad(x, ug)
+  assert np.array_equal(dw, U.gemm(x, ug, ta=True))
+
+
+def test_linear_tcgen05_exact_on_small_integers(U):
+  """TF32-representable integers: products and sums are exact, so the tensor-core Linear kernels -- including the
+  ones-tile MMA that yields the bias gradient and its split-K partials -- must equal the oracle exactly."""
+  rng = np.random.default_rng(5)
+  for M, K, N in ((4096, 256, 128), (8192, 784, 512), (640, 120, 84)):
+    x = rng.integers(-3, 4, (M, K)).astype(np.float64)
+    w = rng.integers(-2, 3, (K, N)).astype(np.float64)
+    b = rng.integers(-5, 6, (1, N)).astype(np.float64)
+    ug = rng.integers(-2, 3, (M, N)).astype(np.float64)
+    z, a = U.linear_fwd(x, w, b, 'relu')
+    zr = x @ w + b
+    assert np.array_equal(z, zr.astype(np.float32)) and np.array_equal(a, np.maximum(zr, 0).astype(np.float32))
+    assert np.array_equal(U.linear_dgrad(ug, w, zr @ w.T, 'relu'), ((ug @ w.T) * ((zr @ w.T) >= 0)).astype(np.float32))
+    dw, db = U.linear_wgrad(x, ug)
+    assert np.array_equal(dw, (x.T @ ug).astype(np.float32))
+    assert np.array_equal(db, ug.sum(axis=0).astype(np.float32))
+
+
+@pytest.mark.parametrize('M,K,N', [(4096, 84, 10), (200, 36, 10), (77, 16, 3), (512, 120, 32)])
+def test_linear_softmax_ce_head(U, M, K, N):
+  """Classifier head in one kernel: logits, SoftmaxCE loss (loss.py:153-157) and its gradient for an upstream 1 (loss.py:170)."""
+  rng = np.random.default_rng(M + N)
+  x, w, b = f32(rng.standard_normal((M, K))), f32(rng.standard_normal((K, N)) / np.sqrt(K)), f32(rng.standard_normal((1, N)))
+  t = np.eye(N)[rng.integers(0, N, M)]
+  z, loss, dz = U.linear_softmax_ce(x, w, b, t)
+  zr = ops.dot_fwd(x, w) + b
+  close(z, zr, TOL32)
+  lr = ops.softmax_ce_fwd(zr, t, 1)
+  assert abs(loss - lr) <= 2e-6 * abs(lr), (loss, lr)
+  close(dz, ops.softmax_ce_bwd(zr, t, 1), 5e-6)
+  # run to run bit-identical (fixed-order loss reduction), and the blocks-done counter is left at zero
+  z2, loss2, dz2 = U.linear_softmax_ce(x, w, b, t)
+  assert loss2 == loss and np.array_equal(dz2, dz)
+
+
 def test_no_pipeline_timeouts(U):
   """Runs last in this file's conv / gemm group: no tcgen05 warp gave up on a barrier during the tests above."""
   U.call('ngb_debug_check_pipelines')
@@ -615,11 +736,17 @@ def test_adam_large_flat_arena(U):
   close(U.host(v), rv, TOL32)
   # graph-friendly variant: iteration count in device memory, incremented by the launch itself
   p2, m2, v2 = U.dev(p0), torch.zeros_like(p), torch.zeros_like(p)
-  t_dev = torch.zeros(1, device='cuda', dtype=torch.int32)
+  t_dev = torch.zeros(2, device='cuda', dtype=torch.int32)     # [steps taken, scratch counter]
+  half = (n // 2) & ~3
   for _ in range(3):
-    U.call('ngb_adam_step_dev', U.ptr(p2), U.ptr(G), U.ptr(m2), U.ptr(v2), n, 5e-3, 0.9, 0.999, 1e-8, U.ptr(t_dev), 1, 1.0, U.st())
+    # one step = two launches over two ranges of the arena (frozen parameters split it): tick 2 (same step number, not
+    # recorded) then tick 1 (recorded by the launch's last block)
+    U.call('ngb_adam_step_dev', U.ptr(p2), U.ptr(G), U.ptr(m2), U.ptr(v2), half, 5e-3, 0.9, 0.999, 1e-8, U.ptr(t_dev), 2, 1.0, U.st())
+    off = ctypes.c_void_p
+    U.call('ngb_adam_step_dev', off(p2.data_ptr() + 4 * half), off(G.data_ptr() + 4 * half), off(m2.data_ptr() + 4 * half),
+           off(v2.data_ptr() + 4 * half), n - half, 5e-3, 0.9, 0.999, 1e-8, U.ptr(t_dev), 1, 1.0, U.st())
   ref, rm, rv = p0, 0.0, 0.0
   for t in (1, 2, 3):
     ref, rm, rv = ops.adam_step(ref, g0, rm, rv, t, 5e-3)
-  assert int(t_dev.item()) == 3
+  assert t_dev.tolist() == [3, 0]
   close(U.host(p2), ref, TOL32)

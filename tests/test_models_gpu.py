@@ -404,6 +404,83 @@ def test_backward_lanes_change_nothing(ng, captured):
     assert np.array_equal(a, b)
 
 
+@pytest.mark.parametrize('precision', ['fp32', 'tf32'])
+def test_fused_linear_changes_nothing(ng, precision):
+  """Linear as one Operation with fused kernels (bias / activation in the GEMM epilogue, activation mask in the data-gradient
+  epilogue, bias gradient from the weight-gradient pass, Linear + SoftmaxCE head in one kernel, upstream 1. as an immediate)
+  against the reference's two-node form `dot(x, W) + b` with separate kernels (D.FUSED_LINEAR = False): losses and
+  first-step gradients of LeNet-B and of the notebook-scale GAN.  fp32 mode: same products, fp32 re-association only; tf32
+  mode: the fused bias gradient sums TF32-rounded upstream gradients (it rides on the tensor-core pass)."""
+  from neograd_b200 import device as D
+  from neograd_b200.configs import GAN, lenet_synthetic, set_params, gan_iteration
+  tol = 2e-6 if precision == 'fp32' else 1e-3
+  prev_mode = ng.set_precision(precision)
+  try:
+    res = []
+    for fused in (False, True):
+      prev, D.FUSED_LINEAR = D.FUSED_LINEAR, fused
+      try:
+        np.random.seed(0)
+        model, Xh, Yh = lenet_synthetic('b', 512)
+        loss = ng.nn.loss.SoftmaxCE(axis=1)(model(ng.tensor(Xh)), ng.tensor(Yh))
+        loss.backward()
+        out = [float(loss.data)] + [p.grad.numpy() for p in model.parameters()]
+        # GAN at notebook scale: LeakyReLU / Sigmoid epilogues, the 25 -> 1 head, frozen halves, BCE on top
+        rng = np.random.default_rng(3)
+        gan = GAN(64, 50, 25)
+        set_params(gan, [0.05 * rng.standard_normal(p.shape) for p in gan.parameters()])
+        og, od = ng.nn.optim.Adam(gan.parameters(), 1e-3), ng.nn.optim.Adam(gan.parameters(), 1e-3)
+        T = lambda a: ng.tensor(a)
+        lg, ld = gan_iteration(gan, og, od, ng.nn.loss.BCE(), T(rng.standard_normal((200, 64))), T(rng.standard_normal((200, 64))),
+                               T(rng.standard_normal((200, 64))), T(np.ones((200, 1))), T(np.zeros((200, 1))))
+        out += [float(lg.data), float(ld.data)] + [p.data.numpy() for p in gan.parameters()]
+        res.append(out)
+      finally:
+        D.FUSED_LINEAR = prev
+    for i, (a, b) in enumerate(zip(res[0], res[1])):
+      if isinstance(a, float):
+        assert abs(a - b) <= max(tol, 2e-6) * abs(a), (i, a, b)
+      else:
+        assert dist(a, b) < tol, (i, dist(a, b))
+  finally:
+    ng.set_precision(prev_mode)
+
+
+def test_forward_only_and_late_reads_of_fused_linear(ng):
+  """Deferred Linear outputs are ordinary arrays for everything else: reading the pre-activation after the activation,
+  eval-mode forward (no pre-activation is written), and a parameter update between forward and a late read all give the
+  forward-time values."""
+  from neograd_b200 import device as D
+  rng = np.random.default_rng(0)
+  np.random.seed(1)
+  lin, act = ng.nn.Linear(64, 48), ng.nn.LeakyReLU()
+  x = ng.tensor(rng.standard_normal((128, 64)))
+  want_z = x.data.numpy() @ lin.weights.data.numpy() + lin.bias.data.numpy()
+  want_a = np.where(want_z >= 0, want_z, 0.01 * want_z)
+  z = lin(x)
+  a = act(z)
+  assert isinstance(z.data, D.LazyArray) and z.data.pending and a.data.pending
+  assert dist(a.data.numpy(), want_a) < 1e-3 and not z.data.pending       # one kernel produced both
+  assert dist(z.data.numpy(), want_z) < 1e-3
+  ng._NG_GRAPH.reset_graph()
+  with ng.no_track():
+    z2 = lin(x)
+    a2 = act(z2)
+    assert dist(a2.data.numpy(), want_a) < 1e-3
+    assert z2.data.pending                                                # forward-only: the pre-activation was not written
+    assert dist(z2.data.numpy(), want_z) < 1e-3                           # ... but is still there for whoever asks
+  opt = ng.nn.optim.GD([lin.weights, lin.bias], 0.1)                      # parameters now live in the optimizer's arena
+  z3 = lin(x)
+  lin.weights.data = np.zeros((64, 48))                                   # in-place write to a source of the deferred array
+  assert dist(z3.data.numpy(), want_z) < 1e-3
+  assert np.all(lin.weights.data.numpy() == 0)
+  z4 = lin(x)
+  opt.zero_grad()
+  opt.step()                                                              # optimizers flush pending arrays before updating
+  assert dist(z4.data.numpy(), lin.bias.data.numpy() + np.zeros((128, 1))) < 1e-3
+  ng._NG_GRAPH.reset_graph()
+
+
 def test_lazy_relu_pool_fusion_changes_nothing(ng):
   """ReLU -> MaxPool pairs run as fused kernels (the ReLU output and the pool's input gradient are never written) and the
   first convolution's weight / bias gradients are taken from the pooled gradient; products and summation orders are
