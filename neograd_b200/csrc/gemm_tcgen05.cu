@@ -447,8 +447,15 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
     while (BN > 64 && tm * ceil_div<int64_t>(N, BN) < (3 * kNumSMs) / 4 && ceil_div<int64_t>(N, BN / 2) > ceil_div<int64_t>(N, BN))
       BN /= 2;
   } else {
-    // with splitting available only drop to a narrower tile when the wide one wastes a large part of its columns
-    while (BN > 64 && ceil_div<int64_t>(N, BN) * BN >= N + BN / 2) BN /= 2;
+    // with splitting available the grid can always be filled: take the width with the fewest shared-memory bytes per
+    // useful MAC, padded_N * (128 + BN) / BN (a narrower tile only wins when the wide one is mostly padding)
+    int best = BN;
+    int64_t best_cost = INT64_MAX;
+    for (int c = BN; c >= 64; c /= 2) {
+      const int64_t cost = ceil_div<int64_t>(N, c) * (128 + c);     // = padded_N * (128 + c) / c
+      if (cost < best_cost) { best_cost = cost; best = c; }
+    }
+    BN = best;
   }
   {
     const int f = env_int("NGB_GEMM_BN", 0);          // tuning / experiments
