@@ -7,6 +7,8 @@ from .workload_defs import (model_classes, set_params, synthetic_params, lenet_d
                             gan_iteration)
 
 _C = model_classes(nn)
+for _cls in _C.values():       # module-level citizens of THIS module, so pickle / dill store them by reference (ng.save(model))
+  _cls.__module__, _cls.__qualname__ = __name__, _cls.__name__
 MLPCircles, DigitsCNN, LeNetA, LeNetB, GAN = _C['MLPCircles'], _C['DigitsCNN'], _C['LeNetA'], _C['LeNetB'], _C['GAN']
 
 

@@ -64,12 +64,15 @@ __device__ __forceinline__ float unary_grad(int op, float alpha, float x, float 
     case NGB_RELU: return x >= 0.f ? ug : 0.f;              // activations.py:31 -- grad is 1 at x == 0
     case NGB_LEAKY_RELU: return x >= 0.f ? ug : alpha * ug;  // activations.py:216
     case NGB_SIGMOID: {
-      float s = 1.f / (1.f + expf(-x));
-      return (s * (1.f - s)) * ug;
+      // s(1 - s) (activations.py:62-63) written as e^-|x| / (1 + e^-|x|)^2: the same number, but `1 - s` cancels in fp32 once
+      // the unit saturates (relative error 6e-8 / (1 - s)), which the float64 reference does not suffer from
+      const float t = expf(-fabsf(x)), d = 1.f + t;
+      return (t / (d * d)) * ug;
     }
     default: {
-      float t = tanhf(x);
-      return (1.f - t * t) * ug;
+      // 1 - tanh^2 (activations.py:94-95) = 4 e^-2|x| / (1 + e^-2|x|)^2, for the same reason
+      const float t = expf(-2.f * fabsf(x)), d = 1.f + t;
+      return (4.f * t / (d * d)) * ug;
     }
   }
 }

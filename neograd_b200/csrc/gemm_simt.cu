@@ -19,8 +19,8 @@ __device__ __forceinline__ float simt_act(int act, float alpha, float v) {
 __device__ __forceinline__ float simt_act_grad(int act, float alpha, float z) {
   if (act == NGB_RELU) return z >= 0.f ? 1.f : 0.f;
   if (act == NGB_LEAKY_RELU) return z >= 0.f ? 1.f : alpha;
-  if (act == NGB_SIGMOID) { const float s = 1.f / (1.f + expf(-z)); return s * (1.f - s); }
-  if (act == NGB_TANH) { const float t = tanhf(z); return 1.f - t * t; }
+  if (act == NGB_SIGMOID) { const float t = expf(-fabsf(z)), d = 1.f + t; return t / (d * d); }            // = s(1-s), no cancellation
+  if (act == NGB_TANH) { const float t = expf(-2.f * fabsf(z)), d = 1.f + t; return 4.f * t / (d * d); }  // = 1 - tanh^2
   return 1.f;
 }
 

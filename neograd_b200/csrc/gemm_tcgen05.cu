@@ -107,21 +107,52 @@ struct GemmArgs {
   int colsum_accumulate;
 };
 
-// activation ids of the fused epilogue (= ngb_unary_op of include/ngb200.h; -1 = none)
-__device__ __forceinline__ float epi_act(int act, float alpha, float v) {
-  if (act == NGB_RELU) return fmaxf(v, 0.f);
-  if (act == NGB_LEAKY_RELU) return v >= 0.f ? v : alpha * v;
-  if (act == NGB_SIGMOID) return 1.f / (1.f + __expf(-v));
-  if (act == NGB_TANH) return tanhf(v);
-  return v;
+// Fused-epilogue activations on a 32-column chunk held in registers.  The activation id is uniform over the launch, so it
+// is switched on OUTSIDE the element loop: only the selected formula is executed (an epilogue warp is alone on its scheduler,
+// nothing hides the latency of evaluating every activation and selecting).  Ids = ngb_unary_op; anything else = identity.
+__device__ __forceinline__ void epi_act32(int act, float alpha, float (&v)[32]) {
+  switch (act) {
+    case NGB_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.f);
+      break;
+    case NGB_LEAKY_RELU:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] >= 0.f ? v[j] : alpha * v[j];
+      break;
+    case NGB_SIGMOID:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+      break;
+    case NGB_TANH:
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = tanhf(v[j]);
+      break;
+    default: break;
+  }
 }
-// d act(z) / dz from the pre-activation z (the reference's masks: relu / leaky use z >= 0)
-__device__ __forceinline__ float epi_act_grad(int act, float alpha, float z) {
-  if (act == NGB_RELU) return z >= 0.f ? 1.f : 0.f;
-  if (act == NGB_LEAKY_RELU) return z >= 0.f ? 1.f : alpha;
-  if (act == NGB_SIGMOID) { const float s = 1.f / (1.f + __expf(-z)); return s * (1.f - s); }
-  if (act == NGB_TANH) { const float t = tanhf(z); return 1.f - t * t; }
-  return 1.f;
+// v[j] *= d act(z[j]) / dz from the pre-activation z (the reference's masks: relu / leaky use z >= 0, activations.py:31, 216)
+__device__ __forceinline__ void epi_mask4(int act, float alpha, float* v, const float4& z) {
+  const float zz[4] = {z.x, z.y, z.z, z.w};
+  switch (act) {
+    case NGB_RELU:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = zz[i] >= 0.f ? v[i] : 0.f;
+      break;
+    case NGB_LEAKY_RELU:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) v[i] = zz[i] >= 0.f ? v[i] : alpha * v[i];
+      break;
+    case NGB_SIGMOID:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float t = __expf(-fabsf(zz[i])), d = 1.f + t; v[i] *= t / (d * d); }   // = s(1-s), no cancellation
+      break;
+    case NGB_TANH:
+#pragma unroll
+      for (int i = 0; i < 4; ++i) { const float t = __expf(-2.f * fabsf(zz[i])), d = 1.f + t; v[i] *= 4.f * t / (d * d); }
+      break;
+    default: break;
+  }
 }
 
 // A_MN / B_MN: operand is MN-major in global memory (1) or K-major (0).
@@ -302,21 +333,20 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] += (nbase + j < g.N) ? __ldg(g.bias + nbase + j) : 0.f;
         }
-        if (g.mask_z && row < g.M) {
+        // act'(z_prev) mask: on the TMA-store path it is applied to the staged tile with COALESCED loads of z_prev (below);
+        // a thread reading the 128 bytes of its own row here costs a 32-line gather per load instruction
+        const bool mask_in_smem = g.mask_z && !g.C2 && g.tma_store && (g.ldm % 4 == 0) && nbase + 32 <= g.N &&
+                                  ((reinterpret_cast<uintptr_t>(g.mask_z) & 15) == 0);
+        if (g.mask_z && !mask_in_smem && row < g.M) {
           const float* zr = g.mask_z + (int64_t)row * g.ldm + nbase;
-          if (nbase + 32 <= g.N && (g.ldm % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.mask_z) & 15) == 0)) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              const float4 z4 = *reinterpret_cast<const float4*>(zr + j);
-              v[j] *= epi_act_grad(g.act, g.alpha, z4.x);
-              v[j + 1] *= epi_act_grad(g.act, g.alpha, z4.y);
-              v[j + 2] *= epi_act_grad(g.act, g.alpha, z4.z);
-              v[j + 3] *= epi_act_grad(g.act, g.alpha, z4.w);
-            }
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nbase + j < g.N) v[j] *= epi_act_grad(g.act, g.alpha, zr[j]);
+          for (int j = 0; j < 32; j += 4) {
+            float4 z4;
+            z4.x = nbase + j < g.N ? zr[j] : 0.f;
+            z4.y = nbase + j + 1 < g.N ? zr[j + 1] : 0.f;
+            z4.z = nbase + j + 2 < g.N ? zr[j + 2] : 0.f;
+            z4.w = nbase + j + 3 < g.N ? zr[j + 3] : 0.f;
+            epi_mask4(g.act, g.alpha, v + j, z4);
           }
         }
         // ---- up to two outputs: C (the values themselves) and C2 = act(values)
@@ -325,8 +355,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           if (which == 0 && !g.store_c) continue;
           if (which == 1) {
             if (!g.C2) break;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = epi_act(g.act, g.alpha, v[j]);
+            epi_act32(g.act, g.alpha, v);
           }
           if (g.tma_store) {
             // registers -> smem tile [128 rows][32 cols] in the 128B-swizzle the store tensor map expects -> one TMA store
@@ -339,6 +368,27 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               *reinterpret_cast<float4*>(rp + ((j ^ (lrow & 7)) << 4)) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+            if (mask_in_smem && which == 0) {
+              // second pass over the staged tile, thread <-> (row, 16-byte column group) so that a warp reads four whole
+              // 128-byte lines of z_prev per instruction
+              asm volatile("bar.sync 1, 128;" ::: "memory");
+              float4 z4[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int idx = i * 128 + et, r = idx >> 3, c16 = idx & 7;
+                z4[i] = (m0 + r < g.M) ? *reinterpret_cast<const float4*>(g.mask_z + (int64_t)(m0 + r) * g.ldm + nbase + c16 * 4)
+                                       : make_float4(0.f, 0.f, 0.f, 0.f);
+              }
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int idx = i * 128 + et, r = idx >> 3, c16 = idx & 7;
+                float4* sp = reinterpret_cast<float4*>(tile_s + r * 128 + ((c16 ^ (r & 7)) << 4));
+                float4 t4 = *sp;
+                float tv[4] = {t4.x, t4.y, t4.z, t4.w};
+                epi_mask4(g.act, g.alpha, tv, z4[i]);
+                *sp = make_float4(tv[0], tv[1], tv[2], tv[3]);
+              }
+            }
             fence_proxy_async();
             asm volatile("bar.sync 1, 128;" ::: "memory");
             if (et == 0) {
@@ -434,30 +484,30 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   const bool fused = e.bias || e.mask_z || e.C2;     // needs the complete sums in the epilogue: no split-K
   if (colsum && !(a_mn && b_mn)) return fail(NGB_ERR_UNSUPPORTED, "tcgen05 GEMM: column sums only in the TN (weight-gradient) form");
 
-  // Tile width and K-splits.  The kernel is bound by shared-memory fill (each k-block brings (128 + BN) x 128 B for
-  // 128 x BN x 32 MACs), so bytes per MAC fall with BN: prefer the widest tile, and when that leaves the grid short of
-  // CTAs cover the SMs with K-splits (deterministic second pass) rather than with narrower tiles.  A narrower tile is taken
-  // only while it gives more whole tiles without splitting (short K) -- see profiles/r02_gemm_tiles.md for the sweep.
+  // Tile width and K-splits from a cost model fitted to a sweep on B200 (profiles/r02_gemm_tiles.md).  At these sizes the
+  // kernel is bound by the shared-memory fill: one k-block brings (128 + BN) x 128 B through TMA at ~75 GB/s per SM (the
+  // chip-wide L2 -> SM cap of ~6300 B/clk), a work item costs ~2.5 us of pipeline fill + epilogue on top, a CTA runs
+  // ceil(items / 148) items in a row, and K-splits pay a second pass over (splits + 1) x M x N floats at ~3 TB/s.
   const int64_t tm = ceil_div<int64_t>(M, BLOCK_M);
   const int k_blocks = (int)ceil_div<int64_t>(K, BLOCK_K);
-  int BN = N <= 64 ? 64 : (N <= 128 ? 128 : 256);
-  if (colsum && BN > 128) BN = 128;                   // two accumulators per stage: 4 x BN TMEM columns <= 512
-  const bool can_split = !fused && k_blocks >= 16;
-  if (!can_split) {
-    while (BN > 64 && tm * ceil_div<int64_t>(N, BN) < (3 * kNumSMs) / 4 && ceil_div<int64_t>(N, BN / 2) > ceil_div<int64_t>(N, BN))
-      BN /= 2;
-  } else {
-    // with splitting available the grid can always be filled: take the width with the fewest shared-memory bytes per
-    // useful MAC, padded_N * (128 + BN) / BN (a narrower tile only wins when the wide one is mostly padding)
-    int best = BN;
-    int64_t best_cost = INT64_MAX;
-    for (int c = BN; c >= 64; c /= 2) {
-      const int64_t cost = ceil_div<int64_t>(N, c) * (128 + c);     // = padded_N * (128 + c) / c
-      if (cost < best_cost) { best_cost = cost; best = c; }
-    }
-    BN = best;
-  }
+  const bool can_split = !fused && k_blocks >= 8;
+  int BN = 64, best_splits = 1;
   {
+    double best = 1e30;
+    for (int c = 64; c <= 256; c *= 2) {
+      if (colsum && c > 128) break;                     // two accumulators per stage: 4 x BN TMEM columns <= 512
+      if (c > 64 && c / 2 >= N) break;                  // (a tile more than twice as wide as the problem)
+      const int64_t tiles_c = tm * ceil_div<int64_t>(N, c);
+      const int max_s = can_split ? (k_blocks / 2 < 64 ? k_blocks / 2 : 64) : 1;
+      for (int sp = 1; sp <= max_s; ++sp) {
+        const int kb = (int)ceil_div<int64_t>(k_blocks, sp);
+        const int sp_eff = (int)ceil_div<int64_t>(k_blocks, kb);
+        const double rounds = (double)ceil_div<int64_t>(tiles_c * sp_eff, kNumSMs);
+        double t = rounds * (2.5 + kb * (128.0 + c) * 128.0 / 75e3);
+        if (sp_eff > 1) t += 2.5 + (sp_eff + 1.0) * (double)M * (double)N * 4.0 / 3.0e6;
+        if (t < best) { best = t; BN = c; best_splits = sp_eff; }
+      }
+    }
     const int f = env_int("NGB_GEMM_BN", 0);          // tuning / experiments
     if (f == 64 || f == 128 || (f == 256 && !colsum)) BN = f;
   }
@@ -501,13 +551,10 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   g.tiles_m = (int)tm;
   g.tiles_n = (int)ceil_div<int64_t>(N, BN);
   const int tiles = g.tiles_m * g.tiles_n;
-  int splits = 1;
-  if (can_split && tiles < (3 * kNumSMs) / 4) {
-    splits = ceil_div(kNumSMs, tiles);
-    // every split should still stream a few k-blocks: below ~4 the pipeline fill / drain and the partials dominate
-    if (splits > g.k_blocks / 4) splits = g.k_blocks / 4;
+  int splits = can_split ? best_splits : 1;
+  {
     const int f = env_int("NGB_GEMM_SPLITS", 0);
-    if (f > 0) splits = f < g.k_blocks ? f : g.k_blocks;
+    if (f > 0 && can_split) splits = f < g.k_blocks ? f : g.k_blocks;
     if (splits > 1) {
       if (ensure_init() != NGB_OK) return NGB_ERR_CUDA;
       const int64_t cap = scratch_bytes() / ((M * N + N) * (int64_t)sizeof(float));

@@ -1,6 +1,11 @@
 """Checkpoint (reference: neograd/nn/checkpoint.py): sessions + checkpoints.json + one params file per checkpoint.
 Pure file bookkeeping; the parameter files are written by `Model.save` (device -> host float64, the reference's
-nested-dict format), so checkpoints are interchangeable with the reference's."""
+nested-dict format), so checkpoints are interchangeable with the reference's.
+
+New: `Checkpoint(model, dirpath, optimizer=optim)` also writes the optimizer's state
+(`Optimizer.state_dict()`: hyper-parameters, iteration count, per-parameter moments) next to every parameter file as
+`<hash>.optim`, and `load()` restores it, so a resumed run continues the exact Adam trajectory.  Without the keyword the
+class behaves -- and its files look -- exactly like the reference's."""
 import datetime as dt
 import json
 import os
@@ -9,7 +14,8 @@ from hashlib import sha256
 
 
 class Checkpoint:
-  def __init__(self, model, dirpath, hash_length=16):
+  def __init__(self, model, dirpath, hash_length=16, optimizer=None):
+    self.optimizer = optimizer
     self.session = None
     self.dirpath = None
     assert hash_length > 0 and hash_length <= 64, 'Hash length must be between 1 and 64'
@@ -60,6 +66,10 @@ class Checkpoint:
     with open(self._json_path(), 'w') as fp:
       json.dump(existing, fp, indent=4)
     self.model.save(f'{self.dirpath}/{self.session}/{params_fname_hash}.hkl')
+    if self.optimizer is not None:
+      from .model import _pickler
+      with open(f'{self.dirpath}/{self.session}/{params_fname_hash}.optim', 'wb') as fp:
+        _pickler.dump(self.optimizer.state_dict(), fp)
 
   def load(self, params_fname, load_params=True):
     """checkpoint.py:122-148."""
@@ -72,6 +82,11 @@ class Checkpoint:
       raise ValueError(f"File {params_fname} not in current session {self.session} directory! Please specify the session using Checkpoint.specify_session")
     if load_params:
       self.model.load(f'{self.dirpath}/{self.session}/{params_fname_hash}.hkl')
+      optim_path = f'{self.dirpath}/{self.session}/{params_fname_hash}.optim'
+      if self.optimizer is not None and os.path.exists(optim_path):
+        from .model import _pickler
+        with open(optim_path, 'rb') as fp:
+          self.optimizer.load_state_dict(_pickler.load(fp))
     return session[params_fname_hash]
 
   def _init_files(self, dirpath):

@@ -19,17 +19,24 @@ from .. import device as D
 from .. import _backend as B
 from .. import distributed as dist
 
-_ARENAS = {}   # tuple(id(param)) -> Arena   (params keep the arena alive through their pinned views)
+import weakref
+
+import numpy as np
+
+# tuple(id(param)) -> Arena, WEAKLY: an arena lives as long as an optimizer over it (Optimizer.arena) or one of its
+# parameters (Param._arena) does, and its flat buffers, state and peer-memory exchange are released with the last of them.
+_ARENAS = weakref.WeakValueDictionary()
 
 
 class Arena:
   """Flat storage for a parameter list.  Offsets are padded to 4 floats so every view stays 16-byte aligned."""
 
   def __init__(self, params):
-    self.params = list(params)
+    params = list(params)
+    self._param_refs = [weakref.ref(p) for p in params]      # (params point at the arena, not the other way round)
     self.offsets = []
     n = 0
-    for p in self.params:
+    for p in params:
       self.offsets.append(n)
       n += (p.data.size + 3) & ~3
     self.numel = n
@@ -44,7 +51,7 @@ class Arena:
       self.grad = DeviceArray.zeros((max(n, 1),))
       self.grad_sum = self.grad
     self.state = {}
-    for p, off in zip(self.params, self.offsets):
+    for p, off in zip(params, self.offsets):
       size, shape = p.data.size, p.shape
       view = self.data[off:off + size].reshape(shape)
       view.assign(p.data)
@@ -53,23 +60,35 @@ class Arena:
         gview.assign(p._grad)
       p._data, p._pinned = view, True
       p._grad, p._grad_pinned = gview, True
+      p._arena = self
 
-  def state_buffer(self, name, attr):
-    """Flat state buffer `name`, (re)zeroed, with a view installed on every trainable Param as `attr`."""
+  @property
+  def params(self):
+    return [r() for r in self._param_refs]
+
+  def state_buffer(self, name, attr, only=None):
+    """Flat state buffer `name` with a view installed as `attr` on every trainable Param (of `only`, a set of ids, when the
+    optimizer covers part of the arena), (re)zeroed for those Params -- the reference's init_*_grads, optim.py:181-189."""
     buf = self.state.get(name)
-    if buf is None:
+    fresh = buf is None
+    if fresh:
       buf = self.state[name] = DeviceArray.empty((max(self.numel, 1),))
-    buf.fill(0.0)
+    if fresh or only is None:
+      buf.fill(0.0)
     for p, off in zip(self.params, self.offsets):
-      if p.requires_grad:
-        setattr(p, attr, buf[off:off + p.data.size].reshape(p.shape))
+      if p is None or not p.requires_grad or (only is not None and id(p) not in only):
+        continue
+      view = buf[off:off + p.data.size].reshape(p.shape)
+      if only is not None and not fresh:
+        view.fill(0.0)
+      setattr(p, attr, view)
     return buf
 
   def ranges(self):
     """Contiguous [begin, end) element ranges covering the trainable params (one range when nothing is frozen)."""
     out = []
     for p, off in zip(self.params, self.offsets):
-      if not p.requires_grad:
+      if p is None or not p.requires_grad:
         continue
       end = off + ((p.data.size + 3) & ~3)
       if out and out[-1][1] == off:
@@ -81,19 +100,27 @@ class Arena:
   def prepare_grads(self):
     """A trainable param that received no gradient holds the reference's `0.`: make its slice of the arena say so."""
     for p in self.params:
-      if p.requires_grad and not p._grad_live:
+      if p is not None and p.requires_grad and not p._grad_live:
         p._grad.fill(0.0)
 
 
 def _arena_for(params):
+  """The arena holding exactly this parameter list, created on first use.  A list that is a SUBSET of an existing arena's
+  parameters (e.g. GD(model.parameters()[:2]) after Adam(model.parameters()), which the reference allows) is served by
+  that arena: the optimizer then updates only its own parameters' ranges (Optimizer._ranges)."""
   key = tuple(id(p) for p in params)
   arena = _ARENAS.get(key)
-  if arena is None:
-    for p in params:
-      if p._pinned:
-        raise ValueError('a parameter is already registered with an optimizer over a different parameter list; '
-                         'construct optimizers over the same list (e.g. model.parameters()) and use freeze()/unfreeze()')
-    arena = _ARENAS[key] = Arena(params)
+  if arena is not None:
+    return arena
+  owners = {id(getattr(p, '_arena', None)) for p in params if getattr(p, '_pinned', False)}
+  if owners:
+    host = getattr(params[0], '_arena', None) if getattr(params[0], '_pinned', False) else None
+    if len(owners) == 1 and host is not None and all(getattr(p, '_arena', None) is host for p in params):
+      return host
+    raise ValueError('the parameters are registered with different optimizer arenas (or only some of them are registered); '
+                     'construct optimizers over lists drawn from one model.parameters()')
+  arena = Arena(params)
+  _ARENAS[key] = arena
   return arena
 
 
@@ -108,6 +135,55 @@ class Optimizer:
     self.params = params
     self.lr = lr
     self.arena = _arena_for(params)
+    mine = {id(p) for p in params}
+    self._whole = all(id(p) in mine for p in self.arena.params if p is not None)
+
+  def _only(self):
+    return None if self._whole else {id(p) for p in self.params}
+
+  def _ranges(self):
+    """[begin, end) element ranges of the arena this optimizer updates: its own trainable parameters."""
+    if self._whole:
+      return self.arena.ranges()
+    mine = {id(p) for p in self.params}
+    out = []
+    for p, off in zip(self.arena.params, self.arena.offsets):
+      if p is None or id(p) not in mine or not p.requires_grad:
+        continue
+      end = off + ((p.data.size + 3) & ~3)
+      if out and out[-1][1] == off:
+        out[-1][1] = end
+      else:
+        out.append([off, end])
+    return out
+
+  # ---------------------------------------------------------------- state for checkpoints (new; SURVEY 8f row 3)
+  _STATE_ATTRS = ()       # Param attributes holding this optimizer's per-parameter state
+  _HYPER = ('lr',)
+
+  def state_dict(self):
+    """Everything needed to resume exactly: hyper-parameters, iteration count, per-parameter state as float64 host arrays
+    (same nesting as the reference keeps it: ON the Params, optim.py:188-189 / 196-197)."""
+    state = {'class': type(self).__name__, 'hyper': {k: getattr(self, k) for k in self._HYPER}}
+    if hasattr(self, 'iter'):
+      state['iter'] = int(self.iter)
+    state['params'] = [{a: (getattr(p, a).numpy() if p.requires_grad and hasattr(p, a) and hasattr(getattr(p, a), 'numpy') else None)
+                        for a in self._STATE_ATTRS} for p in self.params]
+    return state
+
+  def load_state_dict(self, state):
+    if state.get('class') != type(self).__name__:
+      raise ValueError(f"optimizer state of a {state.get('class')} cannot be loaded into a {type(self).__name__}")
+    if len(state['params']) != len(self.params):
+      raise ValueError('optimizer state does not match the parameter list')
+    for k, v in state['hyper'].items():
+      setattr(self, k, v)
+    for p, st in zip(self.params, state['params']):
+      for a, val in st.items():
+        if val is not None and hasattr(p, a):
+          getattr(p, a).assign(D.DeviceArray.from_host(np.asarray(val).reshape(p.shape)))
+    if 'iter' in state and hasattr(self, 'iter'):
+      self.iter = state['iter']
 
   def zero_grad(self, all_members=False):
     if all_members:
@@ -139,7 +215,7 @@ class GD(Optimizer):
   def step(self):
     gs = self._sync_grads()
     a = self.arena
-    for b, e in a.ranges():
+    for b, e in self._ranges():
       B.check(B.lib.ngb_sgd_step(_off(a.data, b), _off(a.grad_sum, b), e - b, self.lr, gs, _st()))
 
   def __repr__(self):
@@ -150,6 +226,8 @@ class GD(Optimizer):
 
 class Momentum(Optimizer):
   """optim.py:56-99."""
+  _STATE_ATTRS = ('momentum_grad',)
+  _HYPER = ('lr', 'beta')
 
   def __init__(self, params, lr, beta=0.9):
     super().__init__(params, lr)
@@ -157,12 +235,12 @@ class Momentum(Optimizer):
     self.init_momentum_grads()
 
   def init_momentum_grads(self):
-    self._m = self.arena.state_buffer('momentum', 'momentum_grad')
+    self._m = self.arena.state_buffer('momentum', 'momentum_grad', self._only())
 
   def step(self):
     gs = self._sync_grads()
     a = self.arena
-    for b, e in a.ranges():
+    for b, e in self._ranges():
       B.check(B.lib.ngb_momentum_step(_off(a.data, b), _off(a.grad_sum, b), _off(self._m, b), e - b, self.lr, self.beta, gs, _st()))
 
   def __repr__(self):
@@ -173,6 +251,8 @@ class Momentum(Optimizer):
 
 class RMSProp(Optimizer):
   """optim.py:102-147."""
+  _STATE_ATTRS = ('rms_grad',)
+  _HYPER = ('lr', 'beta', 'epsilon')
 
   def __init__(self, params, lr, beta=0.9, epsilon=1e-8):
     super().__init__(params, lr)
@@ -181,12 +261,12 @@ class RMSProp(Optimizer):
     self.init_rms_grads()
 
   def init_rms_grads(self):
-    self._r = self.arena.state_buffer('rms', 'rms_grad')
+    self._r = self.arena.state_buffer('rms', 'rms_grad', self._only())
 
   def step(self):
     gs = self._sync_grads()
     a = self.arena
-    for b, e in a.ranges():
+    for b, e in self._ranges():
       B.check(B.lib.ngb_rmsprop_step(_off(a.data, b), _off(a.grad_sum, b), _off(self._r, b), e - b, self.lr, self.beta,
                                      self.epsilon, gs, _st()))
 
@@ -200,31 +280,41 @@ class Adam(Optimizer):
   """optim.py:150-208.  `iter` also lives in device memory and is advanced by the step's own launch, so a training
   step captured in a CUDA graph keeps the correct bias correction on every replay."""
 
+  _STATE_ATTRS = ('momentum_grad', 'rms_grad')
+  _HYPER = ('lr', 'beta1', 'beta2', 'epsilon')
+
   def __init__(self, params, lr, beta1=0.9, beta2=0.999, epsilon=1e-8):
     super().__init__(params, lr)
     self._t_dev = torch().zeros(2, device='cuda', dtype=torch().int32)   # [steps taken, scratch counter of the update kernel]
-    self.iter = 0
     self.beta1, self.beta2 = beta1, beta2
     self.epsilon = epsilon
     self.init_adam_grads()
 
   def init_adam_grads(self):
-    self._m = self.arena.state_buffer('momentum', 'momentum_grad')
-    self._v = self.arena.state_buffer('rms', 'rms_grad')
+    self._m = self.arena.state_buffer('momentum', 'momentum_grad', self._only())
+    self._v = self.arena.state_buffer('rms', 'rms_grad', self._only())
+
+  @property
+  def iter(self):
+    """optim.py:160: iterations taken so far.  The count lives on the device (a captured step advances it on every replay);
+    reading it here synchronises, assigning to it (e.g. when resuming from a checkpoint) takes effect on the next step."""
+    return int(self._t_dev[0].item())
+
+  @iter.setter
+  def iter(self, value):
+    self._t_dev[0] = int(value)
 
   def step(self):
-    self.iter += 1
     gs = self._sync_grads()
     a = self.arena
     t_ptr = ctypes.c_void_p(self._t_dev.data_ptr())
-    ranges = a.ranges() or [[0, 0]]          # (nothing trainable: the step is still counted, optim.py:169)
+    ranges = self._ranges() or [[0, 0]]          # (nothing trainable: the step is still counted, optim.py:169)
     for i, (b, e) in enumerate(ranges):
       tick = 1 if i == len(ranges) - 1 else 2      # the last launch of the step records the new iteration count
       B.check(B.lib.ngb_adam_step_dev(_off(a.data, b), _off(a.grad_sum, b), _off(self._m, b), _off(self._v, b), e - b, self.lr,
                                       self.beta1, self.beta2, self.epsilon, t_ptr, tick, gs, _st()))
 
   def reset_iter(self):
-    self.iter = 0
     self._t_dev.zero_()
 
   def __repr__(self):
