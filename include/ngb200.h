@@ -256,15 +256,24 @@ int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, double lr, d
                      double grad_scale, ngb_stream_t stream);                               /* optim.py:112-118, 134-140 */
 
 /* ---- data parallel over NVLink peer memory (new) -------------------------------------------------------
- * Every rank keeps its flat gradient buffer in symmetric (peer-mapped) memory.  `peer_ptrs_dev` / `flag_ptrs_dev` are DEVICE
- * arrays of `world` pointers: rank r's gradient buffer / rank r's flag words (>= world uint32, zero-initialised).
- * ngb_xgpu_barrier: rank publishes (*epoch_dev + 1) into every peer's flag word [rank] and waits until all peers have
- *   published it here; *epoch_dev is advanced by the kernel itself, so a captured step replays correctly.  Bounded wait.
- * ngb_xgpu_reduce_sum: out[i] = sum over ranks (in rank order) of peer r's buffer[i], loaded over NVLink.
- * Sequence per step: barrier (all gradients final) -> reduce_sum -> barrier (all peers have read) -> optimizer on `out`. */
-int ngb_xgpu_barrier(const void* flag_ptrs_dev, int rank, int world, uint32_t* epoch_dev, ngb_stream_t stream);
-int ngb_xgpu_reduce_sum(const void* peer_ptrs_dev, float* out, int64_t n, int world, ngb_stream_t stream);
-int ngb_xgpu_check(void);   /* NGB_ERR_CUDA if a cross-GPU barrier timed out since the last call (synchronises) */
+ * The gradient exchange FUSED with the optimizer update (one launch per optimizer step and parameter range; replaces the
+ * reference's single-process optim.py:42-47 / 63-92 / 112-140 / 168-197 under data parallelism).  Every rank owns a receive
+ * buffer [2 parities][world][slot_stride] floats and flag words [world][max_blocks] in memory its peers can store to
+ * (recv_ptrs_dev / flag_ptrs_dev: DEVICE arrays of `world` device pointers, entry r = rank r's buffer).  The kernel pushes
+ * the range [off, off + n) of `grad` into slot [rank] of every peer, signals, waits for the peers' pushes (bounded by
+ * timeout_s; <= 0 means 60 s), sums the slots in rank order (own gradient in place), multiplies by grad_scale and updates
+ * params / state.  epoch_dev: two uint32 (exchanges completed, scratch counter).  kind: 0 Adam (state1 = m, state2 = v,
+ * t_dev / tick as ngb_adam_step_dev), 1 GD, 2 Momentum (state1; beta1 = beta), 3 RMSProp (state1; beta1 = beta).
+ * A failed exchange applies NO update and makes every later call a no-op; ngb_xgpu_status reports it. */
+int ngb_xgpu_exchange_update(const void* recv_ptrs_dev, const void* flag_ptrs_dev, int rank, int world, int max_blocks,
+                             int64_t slot_stride, int64_t off, int64_t n, const float* grad, float* params, float* state1,
+                             float* state2, uint32_t* epoch_dev, int kind, double lr, double beta1, double beta2,
+                             double epsilon, int32_t* t_dev, int tick, double grad_scale, double timeout_s,
+                             ngb_stream_t stream);
+int ngb_xgpu_blocks(int64_t n, int max_blocks);   /* blocks the launch above uses for n floats (same on every rank) */
+int ngb_xgpu_status(void);  /* non-blocking: NGB_ERR_CUDA once an exchange has timed out (reads a host-mapped word) */
+int ngb_xgpu_check(void);   /* same, after synchronising the device (tests / tools) */
+int ngb_xgpu_reset(void);   /* clears the sticky failure (tests that provoke a timeout) */
 
 #ifdef __cplusplus
 }

@@ -56,9 +56,12 @@ SIGNATURES = {
   'ngb_set_default_engine': ([c_int], c_int),
   'ngb_set_lane': ([c_int], c_int),
   'ngb_set_corun': ([c_int], c_int),
-  'ngb_xgpu_barrier': ([_P, c_int, c_int, _P, _S], c_int),
-  'ngb_xgpu_reduce_sum': ([_P, _P, c_int64, c_int, _S], c_int),
+  'ngb_xgpu_exchange_update': ([_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_int] +
+                               [c_double] * 4 + [_P, c_int, c_double, c_double, _S], c_int),
+  'ngb_xgpu_blocks': ([c_int64, c_int], c_int),
+  'ngb_xgpu_status': ([], c_int),
   'ngb_xgpu_check': ([], c_int),
+  'ngb_xgpu_reset': ([], c_int),
   'ngb_gemm_query': ([c_int, c_int, c_int64, c_int64, c_int64, c_int64, c_int64, c_int64], c_int),
   'ngb_launch_count': ([], c_int64),
   'ngb_gemm': ([c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, _S], c_int),
@@ -263,7 +266,7 @@ class profile_calls:
   `records` is a list of (name, args, start_event, end_event); call `summary()` after the block (it synchronises).
   Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
   SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
-          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane', 'ngb_set_corun', 'ngb_xgpu_check',
+          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane', 'ngb_set_corun', 'ngb_xgpu_check', 'ngb_xgpu_status', 'ngb_xgpu_reset', 'ngb_xgpu_blocks',
           'ngb_debug_wgrad_layout', 'ngb_conv_relu_pool_fwd_serves', 'ngb_conv_wbgrad_pooled_is_fused', 'ngb_linear_softmax_ce_serves')
 
   def __enter__(self):

@@ -116,7 +116,7 @@ class Linear(Operation):
 
     inputs.set_grad_fn(GradFn(dgrad, None, dgrad_lazy))
     weights.set_grad_fn(GradFn(wgrad, joint=(bias, wbgrad, lambda ug: True)))
-    bias.set_grad_fn(GradFn(bgrad))
+    bias.set_grad_fn(GradFn(bgrad, joint=(weights, wbgrad, lambda ug: True, False)))
 
 
 def fusable(inputs, weights, bias):

@@ -25,9 +25,11 @@ class GradFn:
 
   def __init__(self, into, alias=None, lazy=None, lazy_ok=False, joint=None):
     self.into = into
-    # joint = (other_leaf, fn, usable): fn(ug, dst, accumulate, other_dst, other_accumulate) produces this operand's AND
-    # other_leaf's gradient in one go (conv weight + bias from one pass over the upstream gradient) when usable(ug); used by
-    # the backward lanes when both are leaves waiting on the same upstream gradient
+    # joint = (other_leaf, fn, usable[, primary]): fn(ug, dst, accumulate, other_dst, other_accumulate) produces the PRIMARY
+    # operand's gradient (dst) AND its partner's (other_dst) in one go (weight + bias from one pass over the upstream
+    # gradient) when usable(ug).  primary (default True) says whether this operand is fn's first; a partner may carry the
+    # mirrored entry with primary = False so that whichever leaf is visited first triggers the kernel.  Used by the backward
+    # lanes when both are leaves waiting on the same upstream gradient, and by the single-stream visit otherwise
     self.joint = joint
     # lazy_ok: `into` understands a still-deferred upstream gradient (device.LazyArray) and need not have it materialised
     self.lazy_ok = lazy_ok
@@ -198,7 +200,24 @@ class Tensor:
               self._ensure_grad_buffer()
               if self._grad_live:
                 self._unshare_grad()
-              gf.into(upper_grad, self._grad, self._grad_live)
+              other = self._joint_partner(gf, child, node, upper_grad)
+              if other is not None:
+                # one kernel yields this leaf's gradient AND its partner's (weight + bias from one pass over the upstream
+                # gradient): the partner's own visit then finds its contribution from this op already accumulated
+                other._ensure_grad_buffer()
+                if other._grad_live:
+                  other._unshare_grad()
+                mine_first = gf.joint[3] if len(gf.joint) > 3 else True
+                if mine_first:
+                  gf.joint[1](upper_grad, self._grad, self._grad_live, other._grad, other._grad_live)
+                else:
+                  gf.joint[1](upper_grad, other._grad, other._grad_live, self._grad, self._grad_live)
+                other._grad_live = True
+                if child.lane_done is None:
+                  child.lane_done = {}
+                child.lane_done[id(other)] = 'lane'
+              else:
+                gf.into(upper_grad, self._grad, self._grad_live)
               self._grad_live = True
             if child.defer_leaves:                   # the op's data gradient is on its way: now its weight / bias gradients
               child.defer_leaves = False
@@ -220,6 +239,25 @@ class Tensor:
         self._issue_leaf_grads(node, corun=False)   # end of a chain: nothing of this op runs on the main stream
     if not retain_graph and node.are_parents_visited():
       graph.remove_tensor(node.tens)
+
+  def _joint_partner(self, gf, child, node, upper_grad):
+    """The leaf whose gradient from `child` can come out of the same kernel as this leaf's (GradFn.joint), if it is still
+    pending there; None otherwise.  Only for leaves visited on the main stream (the lanes pair leaves themselves)."""
+    if gf.joint is None or node.parents or _lanes.active():
+      return None
+    other = gf.joint[0]
+    if other is self or not other.requires_grad or not isinstance(other.grad_fn, GradFn):
+      return None
+    onode = None
+    for p in child.parents:
+      if p.tens is other:
+        onode = p
+        break
+    if onode is None or onode.parents or onode.visited:       # (visited: its contribution from this op is already in)
+      return None
+    if child.lane_done is not None and id(other) in child.lane_done:
+      return None
+    return other if gf.joint[2](upper_grad) else None
 
   def _issue_leaf_grads(self, node, corun=True):
     leaves = [p for p in node.parents if not p.parents and p.tens.requires_grad and p.tens is not self]
@@ -251,7 +289,7 @@ class Tensor:
     partner_of = {}
     for p in leaves:
       gf = p.tens.grad_fn
-      if isinstance(gf, GradFn) and gf.joint is not None and pending(p.tens):
+      if isinstance(gf, GradFn) and gf.joint is not None and pending(p.tens) and (len(gf.joint) < 4 or gf.joint[3]):
         other = by_tensor.get(id(gf.joint[0]))
         if (other is not None and other is not p.tens and pending(other) and _lanes.can_share(p.tens, other)
             and gf.joint[2](upper_grad)):

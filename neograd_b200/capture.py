@@ -34,9 +34,16 @@ class CapturedStep:
     with t.cuda.graph(self.graph, stream=t.cuda.Stream(priority=-1)):
       self.result = fn()
     self.launches = int(B.lib.ngb_launch_count() - n0)   # kernels of libngb200 recorded in the graph
+    self._replays = 0
 
   def __call__(self):
     self.graph.replay()
+    self._replays += 1
+    if (self._replays & 63) == 0:
+      # a captured data-parallel step runs with no host involvement: poll the peer exchange's health word now and then
+      # (a host-memory read), so a rank that lost a peer raises instead of replaying no-op updates forever
+      from . import _backend as B
+      B.check(B.lib.ngb_xgpu_status())
     return self.result
 
   replay = __call__

@@ -74,6 +74,9 @@ __global__ void __launch_bounds__(256) linear_smalln_fwd_kernel(const float* __r
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
   float bias_mine = (b != nullptr && lane < N) ? b[lane] : 0.f;
+  float bias_all[NT];                                    // (HEAD only; dead code otherwise)
+#pragma unroll
+  for (int n = 0; n < NT; ++n) bias_all[n] = (HEAD && b != nullptr && n < N) ? b[n] : 0.f;
   float loss_acc = 0.f;
   for (int64_t row = (int64_t)blockIdx.x * nwarp + warp; row < M; row += (int64_t)gridDim.x * nwarp) {
     const float* xr = x + row * K;
@@ -98,17 +101,23 @@ __global__ void __launch_bounds__(256) linear_smalln_fwd_kernel(const float* __r
       if (a) a[row * N + lane] = lin_act(act, alpha, mine);
     }
     if (HEAD) {
-      // softmax over the N logits held one per lane (nn/activations.py:161-174), loss.py:155 and :170
-      float mx = lane < N ? mine : -INFINITY;
+      // softmax over the N logits (nn/activations.py:161-174), loss.py:155 and :170.  Every lane holds all logits, so each
+      // evaluates max and sum SEQUENTIALLY over the classes -- the summation order of softmax_ce_{fwd,bwd}_kernel
+      // (loss.cu), which makes this head's gradient bit-identical to the unfused kernels'.
+      float mx = -INFINITY;
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
-      const float ex = lane < N ? expf(mine - mx) : 0.f;
-      const float sum = warp_sum(ex);
-      const float p = ex / sum;
+      for (int n = 0; n < NT; ++n)
+        if (n < N) mx = fmaxf(mx, acc[n] + bias_all[n]);
+      float sum = 0.f;
+#pragma unroll
+      for (int n = 0; n < NT; ++n)
+        if (n < N) sum += expf(acc[n] + bias_all[n] - mx);
+      const float inv = 1.f / sum;
       if (lane < N) {
+        const float p = expf(mine - mx) * inv;
         const float tv = h.t[row * N + lane];
         if (tv != 0.f) loss_acc += tv * logf(p + h.eps);
-        h.dz[row * N + lane] = (p - tv) * h.inv_n;
+        h.dz[row * N + lane] = h.inv_n * (p - tv);
       }
     }
   }
@@ -123,9 +132,11 @@ __global__ void __launch_bounds__(256) linear_smalln_fwd_kernel(const float* __r
     if (is_last) {      // fixed-order sum of the per-block partials: deterministic
       if (threadIdx.x < 32) {
         __threadfence();
-        float tot = 0.f;
-        for (int i = lane; i < (int)gridDim.x; i += 32) tot += h.partials[i];
-        tot = warp_sum(tot);
+        // (at most 128 blocks: four independent loads per lane, one round trip)
+        const int nbk = (int)gridDim.x;
+        const float t0 = lane < nbk ? h.partials[lane] : 0.f, t1 = lane + 32 < nbk ? h.partials[lane + 32] : 0.f;
+        const float t2 = lane + 64 < nbk ? h.partials[lane + 64] : 0.f, t3 = lane + 96 < nbk ? h.partials[lane + 96] : 0.f;
+        float tot = warp_sum((t0 + t1) + (t2 + t3));
         if (lane == 0) {
           *h.loss = -h.inv_n * tot;      // loss.py:156: (-1/num_examples) * entropy
           *h.done = 0;
@@ -160,74 +171,74 @@ __global__ void __launch_bounds__(256) linear_smalln_dgrad_kernel(const float* _
   }
 }
 
-// dW[k][n] = sum_m x[m][k] ug[m][n], db[n] = sum_m ug[m][n].  Thread = one k (x rows are read coalesced straight from
-// global memory), NT accumulators; a block walks a contiguous range of rows with the ug rows staged in shared memory; the
-// per-block partial results are summed in block order by the last block to finish.
-template <int NT>
+// dW[k][n] = sum_m x[m][k] ug[m][n], db[n] = sum_m ug[m][n]: a reduction over the batch with only K x N outputs.  Block = KB
+// adjacent k (one 16 / 32-byte piece of every x row, so the strided walk down the batch still uses whole sectors), all N
+// outputs of each; the last block sums ug itself (the bias gradient).  Threads stride over the rows with KB x NT register
+// accumulators, then one fixed-shape tree (warp shuffles, then the 8 warp results in order) gives the block's outputs: no
+// partial buffers, no second pass, bit-reproducible.
+template <int NT, int KB>
 __global__ void __launch_bounds__(256) linear_smalln_wgrad_kernel(const float* __restrict__ x, const float* __restrict__ ug,
                                                                   float* __restrict__ dW, float* __restrict__ db, int64_t M, int N,
-                                                                  int K, int rows_per_block, int acc_w, int acc_b,
-                                                                  float* __restrict__ partials, unsigned int* done) {
-  constexpr int RB = 32;
-  __shared__ float us[RB][NT];
-  __shared__ bool is_last;
-  const int64_t r0 = (int64_t)blockIdx.x * rows_per_block;
-  const int64_t r1 = min(M, r0 + rows_per_block);
-  const int psize = K * N + N;
-  float* mypart = partials + (int64_t)blockIdx.x * psize;
-  for (int kbase = 0; kbase < K; kbase += blockDim.x) {
-    const int k = kbase + threadIdx.x;
-    float acc[NT], bs[NT];
+                                                                  int K, int acc_w, int acc_b) {
+  __shared__ float red[8][KB * NT];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const bool is_bias = blockIdx.x == gridDim.x - 1;
+  const int k0 = blockIdx.x * KB;
+  const bool xvec = (KB % 4 == 0) && (K % 4 == 0) && ((reinterpret_cast<uintptr_t>(x) & 15) == 0);
+  float acc[KB][NT];
 #pragma unroll
-    for (int n = 0; n < NT; ++n) { acc[n] = 0.f; bs[n] = 0.f; }
-    for (int64_t rb = r0; rb < r1; rb += RB) {
-      const int nr = (int)((r1 - rb) < (int64_t)RB ? (r1 - rb) : (int64_t)RB);
-      __syncthreads();
-      for (int i = threadIdx.x; i < RB * NT; i += blockDim.x) {
-        const int r = i / NT, n = i - r * NT;
-        us[r][n] = (r < nr && n < N) ? ug[(rb + r) * N + n] : 0.f;
-      }
-      __syncthreads();
-      if (k < K) {
-        for (int r = 0; r < nr; ++r) {
-          const float xv = x[(rb + r) * K + k];
+  for (int j = 0; j < KB; ++j)
 #pragma unroll
-          for (int n = 0; n < NT; ++n) acc[n] = fmaf(xv, us[r][n], acc[n]);
+    for (int n = 0; n < NT; ++n) acc[j][n] = 0.f;
+#pragma unroll 2
+  for (int64_t m = tid; m < M; m += 256) {
+    float u[NT];
+    const float* ur = ug + m * N;
+#pragma unroll
+    for (int n = 0; n < NT; ++n) u[n] = n < N ? ur[n] : 0.f;
+    if (is_bias) {
+#pragma unroll
+      for (int n = 0; n < NT; ++n) acc[0][n] += u[n];
+    } else {
+      float xv[KB];
+      const float* xr = x + m * K + k0;
+      if (xvec && k0 + KB <= K) {
+#pragma unroll
+        for (int j = 0; j < KB; j += 4) {
+          const float4 t = *reinterpret_cast<const float4*>(xr + j);
+          xv[j] = t.x; xv[j + 1] = t.y; xv[j + 2] = t.z; xv[j + 3] = t.w;
         }
+      } else {
+#pragma unroll
+        for (int j = 0; j < KB; ++j) xv[j] = k0 + j < K ? xr[j] : 0.f;
       }
-      if (kbase == 0 && threadIdx.x == 0) {
-        for (int r = 0; r < nr; ++r) {
 #pragma unroll
-          for (int n = 0; n < NT; ++n) bs[n] += us[r][n];
-        }
-      }
-    }
-    if (k < K) {
+      for (int j = 0; j < KB; ++j)
 #pragma unroll
-      for (int n = 0; n < NT; ++n)
-        if (n < N) mypart[k * N + n] = acc[n];
-    }
-    if (kbase == 0 && threadIdx.x == 0) {
-#pragma unroll
-      for (int n = 0; n < NT; ++n)
-        if (n < N) mypart[K * N + n] = bs[n];
+        for (int n = 0; n < NT; ++n) acc[j][n] = fmaf(xv[j], u[n], acc[j][n]);
     }
   }
-  __syncthreads();
-  if (threadIdx.x == 0) {
-    __threadfence();
-    is_last = atomicAdd(done, 1u) == gridDim.x - 1;
-  }
-  __syncthreads();
-  if (is_last) {
-    __threadfence();
-    for (int i = threadIdx.x; i < psize; i += blockDim.x) {
-      float s = 0.f;
-      for (int bidx = 0; bidx < (int)gridDim.x; ++bidx) s += partials[(int64_t)bidx * psize + i];
-      if (i < K * N) dW[i] = acc_w ? dW[i] + s : s;
-      else if (db) { const int n = i - K * N; db[n] = acc_b ? db[n] + s : s; }
+#pragma unroll
+  for (int j = 0; j < KB; ++j)
+#pragma unroll
+    for (int n = 0; n < NT; ++n) {
+      const float w = warp_sum(acc[j][n]);
+      if (lane == 0) red[warp][j * NT + n] = w;
     }
-    if (threadIdx.x == 0) *done = 0;
+  __syncthreads();
+  if (tid < KB * NT) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) s += red[w][tid];
+    const int j = tid / NT, n = tid - j * NT;
+    if (n < N) {
+      if (is_bias) {
+        if (j == 0 && db) db[n] = acc_b ? db[n] + s : s;
+      } else if (k0 + j < K) {
+        float* d = dW + (int64_t)(k0 + j) * N + n;
+        *d = acc_w ? *d + s : s;
+      }
+    }
   }
 }
 
@@ -259,7 +270,8 @@ int launch_small_fwd(const float* x, const float* W, const float* b, float* z, f
   if (rc) return rc;
   const int threads = 256, rows_per_cta = threads / 32;
   int64_t grid = ceil_div<int64_t>(M, rows_per_cta);
-  if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+  const int64_t cap = HEAD ? 128 : 2 * kNumSMs;              // (HEAD: the last block sums one partial per block)
+  if (grid > cap) grid = cap;
   kern<<<(int)grid, threads, smem, st>>>(x, W, b, z, a, act, alpha, M, (int)N, (int)K, h);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
@@ -291,20 +303,9 @@ int launch_small_dgrad(const float* ug, const float* W, const float* zprev, floa
 template <int NT>
 int launch_small_wgrad(const float* x, const float* ug, float* dW, float* db, int64_t M, int64_t N, int64_t K, int acc_w, int acc_b,
                        cudaStream_t st) {
-  int rc = ensure_init();
-  if (rc) return rc;
-  const int psize = (int)(K * N + N);
-  int64_t blocks = ceil_div<int64_t>(M, 32);
-  if (blocks > kNumSMs) blocks = kNumSMs;
-  const int64_t cap = scratch_bytes() / (psize * (int64_t)sizeof(float));
-  if (blocks > cap) blocks = cap;
-  if (blocks < 1) return fail(NGB_ERR_SCRATCH, "ngb_linear_wgrad: scratch arena too small");
-  const int rpb = (int)(ceil_div<int64_t>(ceil_div<int64_t>(M, blocks), 32) * 32);
-  blocks = ceil_div<int64_t>(M, rpb);
-  int threads = (int)(ceil_div<int64_t>(K, 32) * 32);
-  if (threads > 256) threads = 256;
-  linear_smalln_wgrad_kernel<NT><<<(int)blocks, threads, 0, st>>>(x, ug, dW, db, M, (int)N, (int)K, rpb, acc_w, acc_b, scratch_ptr(),
-                                                                  done_counter());
+  constexpr int KB = NT <= 4 ? 8 : (NT <= 16 ? 4 : 2);       // KB x NT <= 64 accumulators per thread
+  const int blocks = (int)ceil_div<int64_t>(K, KB) + 1;      // + the bias block
+  linear_smalln_wgrad_kernel<NT, KB><<<blocks, 256, 0, st>>>(x, ug, dW, db, M, (int)N, (int)K, acc_w, acc_b);
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }

@@ -59,28 +59,29 @@ def all_reduce_sum(arr):
 
 
 class PeerExchange:
-  """Gradient exchange over NVLink peer memory (csrc/xgpu.cu) for one flat arena of `numel` floats.
+  """Gradient exchange FUSED with the optimizer update over NVLink peer memory (csrc/xgpu.cu) for one flat arena of `numel`
+  floats: one kernel per optimizer step pushes this rank's gradients into every peer's receive slots, waits for the peers'
+  pushes, sums the `world` slots in rank order (bit-identical replicas), scales by 1/world and applies the update.
 
-  `grad` is this rank's gradient buffer, allocated in symmetric memory so every GPU of the node can load it; `summed` is
-  the local result.  `run(stream)` issues barrier -> reduce (each GPU sums the `world` peer buffers in rank order, so all
-  replicas get bit-identical sums) -> barrier.  Construction is collective (every rank must build its exchanges in the
-  same order).  `create` returns None when symmetric memory is unavailable (gloo / CPU, single process, NGB_NO_P2P=1):
-  the caller then uses the NCCL allreduce."""
+  `recv` is this rank's receive buffer [2 parities][world][stride] in symmetric memory (torch.distributed._symmetric_memory:
+  plumbing only), `flags` the per-(source, block) arrival words.  Construction is collective (every rank must build its
+  exchanges in the same order).  `create` returns None when symmetric memory is unavailable (gloo / CPU, single process,
+  NGB_NO_P2P=1): the caller then uses the NCCL allreduce followed by the plain update kernel."""
+  MAX_BLOCKS = 148
+  KIND = {'adam': 0, 'sgd': 1, 'momentum': 2, 'rmsprop': 3}
 
-  def __init__(self, grad, summed, peer_ptrs, flags, flag_ptrs, epoch, handles):
-    self.grad, self.summed = grad, summed
-    self._peer_ptrs, self._flags, self._flag_ptrs, self._epoch, self._handles = peer_ptrs, flags, flag_ptrs, epoch, handles
+  def __init__(self, stride, recv, recv_ptrs, flags, flag_ptrs, epoch, handles):
+    self.stride, self.recv, self._recv_ptrs, self._flags, self._flag_ptrs, self._epoch, self._handles = (
+      stride, recv, recv_ptrs, flags, flag_ptrs, epoch, handles)
     self.rank, self.world = rank(), world_size()
+    self.timeout_s = float(os.environ.get('NGB_XGPU_TIMEOUT_S', '60'))
+    self._calls = 0
 
   @staticmethod
   def create(numel):
-    import ctypes
     import torch
     import torch.distributed as td
-    # measured on 8 x B200 (tools/p2p_check.py): 3.6 us per step faster than the NCCL allreduce at 8 GPUs, 5 us slower at 2
-    # (two operands: NCCL's low-latency protocol wins), so the exchange is used from 4 GPUs up (NGB_P2P=1 / NGB_NO_P2P=1 force)
-    force = os.environ.get('NGB_P2P') == '1'
-    if not is_initialized() or world_size() <= 1 or os.environ.get('NGB_NO_P2P') == '1' or (world_size() < 4 and not force):
+    if not is_initialized() or world_size() <= 1 or os.environ.get('NGB_NO_P2P') == '1':
       return None
     if td.get_backend() != 'nccl' or not torch.cuda.is_available():
       return None
@@ -93,17 +94,17 @@ class PeerExchange:
         sm.enable_symm_mem_for_group(group.group_name)
       except Exception:
         pass
-      n = max((int(numel) + 3) & ~3, 4)
-      grad = sm.empty(n, dtype=torch.float32, device='cuda')
-      grad.zero_()
-      hg = sm.rendezvous(grad, group)
-      flags = sm.empty(64, dtype=torch.int32, device='cuda')
+      w = world_size()
+      stride = max((int(numel) + 3) & ~3, 4)
+      recv = sm.empty(2 * w * stride, dtype=torch.float32, device='cuda')
+      recv.zero_()
+      hr = sm.rendezvous(recv, group)
+      flags = sm.empty(w * PeerExchange.MAX_BLOCKS, dtype=torch.int32, device='cuda')
       flags.zero_()
       hf = sm.rendezvous(flags, group)
-      peer_ptrs = torch.tensor([int(p) for p in hg.buffer_ptrs], dtype=torch.int64, device='cuda')
+      recv_ptrs = torch.tensor([int(p) for p in hr.buffer_ptrs], dtype=torch.int64, device='cuda')
       flag_ptrs = torch.tensor([int(p) for p in hf.buffer_ptrs], dtype=torch.int64, device='cuda')
-      ex = PeerExchange(grad, torch.zeros(n, dtype=torch.float32, device='cuda'), peer_ptrs, flags, flag_ptrs,
-                        torch.zeros(1, dtype=torch.int32, device='cuda'), (hg, hf))
+      ex = PeerExchange(stride, recv, recv_ptrs, flags, flag_ptrs, torch.zeros(2, dtype=torch.int32, device='cuda'), (hr, hf))
     except Exception as e:   # noqa: BLE001 -- any failure means "no peer memory here"
       sys_msg = f'neograd_b200: peer-memory gradient exchange unavailable ({type(e).__name__}: {e}); using NCCL'
       if rank() == 0:
@@ -115,15 +116,25 @@ class PeerExchange:
     td.barrier()
     return ex if ok.item() > 0 else None
 
-  def run(self, n, stream):
-    """summed[:n] = sum over ranks of grad[:n]; everything is stream-ordered and graph-capturable."""
+  def update(self, kind, off, n, grad, params, state1, state2, lr, beta1, beta2, epsilon, t_dev, tick, grad_scale, stream):
+    """One launch: exchange the range [off, off + n) of `grad` and update params / state in place (stream-ordered and
+    graph-capturable; the epoch that selects the receive-slot parity lives in device memory)."""
     import ctypes
     from . import _backend as B
-    fp, pp = ctypes.c_void_p(self._flag_ptrs.data_ptr()), ctypes.c_void_p(self._peer_ptrs.data_ptr())
-    ep = ctypes.c_void_p(self._epoch.data_ptr())
-    B.check(B.lib.ngb_xgpu_barrier(fp, self.rank, self.world, ep, stream))          # every rank's gradients are final
-    B.check(B.lib.ngb_xgpu_reduce_sum(pp, ctypes.c_void_p(self.summed.data_ptr()), int(n), self.world, stream))
-    B.check(B.lib.ngb_xgpu_barrier(fp, self.rank, self.world, ep, stream))          # every rank has read every buffer
+    P = lambda t: ctypes.c_void_p(t.data_ptr()) if t is not None else None
+    self._calls += 1
+    if (self._calls & 15) == 0:
+      self.check()
+    B.check(B.lib.ngb_xgpu_exchange_update(P(self._recv_ptrs), P(self._flag_ptrs), self.rank, self.world, self.MAX_BLOCKS,
+                                           self.stride, int(off), int(n), P(grad), P(params), P(state1), P(state2),
+                                           P(self._epoch), self.KIND[kind], lr, beta1, beta2, epsilon, P(t_dev), int(tick),
+                                           grad_scale, self.timeout_s, stream))
+
+  @staticmethod
+  def check():
+    """Raises if an exchange gave up on a peer (the kernels stop updating from then on); a cheap host-memory read."""
+    from . import _backend as B
+    B.check(B.lib.ngb_xgpu_status())
 
 
 def shard(n, r=None, w=None):

@@ -41,15 +41,11 @@ class Arena:
       n += (p.data.size + 3) & ~3
     self.numel = n
     self.data = DeviceArray.zeros((max(n, 1),))
-    # data parallel on one node: the gradient buffer lives in symmetric (peer-mapped) memory and the ranks sum each
-    # other's buffers over NVLink themselves (distributed.PeerExchange); otherwise a plain buffer + NCCL allreduce
+    # data parallel on one node: the ranks push their gradients into each other's receive slots over NVLink and sum them
+    # inside the update kernel (distributed.PeerExchange); otherwise one NCCL allreduce of the flat buffer, then the update
     self.exchange = dist.PeerExchange.create(n)
-    if self.exchange is not None:
-      self.grad = DeviceArray(self.exchange.grad[:max(n, 1)])
-      self.grad_sum = DeviceArray(self.exchange.summed[:max(n, 1)])
-    else:
-      self.grad = DeviceArray.zeros((max(n, 1),))
-      self.grad_sum = self.grad
+    self.grad = DeviceArray.zeros((max(n, 1),))
+    self.grad_sum = self.grad
     self.state = {}
     for p, off in zip(params, self.offsets):
       size, shape = p.data.size, p.shape
@@ -192,18 +188,32 @@ class Optimizer:
       param.zero_grad()
 
   def _sync_grads(self):
-    """Data parallel: sum the flat gradient buffer over ranks -- peer-memory exchange over NVLink (the summed gradient is
-    then `arena.grad_sum`), or one NCCL allreduce in place when peer memory is unavailable; returns grad_scale."""
+    """Data parallel without peer memory: one NCCL allreduce of the flat gradient buffer in place; returns grad_scale.
+    (With peer memory the exchange happens inside the update kernel: _fused_exchange.)"""
     a = self.arena
-    D.flush_lazy()           # deferred conv outputs somebody still holds are produced before the weights change
+    D.flush_lazy()           # deferred arrays somebody still holds are produced before the weights change
     a.prepare_grads()
     if dist.is_initialized() and dist.world_size() > 1:
-      if a.exchange is not None:
-        a.exchange.run(a.numel, _st())
-      else:
+      if a.exchange is None:
         dist.all_reduce_sum(a.grad)
       return 1.0 / dist.world_size()
     return 1.0
+
+  def _fused_exchange(self, kind, s1=None, s2=None, beta1=0.0, beta2=0.0, epsilon=0.0, t_dev=None):
+    """Data parallel over NVLink peer memory: ONE kernel per parameter range pushes / gathers the gradients, sums them in
+    rank order, scales by 1/world and applies the update (csrc/xgpu.cu).  Returns False when this arena has no exchange."""
+    a = self.arena
+    if a.exchange is None or not (dist.is_initialized() and dist.world_size() > 1):
+      return False
+    gs = self._sync_grads()
+    ranges = self._ranges()
+    if not ranges and kind == 'adam':
+      ranges = [[0, 0]]
+    for i, (b, e) in enumerate(ranges):
+      tick = (1 if i == len(ranges) - 1 else 2) if kind == 'adam' else 0
+      a.exchange.update(kind, b, e - b, a.grad.t, a.data.t, s1.t if s1 is not None else None, s2.t if s2 is not None else None,
+                        self.lr, beta1, beta2, epsilon, t_dev, tick, gs, _st())
+    return True
 
 
 class GD(Optimizer):
@@ -213,6 +223,8 @@ class GD(Optimizer):
     super().__init__(params, lr)
 
   def step(self):
+    if self._fused_exchange('sgd'):
+      return
     gs = self._sync_grads()
     a = self.arena
     for b, e in self._ranges():
@@ -238,6 +250,8 @@ class Momentum(Optimizer):
     self._m = self.arena.state_buffer('momentum', 'momentum_grad', self._only())
 
   def step(self):
+    if self._fused_exchange('momentum', self._m, None, beta1=self.beta):
+      return
     gs = self._sync_grads()
     a = self.arena
     for b, e in self._ranges():
@@ -264,6 +278,8 @@ class RMSProp(Optimizer):
     self._r = self.arena.state_buffer('rms', 'rms_grad', self._only())
 
   def step(self):
+    if self._fused_exchange('rmsprop', self._r, None, beta1=self.beta, epsilon=self.epsilon):
+      return
     gs = self._sync_grads()
     a = self.arena
     for b, e in self._ranges():
@@ -305,6 +321,8 @@ class Adam(Optimizer):
     self._t_dev[0] = int(value)
 
   def step(self):
+    if self._fused_exchange('adam', self._m, self._v, self.beta1, self.beta2, self.epsilon, self._t_dev):
+      return
     gs = self._sync_grads()
     a = self.arena
     t_ptr = ctypes.c_void_p(self._t_dev.data_ptr())

@@ -303,7 +303,8 @@ def test_c4_gan784_vs_oracle_at_size(ng, precision):
     # Gradient tolerances (dist), measured on B200 and stated with headroom.  The generator's gradients pass through the
     # discriminator's sigmoid head, which this configuration drives into saturation (|z| ~ 10): d sigma = e^-|z| turns an
     # ABSOLUTE error of the logit into a RELATIVE error of the gradient, and the first generator weight -- noise^T . g over
-    # 8192 random-sign rows -- cancels on top of that.  fp32 mode: 2.3e-4 for that weight, <= 1.1e-5 elsewhere.  TF32 mode
+    # 8192 random-sign rows -- cancels on top of that (so does the discriminator's first weight, data^T . g: 7e-5 in fp32
+    # mode).  fp32 mode: 2.3e-4 for that weight, <= 1.1e-5 elsewhere.  TF32 mode
     # (operands rounded to 11 bits, fp32 accumulate): 1.0e-2 for that weight, <= 6e-4 elsewhere; identical with the fused
     # and the unfused kernels (tools/dbg_gan.py).
     tol = 2e-3 if precision == 'tf32' else 5e-5
@@ -324,7 +325,7 @@ def test_c4_gan784_vs_oracle_at_size(ng, precision):
     loss_d = loss_fn(model.discriminator(ng.tensor(real)), ones) + loss_fn(model.discriminator(fake), zeros)
     loss_d.backward()
     for i, (p, r) in enumerate(zip(model.parameters()[6:], ogd)):
-      assert dist(p.grad.numpy(), r) < tol, ('disc', i, dist(p.grad.numpy(), r))
+      assert dist(p.grad.numpy(), r) < (tol_w1 if i == 0 else tol), ('disc', i, dist(p.grad.numpy(), r))
     optim_d.step()
     model.generator.unfreeze()
     assert abs(float(loss_g.data) - olg) < tol * abs(olg), (float(loss_g.data), olg)
