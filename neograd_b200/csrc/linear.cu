@@ -129,18 +129,16 @@ __global__ void __launch_bounds__(256) linear_smalln_fwd_kernel(const float* __r
       is_last = atomicAdd(h.done, 1u) == gridDim.x - 1;
     }
     __syncthreads();
-    if (is_last) {      // fixed-order sum of the per-block partials: deterministic
-      if (threadIdx.x < 32) {
-        __threadfence();
-        // (at most 128 blocks: four independent loads per lane, one round trip)
-        const int nbk = (int)gridDim.x;
-        const float t0 = lane < nbk ? h.partials[lane] : 0.f, t1 = lane + 32 < nbk ? h.partials[lane + 32] : 0.f;
-        const float t2 = lane + 64 < nbk ? h.partials[lane + 64] : 0.f, t3 = lane + 96 < nbk ? h.partials[lane + 96] : 0.f;
-        float tot = warp_sum((t0 + t1) + (t2 + t3));
-        if (lane == 0) {
-          *h.loss = -h.inv_n * tot;      // loss.py:156: (-1/num_examples) * entropy
-          *h.done = 0;
-        }
+    if (is_last) {      // fixed-shape sum of the per-block partials (<= 1024 of them, four per thread): deterministic
+      __threadfence();
+      const int nbk = (int)gridDim.x, t = threadIdx.x;
+      const volatile float* pp = h.partials;     // written by other blocks of this launch
+      const float t0 = t < nbk ? pp[t] : 0.f, t1 = t + 256 < nbk ? pp[t + 256] : 0.f;
+      const float t2 = t + 512 < nbk ? pp[t + 512] : 0.f, t3 = t + 768 < nbk ? pp[t + 768] : 0.f;
+      const float tot = block_sum((t0 + t1) + (t2 + t3), red);
+      if (t == 0) {
+        *h.loss = -h.inv_n * tot;      // loss.py:156: (-1/num_examples) * entropy
+        *h.done = 0;
       }
     }
   }
@@ -190,7 +188,7 @@ __global__ void __launch_bounds__(256) linear_smalln_wgrad_kernel(const float* _
   for (int j = 0; j < KB; ++j)
 #pragma unroll
     for (int n = 0; n < NT; ++n) acc[j][n] = 0.f;
-#pragma unroll 2
+#pragma unroll 4
   for (int64_t m = tid; m < M; m += 256) {
     float u[NT];
     const float* ur = ug + m * N;
@@ -270,7 +268,7 @@ int launch_small_fwd(const float* x, const float* W, const float* b, float* z, f
   if (rc) return rc;
   const int threads = 256, rows_per_cta = threads / 32;
   int64_t grid = ceil_div<int64_t>(M, rows_per_cta);
-  const int64_t cap = HEAD ? 128 : 2 * kNumSMs;              // (HEAD: the last block sums one partial per block)
+  const int64_t cap = 4 * kNumSMs;                           // rows are independent: many warps in flight hide the row loads
   if (grid > cap) grid = cap;
   kern<<<(int)grid, threads, smem, st>>>(x, W, b, z, a, act, alpha, M, (int)N, (int)K, h);
   NGB_LAUNCH_CHECK();
