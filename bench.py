@@ -440,6 +440,20 @@ class LeNetWorkload:
     model, optim, loss_fn, train_step = self.model, self.optim, self.loss_fn, self.train_step
     return lambda: (train_step(model, optim, loss_fn, X, Y),)
 
+  E2E_INPUT = 'uint8 28x28 images + int32 class ids in pinned host memory; normalisation and one-hot on the device (nn.DeviceLoader)'
+
+  def e2e_loader(self, nbatches, rank):
+    """End-to-end input: images as they sit on disk / in host RAM (uint8 pixels, integer class ids), streamed through the
+    library's DeviceLoader (pinned H2D on a copy stream, double buffered; cast + normalise + one-hot as device kernels)."""
+    rng = np.random.default_rng(1000 + rank)
+    shape = (28, 28) if self.name[-1] == 'a' else (1, 28, 28)
+    imgs = rng.integers(0, 256, (nbatches * self.batch,) + shape, dtype=np.uint8)
+    labels = rng.integers(0, 10, nbatches * self.batch).astype(np.int32)
+    return self.ng.nn.DeviceLoader(imgs, labels, self.batch, normalize=(1.0 / 73.9, -127.5 / 73.9), num_classes=10)
+
+  def make_e2e_step(self, slot_tensors):
+    return self.make_step(slot_tensors)
+
 
 class GanWorkload:
   """examples/gans/basic.ipynb cells 9-10 at 784-512-256: one generator step + one discriminator step per iteration."""
@@ -464,6 +478,28 @@ class GanWorkload:
     REAL, NG, ND = tensors
     it, model, og, od, lf, ones, zeros = self.gan_iteration, self.model, self.og, self.od, self.loss_fn, self.ones, self.zeros
     return lambda: it(model, og, od, lf, NG, ND, REAL, ones, zeros)
+
+  E2E_INPUT = ('uint8 784-d real rows in pinned host memory, normalised on the device (nn.DeviceLoader); the two noise batches are '
+               'drawn on the device inside the step (nn.randn, Philox), as np.random.randn draws them on the host in the notebook')
+
+  def e2e_loader(self, nbatches, rank):
+    rng = np.random.default_rng(1000 + rank)
+    rows = rng.integers(0, 256, (nbatches * self.batch, 784), dtype=np.uint8)
+    return self.ng.nn.DeviceLoader(rows, None, self.batch, normalize=(1.0 / 73.9, -127.5 / 73.9))
+
+  def make_e2e_step(self, slot_tensors):
+    import torch
+    ng = self.ng
+    REAL = slot_tensors[0]
+    NG, ND = ng.tensor(np.zeros((self.batch, 784))), ng.tensor(np.zeros((self.batch, 784)))
+    counter = torch.zeros(1, dtype=torch.int32, device='cuda')
+    inner = self.make_step((REAL, NG, ND))
+
+    def step():
+      ng.nn.randn(None, seed=11, out=NG, counter=counter)       # fresh noise on every replay: the counter lives on the device
+      ng.nn.randn(None, seed=12, out=ND, counter=counter)
+      return inner()
+    return step
 
 
 def make_workload(ng, name, batch, rank):
@@ -551,58 +587,38 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
   eager_ms = h.max_over_ranks(h.timed(step, args.steps))
   out['eager'] = {'value': total_samples / (eager_ms * 1e-3), 'unit': 'samples/s', 'ms_per_step': eager_ms / args.steps}
 
-  # ---- e2e: host inputs -> pinned H2D copy -> step -> D2H loss, wall clock.  Double buffered at the INPUT level: two
-  # captured steps over the same model / optimizer, each reading its own input buffer (one contiguous buffer per batch, so
-  # a batch is ONE pinned H2D copy).  The copy of batch i+1 (copy stream) overlaps step i; every step copies its full
-  # batch from host memory and reads its loss(es) back; the loss of step i is consumed on the host before step i+2 is
-  # issued.
-  sizes = [a.size for a in wl.host_inputs]
-  total = int(sum(sizes))
-  xyh = torch.empty(total, dtype=torch.float32).pin_memory()
-  off = 0
-  for a in wl.host_inputs:
-    xyh[off:off + a.size].copy_(torch.from_numpy(np.ascontiguousarray(a)).view(-1))
-    off += a.size
-  bufs = [torch.empty(total, device='cuda', dtype=torch.float32) for _ in range(2)]
-  inputs = []
-  for bb in bufs:
-    off, ts = 0, []
-    for a in wl.host_inputs:
-      ts.append(ng.tensor(DeviceArray(bb[off:off + a.size].view(a.shape))))
-      off += a.size
-    inputs.append(ts)
-    bb.copy_(xyh)
-  steps2 = [CapturedStep(wl.make_step(ts), warmup=2) for ts in inputs]
+  # ---- e2e: host inputs -> pinned H2D copy -> on-device preparation -> step -> D2H loss, wall clock, through the library's
+  # public input API (nn.DeviceLoader): the batch crosses PCIe in its source format and is expanded by device kernels; the
+  # copy of batch i+1 (copy stream) overlaps step i.  Double buffered at the INPUT level: one captured step per loader slot
+  # over the same model / optimizer; every step copies its full batch from host memory and reads its loss(es) back; the
+  # loss of step i is consumed on the host before step i+2 is issued.
+  loader = wl.e2e_loader(8, rank)
+  steps2 = [CapturedStep(wl.make_e2e_step([t_ for t_ in loader.slots[i] if t_ is not None]), warmup=2) for i in range(2)]
+  e2e_launches = steps2[0].launches + (1 if loader._needs_prep else 0) + (1 if loader._labels is not None else 0)
   n_loss = len(steps2[0].result)
   loss_host = [torch.empty(n_loss, dtype=torch.float32).pin_memory() for _ in range(2)]
   loss_dev = [torch.empty(n_loss, device='cuda', dtype=torch.float32) for _ in range(2)]
-  copy_stream = torch.cuda.Stream()
-  h2d_done = [torch.cuda.Event() for _ in range(2)]
   step_done = [torch.cuda.Event() for _ in range(2)]
   main = torch.cuda.current_stream()
 
-  def issue_h2d(i):
-    with torch.cuda.stream(copy_stream):
-      copy_stream.wait_event(step_done[i & 1])          # the step that last read this input buffer has finished
-      bufs[i & 1].copy_(xyh, non_blocking=True)
-      h2d_done[i & 1].record(copy_stream)
-
   def e2e_run(nsteps):
-    for b in range(2):
-      step_done[b].record(main)
-    issue_h2d(0)
+    loader.reset()
     for i in range(nsteps):
-      if i + 1 < nsteps:
-        issue_h2d(i + 1)
-      main.wait_event(h2d_done[i & 1])
-      losses = steps2[i & 1]()
-      step_done[i & 1].record(main)
+      item = loader.next()
+      if item is None:
+        loader.reset()
+        item = loader.next()
+      slot = item[2]
+      losses = steps2[slot]()
+      loader.release(slot)
+      b_ = i & 1
       if n_loss == 1:
-        loss_host[i & 1].copy_(losses[0].data.t.view(1), non_blocking=True)
+        loss_host[b_].copy_(losses[0].data.t.view(1), non_blocking=True)
       else:
         for j, l in enumerate(losses):
-          loss_dev[i & 1][j:j + 1].copy_(l.data.t.view(1), non_blocking=True)
-        loss_host[i & 1].copy_(loss_dev[i & 1], non_blocking=True)
+          loss_dev[b_][j:j + 1].copy_(l.data.t.view(1), non_blocking=True)
+        loss_host[b_].copy_(loss_dev[b_], non_blocking=True)
+      step_done[b_].record(main)
       if i >= 1:
         step_done[(i - 1) & 1].synchronize()              # loss of the previous step is now on the host
         float(loss_host[(i - 1) & 1][0])
@@ -644,17 +660,19 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
 
   # the copy this pipeline hides behind the step (measured warm, right after the pipelined loop)
   h2d_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-  with torch.cuda.stream(copy_stream):
+  src_x = loader._x_all[:loader.batch_size] if loader._whole else loader._pin_x[0]
+  with torch.cuda.stream(loader._copy_stream):
     for _ in range(3):
-      bufs[0].copy_(xyh, non_blocking=True)
-    h2d_ev[0].record(copy_stream)
+      loader._raw_x[0].copy_(src_x, non_blocking=True)
+    h2d_ev[0].record(loader._copy_stream)
     for _ in range(10):
-      bufs[0].copy_(xyh, non_blocking=True)
-    h2d_ev[1].record(copy_stream)
+      loader._raw_x[0].copy_(src_x, non_blocking=True)
+    h2d_ev[1].record(loader._copy_stream)
   torch.cuda.synchronize()
   h2d_ms = h2d_ev[0].elapsed_time(h2d_ev[1]) / 10
-  out['e2e'] = {'value': total_samples / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(4 * total),
+  out['e2e'] = {'value': total_samples / e2e_s, 'unit': 'samples/s', 'h2d_bytes_per_step': int(loader.bytes_per_batch),
                 'd2h_bytes_per_step': 4 * n_loss, 'ms_per_step': e2e_s / args.steps * 1e3, 'last_loss': last_loss,
+                'input': wl.E2E_INPUT, 'gpu_launches_per_step': e2e_launches,
                 'method': f'median of {E2E_REPEATS} wall-clock measurements of {args.steps} steps each',
                 'h2d_ms_per_batch': h2d_ms,   # PCIe time of one batch alone: the floor of the pipelined end-to-end step
                 'ms_per_step_all': [t / args.steps * 1e3 for t in e2e_samples]}

@@ -255,6 +255,19 @@ int ngb_momentum_step(float* p, const float* g, float* m, int64_t n, double lr, 
 int ngb_rmsprop_step(float* p, const float* g, float* r, int64_t n, double lr, double beta, double epsilon,
                      double grad_scale, ngb_stream_t stream);                               /* optim.py:112-118, 134-140 */
 
+/* ---- input pipeline on the device (new) -----------------------------------------------------------
+ * A batch crosses PCIe in its source format (uint8 pixels, int32 class ids) and is expanded in HBM. */
+/* dst[i] = src[i] * scale + shift  (e.g. scale = 1/(255 std), shift = -mean/std) */
+int ngb_prep_u8_affine(const uint8_t* src, float* dst, int64_t n, float scale, float shift, ngb_stream_t stream);
+/* per-row standardisation (x - mean) / std, population std: examples/digits.ipynb cell 5; src is uint8 or float32 */
+int ngb_prep_standardize_rows(const void* src, int src_is_u8, float* dst, int64_t rows, int64_t cols, ngb_stream_t stream);
+/* dst (rows, classes) = np.eye(classes)[labels]: examples/digits.ipynb cell 6 */
+int ngb_prep_one_hot(const int32_t* labels, float* dst, int64_t rows, int64_t classes, ngb_stream_t stream);
+/* standard-normal fill (Philox4x32-10 + Box-Muller; the role of np.random.randn in examples/gans/basic.ipynb cell 9).
+ * Element i depends only on (seed, call offset, i).  offset_dev != NULL: the offset is read from -- and then advanced in --
+ * device memory (a captured graph draws fresh noise on every replay); else `offset` is used. */
+int ngb_randn(float* dst, int64_t n, uint64_t seed, uint32_t* offset_dev, uint32_t offset, ngb_stream_t stream);
+
 /* ---- data parallel over NVLink peer memory (new) -------------------------------------------------------
  * The gradient exchange FUSED with the optimizer update (one launch per optimizer step and parameter range; replaces the
  * reference's single-process optim.py:42-47 / 63-92 / 112-140 / 168-197 under data parallelism).  Every rank owns a receive

@@ -6,7 +6,7 @@ torch.distributed (plumbing); every arithmetic kernel on the hot path lives in t
 """
 import ctypes
 import os
-from ctypes import c_double, c_float, c_int, c_int64, c_uint32, c_void_p, c_char_p, POINTER
+from ctypes import c_double, c_float, c_int, c_int64, c_uint32, c_uint64, c_void_p, c_char_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, 'lib', 'libngb200.so')
@@ -56,6 +56,10 @@ SIGNATURES = {
   'ngb_set_default_engine': ([c_int], c_int),
   'ngb_set_lane': ([c_int], c_int),
   'ngb_set_corun': ([c_int], c_int),
+  'ngb_prep_u8_affine': ([_P, _P, c_int64, c_float, c_float, _S], c_int),
+  'ngb_prep_standardize_rows': ([_P, c_int, _P, c_int64, c_int64, _S], c_int),
+  'ngb_prep_one_hot': ([_P, _P, c_int64, c_int64, _S], c_int),
+  'ngb_randn': ([_P, c_int64, c_uint64, _P, c_uint32, _S], c_int),
   'ngb_xgpu_exchange_update': ([_P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int64, _P, _P, _P, _P, _P, c_int] +
                                [c_double] * 4 + [_P, c_int, c_double, c_double, _S], c_int),
   'ngb_xgpu_blocks': ([c_int64, c_int], c_int),
