@@ -593,8 +593,18 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
   # over the same model / optimizer; every step copies its full batch from host memory and reads its loss(es) back; the
   # loss of step i is consumed on the host before step i+2 is issued.
   loader = wl.e2e_loader(8, rank)
-  steps2 = [CapturedStep(wl.make_e2e_step([t_ for t_ in loader.slots[i] if t_ is not None]), warmup=2) for i in range(2)]
-  e2e_launches = steps2[0].launches + (1 if loader._needs_prep else 0) + (1 if loader._labels is not None else 0)
+  for _ in range(2):                # both slots hold a real batch before the steps over them are captured
+    loader.release(loader.next()[2])
+  torch.cuda.synchronize()
+
+  def with_prepare(slot, inner):
+    def fn():
+      loader.prepare(slot)          # cast + normalise + one-hot of the freshly copied batch: part of the captured step
+      return inner()
+    return fn
+  steps2 = [CapturedStep(with_prepare(i, wl.make_e2e_step([t_ for t_ in loader.slots[i] if t_ is not None])), warmup=2)
+            for i in range(2)]
+  e2e_launches = steps2[0].launches
   n_loss = len(steps2[0].result)
   loss_host = [torch.empty(n_loss, dtype=torch.float32).pin_memory() for _ in range(2)]
   loss_dev = [torch.empty(n_loss, device='cuda', dtype=torch.float32) for _ in range(2)]
@@ -604,10 +614,10 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
   def e2e_run(nsteps):
     loader.reset()
     for i in range(nsteps):
-      item = loader.next()
+      item = loader.next(prepare=False)
       if item is None:
         loader.reset()
-        item = loader.next()
+        item = loader.next(prepare=False)
       slot = item[2]
       losses = steps2[slot]()
       loader.release(slot)

@@ -52,7 +52,7 @@ class DeviceLoader:
     B.ensure_runtime()
     inputs = np.asarray(inputs)
     self.n = inputs.shape[0]
-    self.batch_size = int(batch_size or self.n)
+    self.batch_size = self.n if batch_size is None else int(batch_size)
     if self.batch_size <= 0 or self.batch_size > self.n:
       raise ValueError("Batch size must be between 1 and the number of examples")
     self.sample_shape = tuple(inputs.shape[1:])
@@ -148,11 +148,11 @@ class DeviceLoader:
     self._issued.append((slot, rows))
     return True
 
-  def _prepare(self, slot, rows):
-    """On the consumer's stream: wait for the slot's copy, expand the raw batch into the fp32 tensors."""
-    t = torch()
-    main = t.cuda.current_stream()
-    main.wait_event(self._copied[slot])
+  def prepare(self, slot, rows=None):
+    """Expands the slot's raw batch (as copied from the host) into its fp32 tensors: the normalisation / one-hot kernels,
+    on the current stream.  `next()` calls it; a CAPTURED step calls it itself as its first statement (the slot's
+    buffers are fixed, so the kernels replay with the graph) and asks `next(prepare=False)` for the batches."""
+    rows = self.batch_size if rows is None else rows
     st = _st()
     if self._needs_prep:
       src = ctypes.c_void_p(self._raw_x[slot].data_ptr())
@@ -175,15 +175,18 @@ class DeviceLoader:
     """Start a new epoch (pending copies are dropped)."""
     self._cursor, self._issued = 0, []
 
-  def next(self):
+  def next(self, prepare=True):
     """-> (X, Y, slot) of the next batch, or None at the end of the epoch.  The batch after it is already on its way.
     X / Y stay valid until the batch after the NEXT one is requested; call `release(slot)` once the work that reads the
-    slot has been enqueued (iteration does it for you)."""
+    slot has been enqueued (iteration does it for you).  prepare=False: only make the current stream wait for the slot's
+    host -> device copy (the caller's captured step runs `prepare(slot)` itself)."""
     if not self._issued and not self._stage():
       return None
     slot, rows = self._issued.pop(0)
     self._stage()                                            # prefetch: overlaps this batch's compute
-    self._prepare(slot, rows)
+    torch().cuda.current_stream().wait_event(self._copied[slot])
+    if prepare:
+      self.prepare(slot, rows)
     X, Y = self.slots[slot]
     if rows < self.batch_size:
       X, Y = X[0:rows], (Y[0:rows] if Y is not None else None)
