@@ -143,17 +143,35 @@ def ensure_runtime():
   """Allocates the library's scratch arena once (must happen before any CUDA-graph capture)."""
   global _runtime_ready
   if not _runtime_ready:
-    import torch
+    torch = _t()
     if not torch.cuda.is_available():
       raise NgbError("neograd_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
     check(lib.ngb_init(0))
     _runtime_ready = True
 
 
+_torch = None
+_raw_stream = None
+_dev_index = None
+
+
+def _t():
+  global _torch
+  if _torch is None:
+    import torch as _tm
+    _torch = _tm
+  return _torch
+
+
 def stream():
-  """cudaStream_t of torch's current stream (so torch.cuda.graph / stream contexts apply to our launches)."""
-  import torch
-  return torch._C._cuda_getCurrentRawStream(torch.cuda.current_device())
+  """cudaStream_t of torch's current stream (so torch.cuda.graph / stream contexts apply to our launches).  One process
+  drives one GPU: the device index is looked up once."""
+  global _raw_stream, _dev_index
+  if _raw_stream is None:
+    torch = _t()
+    _raw_stream = torch._C._cuda_getCurrentRawStream
+    _dev_index = torch.cuda.current_device()
+  return _raw_stream(_dev_index)
 
 
 class _Lanes:
@@ -178,7 +196,7 @@ class _Lanes:
     return self.n > 0
 
   def _init(self):
-    import torch
+    torch = _t()
     ensure_runtime()
     self.streams = {}
     for lane in range(1, self.n + 1):
@@ -192,7 +210,7 @@ class _Lanes:
     """Event on the current (main) stream: everything issued so far -- in particular the gradient of the tensor the
     engine has just finished -- is complete.  Side-lane work that consumes that gradient waits on THIS event, not on the
     main stream's tail at the time it is issued (leaves are visited last, long after their upstream gradient exists)."""
-    import torch
+    torch = _t()
     ev = torch.cuda.Event()
     ev.record()
     return ev
@@ -203,7 +221,7 @@ class _Lanes:
     return la is None or lb is None or la == lb
 
   def run(self, key, fn, keep, ready=None, corun=True, also=None):
-    import torch
+    torch = _t()
     if self.streams is None or len(self.streams) != self.n:
       self._init()
     lane = self.assign.get(id(key))
@@ -222,10 +240,12 @@ class _Lanes:
       side.wait_stream(torch.cuda.current_stream())
     prev = lib.ngb_set_lane(lane)
     prev_corun = lib.ngb_set_corun(1 if corun else 0)
+    main = torch.cuda.current_stream()
     try:
-      with torch.cuda.stream(side):
-        fn()
+      torch.cuda.set_stream(side)            # (the `with torch.cuda.stream(...)` context manager costs several us per use)
+      fn()
     finally:
+      torch.cuda.set_stream(main)
       lib.ngb_set_lane(prev)
       lib.ngb_set_corun(prev_corun)
     self.used.add(lane)
@@ -234,7 +254,7 @@ class _Lanes:
   def join(self):
     if not self.used:
       return
-    import torch
+    torch = _t()
     main = torch.cuda.current_stream()
     for lane in sorted(self.used):
       main.wait_stream(self.streams[lane])
@@ -274,7 +294,7 @@ class profile_calls:
           'ngb_debug_wgrad_layout', 'ngb_conv_relu_pool_fwd_serves', 'ngb_conv_wbgrad_pooled_is_fused', 'ngb_linear_softmax_ce_serves')
 
   def __enter__(self):
-    import torch
+    torch = _t()
     self.records = []
     self._saved = {}
     for name in SIGNATURES:
@@ -299,7 +319,7 @@ class profile_calls:
 
   def summary(self):
     """{name: {'calls': n, 'ms': total, 'items': [(args, ms), ...]}} sorted by total time."""
-    import torch
+    torch = _t()
     torch.cuda.synchronize()
     out = {}
     for name, args, e0, e1 in self.records:

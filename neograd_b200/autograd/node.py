@@ -53,7 +53,7 @@ class Node:
 
   def backward(self, retain_graph):
     """node.py:53-86: backward may start at any intermediate node; tensors downstream of it take no part."""
-    from .utils import get_graph
+    from .utils import get_graph   # (cheap: once per backward)
     graph = get_graph()
     graph.reset_visited()
     self.visit_all_children()

@@ -11,7 +11,8 @@ Anything the fused kernels do not cover (operands that are not 2-D, a bias that 
 `dot(...) + b` path in nn/layers/misc.py."""
 from ... import _backend as B
 from ... import device as D
-from ..tensor import GradFn
+from ..tensor import GradFn, Tensor
+from ..utils import get_graph
 from .operation import Operation
 
 
@@ -69,7 +70,6 @@ class LinearDgradPending:
 
 class Linear(Operation):
   def forward(self, inputs, weights, bias):
-    from ..utils import get_graph
     inputs, weights, bias = self.get_tensors(inputs, weights, bias)
     x, W, b = inputs.data, weights.data, bias.data
     pend = LinearPending(x, W, b, get_graph().track)
@@ -121,7 +121,6 @@ class Linear(Operation):
 
 def fusable(inputs, weights, bias):
   """Whether `dot(inputs, weights) + bias` is the plain Linear case the fused kernels serve."""
-  from ..tensor import Tensor
   if not D.FUSED_LINEAR or not isinstance(inputs, Tensor) or inputs._data is None:
     return False
   xs, ws, bs = inputs.shape, weights.shape, bias.shape

@@ -9,11 +9,22 @@
 import numpy as np
 
 from ..node import Node
+from ..utils import get_graph
+
+_TENSOR = None
+
+
+def _tensor_cls():
+  global _TENSOR
+  if _TENSOR is None:
+    from ..tensor import Tensor
+    _TENSOR = Tensor
+  return _TENSOR
 
 
 class Operation:
   def process_operands(self, operands):
-    from ..tensor import Tensor
+    Tensor = _tensor_cls()
     return tuple(o if isinstance(o, Tensor) else Tensor(o) for o in operands)   # operation.py:13-27
 
   def get_tensors(self, *operands):
@@ -39,8 +50,7 @@ class Operation:
 
   def get_result_tensor(self, result, *tensors):
     """operation.py:83-109 (without the object-dtype round trip: `result` already lives on the device)."""
-    from ..tensor import Tensor
-    from ..utils import get_graph
+    Tensor = _tensor_cls()
     graph = get_graph()
     result_tensor = Tensor(result, self.result_requires_grad(tensors))
     if graph.track:

@@ -14,7 +14,7 @@ import numpy as np
 
 from .._backend import lanes as _lanes
 from ..device import ConstScalar, DeviceArray
-from .utils import process_data, unbroadcast_data
+from .utils import get_graph, process_data, unbroadcast_data
 
 
 class GradFn:
@@ -138,7 +138,6 @@ class Tensor:
     """tensor.py:44-73."""
     if not self.requires_grad:
       raise ValueError("Only tensors who requires_grad can call backward")
-    from .utils import get_graph
     graph = get_graph()
     if type(upper_grad) in (int, float):
       if self.shape != ():
@@ -157,8 +156,7 @@ class Tensor:
     try:
       node.backward(retain_graph)
     finally:
-      from .._backend import lanes
-      lanes.join()               # weight / bias gradients issued on side streams are complete for whatever follows
+      _lanes.join()               # weight / bias gradients issued on side streams are complete for whatever follows
     if not retain_graph:
       graph.reset_graph()
 
@@ -170,7 +168,6 @@ class Tensor:
     produced it (weights, biases) are issued right away on side streams -- nothing else in the pass consumes them, so
     they run beside the data-gradient chain instead of after it.  The leaf's own visit then finds that contribution
     already accumulated."""
-    from .utils import get_graph
     graph = get_graph()
     for child in node.children:
       if self.requires_grad and calculate_grads:

@@ -3,6 +3,7 @@ finite-difference gradient checking."""
 import numpy as np
 
 from ..device import DeviceArray, reduce_sum
+from .graph import Graph
 
 
 def process_data(data):
@@ -39,25 +40,29 @@ def unbroadcast_data(data, orig_data_shape, broadcasted_shape):
   return reduce_sum(data, axes)
 
 
+_GLOBAL_GRAPH = None     # neograd_b200._NG_GRAPH, looked up once (this function runs several times per op)
+
+
 def get_graph():
   """utils.py:80-93: the graph of the innermost `new_graph()` block, else the global one."""
-  from .graph import Graph
-  if Graph.graph is None:
+  g = Graph.graph
+  if g is not None:
+    return g
+  global _GLOBAL_GRAPH
+  if _GLOBAL_GRAPH is None:
     from .. import _NG_GRAPH
-    return _NG_GRAPH
-  return Graph.graph
+    _GLOBAL_GRAPH = _NG_GRAPH
+  return _GLOBAL_GRAPH
 
 
 class new_graph:
   """utils.py:96-110."""
 
   def __enter__(self):
-    from .graph import Graph
     self._prev = Graph.graph
     Graph.graph = Graph()
 
   def __exit__(self, exc_type, exc_value, exc_traceback):
-    from .graph import Graph
     Graph.graph = self._prev if getattr(self, '_prev', None) is not None else None
 
 

@@ -26,9 +26,17 @@ def torch():
   return _torch
 
 
+_EMPTY = None      # (torch.empty, device, dtype) resolved once: the per-op result allocation is on the eager hot path
+
+
 def _alloc(shape):
-  B.ensure_runtime()
-  return torch().empty(tuple(int(s) for s in shape), device='cuda', dtype=torch().float32)
+  global _EMPTY
+  if _EMPTY is None:
+    B.ensure_runtime()
+    t = torch()
+    _EMPTY = (t.empty, t.device('cuda', t.cuda.current_device()), t.float32)
+  empty, dev, f32 = _EMPTY
+  return empty(tuple(shape), device=dev, dtype=f32)
 
 
 def _ptr(t):
@@ -43,11 +51,12 @@ _HOST_TYPES = (int, float, list, np.ndarray)
 
 
 class DeviceArray:
-  __slots__ = ('t',)
+  __slots__ = ('t', '_shp')
   __array_priority__ = 1000   # ndarray (op) DeviceArray -> our reflected dunder
 
   def __init__(self, t):
     self.t = t   # torch.Tensor, cuda, float32, contiguous
+    self._shp = None
 
   # ------------------------------------------------------------------ construction
   @staticmethod
@@ -74,7 +83,10 @@ class DeviceArray:
   # ------------------------------------------------------------------ metadata
   @property
   def shape(self):
-    return tuple(self.t.shape)
+    s = self._shp
+    if s is None:
+      s = self._shp = tuple(self.t.shape)     # (the buffer of a DeviceArray is never re-shaped in place)
+    return s
 
   @property
   def ndim(self):
