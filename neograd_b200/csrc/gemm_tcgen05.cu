@@ -68,10 +68,13 @@ constexpr uint32_t kSpinNone = 0;
 // (the upstream gradient) -- by multiplying every B stage with an all-ones A tile into a second accumulator (every row of
 // which is the column sum).  Costs one more UMMA per k-step on the CTAs of the first row of output tiles, 16 KB of shared
 // memory for the ones tile and twice the TMEM columns.
-template <int BLOCK_N, bool COLSUM = false>
+// CTAS = 2: a CTA pair (cluster of 2, tcgen05 cta_group::2) computes a 256 x BLOCK_N tile; each CTA stages its own 128 rows
+// of A and HALF of the B tile (BLOCK_N / 2 columns), the leader issues the M = 256 MMAs, each CTA's TMEM receives its 128
+// rows of the accumulator and each CTA runs its own epilogue.
+template <int BLOCK_N, bool COLSUM = false, int CTAS = 1>
 struct Cfg {
   static constexpr int kABytes = BLOCK_M * BLOCK_K * 4;
-  static constexpr int kBBytes = BLOCK_N * BLOCK_K * 4;
+  static constexpr int kBBytes = (BLOCK_N / CTAS) * BLOCK_K * 4;
   static constexpr int kStageBytes = kABytes + kBBytes;
   static constexpr int kOnesBytes = COLSUM ? kABytes : 0;
   static constexpr int kRing = 192 * 1024 - kOnesBytes;
@@ -156,11 +159,17 @@ __device__ __forceinline__ void epi_mask4(int act, float alpha, float* v, const 
 }
 
 // A_MN / B_MN: operand is MN-major in global memory (1) or K-major (0).
-template <int BLOCK_N, int A_MN, int B_MN, bool COLSUM = false>
+template <int BLOCK_N, int A_MN, int B_MN, bool COLSUM = false, int CTAS = 1>
 __global__ void __launch_bounds__(kThreads, 1)
 gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_constant__ CUtensorMap tmap_b,
                  const __grid_constant__ CUtensorMap tmap_c, const __grid_constant__ CUtensorMap tmap_c2, const GemmArgs g) {
-  using C_ = Cfg<BLOCK_N, COLSUM>;
+  using C_ = Cfg<BLOCK_N, COLSUM, CTAS>;
+  constexpr bool PAIR = CTAS == 2;
+  static_assert(!(PAIR && COLSUM), "the ones-tile column sum is a single-CTA feature");
+  const uint32_t cta_rank = PAIR ? cluster_ctarank() : 0u;     // 0 = leader (issues the MMAs)
+  const int unit = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;     // persistent work unit: a CTA, or a CTA pair
+  const int num_units = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  constexpr int TILE_M = BLOCK_M * CTAS;
   constexpr int kStages = C_::kStages;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -181,67 +190,85 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     prefetch_tmap(&tmap_a);
     prefetch_tmap(&tmap_b);
     for (int s = 0; s < kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(&tmem_full[s], 1); mbar_init(&tmem_empty[s], 4 * CTAS); }   // (pair: both CTAs' epilogue warps)
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, C_::kTmemCols);
+  if (warp == 1) {
+    if (PAIR) tmem_alloc_2cta(tmem_slot, C_::kTmemCols);
+    else tmem_alloc(tmem_slot, C_::kTmemCols);
+  }
   if (COLSUM) {
     for (int i = threadIdx.x; i < C_::kOnesBytes / 16; i += kThreads)
       reinterpret_cast<float4*>(smem_ones)[i] = make_float4(1.f, 1.f, 1.f, 1.f);
     fence_proxy_async();       // generic-proxy writes -> visible to the tensor core's async-proxy reads
   }
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // the peer's barriers exist before anything signals them
+  else __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int num_work = g.tiles_m * g.tiles_n * g.splits;
+  const int num_work = g.tiles_m * g.tiles_n * g.splits;     // (pair: tiles_m counts 256-row tiles)
 
   if (warp == 0) {
     // ===================================================================== TMA producer
     if (lane == 0) {
       uint32_t it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x) {
+      for (int w = unit; w < num_work; w += num_units) {
         const int split = w % g.splits, tile = w / g.splits;
-        const int m0 = (tile % g.tiles_m) * BLOCK_M, n0 = (tile / g.tiles_m) * BLOCK_N;
+        // this CTA's 128 rows of A, and (pair) its half of the B tile's columns
+        const int m0 = (tile % g.tiles_m) * TILE_M + (int)cta_rank * BLOCK_M;
+        const int n0 = (tile / g.tiles_m) * BLOCK_N + (int)cta_rank * (BLOCK_N / CTAS);
+        constexpr int BN_LOAD = BLOCK_N / CTAS;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.k_blocks, kb0 + g.kb_per_split);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % kStages;
           const uint32_t ph = (it / kStages) & 1;
           mbar_wait(&empty[s], ph ^ 1);
-          mbar_arrive_expect_tx(&full[s], C_::kStageBytes);
+          // (pair: the leader's barrier counts the bytes of both CTAs' loads)
+          if (cta_rank == 0) mbar_arrive_expect_tx(&full[s], C_::kStageBytes * CTAS);
           uint8_t* sa = smem_a + s * C_::kABytes;
           uint8_t* sb = smem_b + s * C_::kBBytes;
           const int k0 = kb * BLOCK_K;
           if (A_MN) {
             // global dims {M, K}: one {32 x 32} box per 32-wide M chunk; chunk c lands at sa + c*4096
             if (g.a_3d) {
-              tma_load_3d(sa, &tmap_a, &full[s], 0, k0, m0 / 32);
+              if (PAIR) tma_load_3d_2cta(sa, &tmap_a, &full[s], 0, k0, m0 / 32);
+              else tma_load_3d(sa, &tmap_a, &full[s], 0, k0, m0 / 32);
             } else {
 #pragma unroll
-              for (int c = 0; c < BLOCK_M / 32; ++c) tma_load_2d(sa + c * 4096, &tmap_a, &full[s], m0 + c * 32, k0);
+              for (int c = 0; c < BLOCK_M / 32; ++c) {
+                if (PAIR) tma_load_2d_2cta(sa + c * 4096, &tmap_a, &full[s], m0 + c * 32, k0);
+                else tma_load_2d(sa + c * 4096, &tmap_a, &full[s], m0 + c * 32, k0);
+              }
             }
           } else {
-            tma_load_2d(sa, &tmap_a, &full[s], k0, m0);  // global dims {K, M}: box {32, 128}
+            if (PAIR) tma_load_2d_2cta(sa, &tmap_a, &full[s], k0, m0);
+            else tma_load_2d(sa, &tmap_a, &full[s], k0, m0);  // global dims {K, M}: box {32, 128}
           }
           if (B_MN) {
             if (g.b_3d) {
-              tma_load_3d(sb, &tmap_b, &full[s], 0, k0, n0 / 32);
+              if (PAIR) tma_load_3d_2cta(sb, &tmap_b, &full[s], 0, k0, n0 / 32);
+              else tma_load_3d(sb, &tmap_b, &full[s], 0, k0, n0 / 32);
             } else {
 #pragma unroll
-              for (int c = 0; c < BLOCK_N / 32; ++c) tma_load_2d(sb + c * 4096, &tmap_b, &full[s], n0 + c * 32, k0);
+              for (int c = 0; c < BN_LOAD / 32; ++c) {
+                if (PAIR) tma_load_2d_2cta(sb + c * 4096, &tmap_b, &full[s], n0 + c * 32, k0);
+                else tma_load_2d(sb + c * 4096, &tmap_b, &full[s], n0 + c * 32, k0);
+              }
             }
           } else {
-            tma_load_2d(sb, &tmap_b, &full[s], k0, n0);
+            if (PAIR) tma_load_2d_2cta(sb, &tmap_b, &full[s], k0, n0);
+            else tma_load_2d(sb, &tmap_b, &full[s], k0, n0);
           }
         }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc_tf32(BLOCK_M, BLOCK_N, A_MN, B_MN);
+    if (lane == 0 && cta_rank == 0) {
+      constexpr uint32_t idesc = make_idesc_tf32(TILE_M, BLOCK_N, A_MN, B_MN);
       // K-major SW128: 8-row groups 1024 B apart (SBO); LBO unused.  MN-major tf32 must use the 32-byte-atom variant of
       // the 128B swizzle (tools/tc_probe.cu measured every other encoding to give zeros or garbage): 32-element MN
       // chunks 4096 B apart (LBO), 4-row K groups 512 B apart (SBO); one UMMA_K = 8 K-rows = 1024 B.
@@ -250,7 +277,7 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
       constexpr uint32_t a_kstep = A_MN ? 1024 : UMMA_K * 4;  // bytes to advance the start address per UMMA_K
       constexpr uint32_t b_kstep = B_MN ? 1024 : UMMA_K * 4;
       uint32_t it = 0, tile_it = 0;
-      for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+      for (int w = unit; w < num_work; w += num_units, ++tile_it) {
         const int split = w % g.splits;
         const int kb0 = split * g.kb_per_split;
         const int kb1 = min(g.k_blocks, kb0 + g.kb_per_split);
@@ -269,15 +296,21 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
           const uint32_t b_addr = smem_u32(smem_b + s * C_::kBBytes);
 #pragma unroll
           for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-            umma_tf32(d_tmem, smem_desc(adesc_base, a_addr + k * a_kstep), smem_desc(bdesc_base, b_addr + k * b_kstep),
-                      idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            if (PAIR)
+              umma_tf32_2cta(d_tmem, smem_desc(adesc_base, a_addr + k * a_kstep), smem_desc(bdesc_base, b_addr + k * b_kstep),
+                             idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            else
+              umma_tf32(d_tmem, smem_desc(adesc_base, a_addr + k * a_kstep), smem_desc(bdesc_base, b_addr + k * b_kstep),
+                        idesc, (kb > kb0 || k > 0) ? 1u : 0u);
             if (COLSUM && do_colsum)
               umma_tf32(d_tmem + BLOCK_N, smem_desc(adesc_base, ones_addr + k * a_kstep),
                         smem_desc(bdesc_base, b_addr + k * b_kstep), idesc, (kb > kb0 || k > 0) ? 1u : 0u);
           }
-          umma_commit(&empty[s]);  // frees the smem slot once these MMAs have read it
+          if (PAIR) umma_commit_2cta(&empty[s], 0b11);   // frees the slot in BOTH CTAs once these MMAs have read it
+          else umma_commit(&empty[s]);                    // frees the smem slot once these MMAs have read it
         }
-        umma_commit(&tmem_full[acc]);  // accumulator complete
+        if (PAIR) umma_commit_2cta(&tmem_full[acc], 0b11);
+        else umma_commit(&tmem_full[acc]);  // accumulator complete
       }
     }
     __syncwarp();
@@ -287,9 +320,9 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
     const int et = (warp - 2) * 32 + lane;
     uint32_t tile_it = 0, chunk_it = 0;
     const bool vec_ok = g.partial ? (g.N % 4 == 0) : ((g.ldc % 4 == 0) && ((reinterpret_cast<uintptr_t>(g.C) & 15) == 0));
-    for (int w = blockIdx.x; w < num_work; w += gridDim.x, ++tile_it) {
+    for (int w = unit; w < num_work; w += num_units, ++tile_it) {
       const int split = w % g.splits, tile = w / g.splits;
-      const int m0 = (tile % g.tiles_m) * BLOCK_M, n0 = (tile / g.tiles_m) * BLOCK_N;
+      const int m0 = (tile % g.tiles_m) * TILE_M + (int)cta_rank * BLOCK_M, n0 = (tile / g.tiles_m) * BLOCK_N;
       const uint32_t acc = tile_it & 1, acc_ph = (tile_it >> 1) & 1;
       mbar_wait(&tmem_full[acc], acc_ph);
       tc_fence_after();
@@ -324,7 +357,10 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
         if (c0 + 32 >= BLOCK_N) {  // last chunk read: hand the accumulator back before the (slow) global stores
           tc_fence_before();
           __syncwarp();
-          if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+          if (lane == 0) {
+            if (PAIR) mbar_arrive_remote(&tmem_empty[acc], 0);    // the leader's MMA warp waits for both CTAs' epilogues
+            else mbar_arrive(&tmem_empty[acc]);
+          }
         }
         const int nbase = n0 + c0;
         if (nbase >= g.N) continue;           // (uniform across the CTA)
@@ -424,34 +460,61 @@ gemm_tf32_kernel(const __grid_constant__ CUtensorMap tmap_a, const __grid_consta
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (PAIR) cluster_sync_all();      // the leader's MMAs read the peer's shared memory: nobody leaves early
+  else __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C_::kTmemCols);
+    if (PAIR) tmem_dealloc_2cta(tmem_base, C_::kTmemCols);
+    else tmem_dealloc(tmem_base, C_::kTmemCols);
   }
 }
 
 // ---------------------------------------------------------------------------------------------- host launch
-template <int BLOCK_N, int A_MN, int B_MN, bool COLSUM>
+template <int BLOCK_N, int A_MN, int B_MN, bool COLSUM, int CTAS = 1>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_, const CUtensorMap& tc2, const GemmArgs& g,
                   int grid, cudaStream_t st) {
-  using C_ = Cfg<BLOCK_N, COLSUM>;
-  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, COLSUM>;
+  using C_ = Cfg<BLOCK_N, COLSUM, CTAS>;
+  auto kern = gemm_tf32_kernel<BLOCK_N, A_MN, B_MN, COLSUM, CTAS>;
   static bool attr_set = false;
   if (!attr_set) {
     NGB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C_::kSmemBytes));
     attr_set = true;
   }
-  kern<<<grid, kThreads, C_::kSmemBytes, st>>>(ta, tb, tc_, tc2, g);
+  if (CTAS == 1) {
+    kern<<<grid, kThreads, C_::kSmemBytes, st>>>(ta, tb, tc_, tc2, g);
+  } else {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3((unsigned)grid, 1, 1);
+    cfg.blockDim = dim3(kThreads, 1, 1);
+    cfg.dynamicSmemBytes = C_::kSmemBytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    NGB_CUDA(cudaLaunchKernelEx(&cfg, kern, ta, tb, tc_, tc2, g));
+  }
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
 
 template <int BLOCK_N>
-static int launch_major(int a_mn, int b_mn, bool colsum, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_,
+static int launch_major(int a_mn, int b_mn, bool colsum, int ctas, const CUtensorMap& ta, const CUtensorMap& tb, const CUtensorMap& tc_,
                         const CUtensorMap& tc2, const GemmArgs& g, int grid, cudaStream_t st) {
   if constexpr (BLOCK_N <= 128) {
     if (colsum) return launch<BLOCK_N, 1, 1, true>(ta, tb, tc_, tc2, g, grid, st);   // (only the TN weight-gradient form)
+  }
+  if constexpr (BLOCK_N >= 128) {
+    if (ctas == 2) {
+      if (!a_mn && !b_mn) return launch<BLOCK_N, 0, 0, false, 2>(ta, tb, tc_, tc2, g, grid, st);
+      if (!a_mn && b_mn) return launch<BLOCK_N, 0, 1, false, 2>(ta, tb, tc_, tc2, g, grid, st);
+      if (a_mn && !b_mn) return launch<BLOCK_N, 1, 0, false, 2>(ta, tb, tc_, tc2, g, grid, st);
+      return launch<BLOCK_N, 1, 1, false, 2>(ta, tb, tc_, tc2, g, grid, st);
+    }
   }
   if (!a_mn && !b_mn) return launch<BLOCK_N, 0, 0, false>(ta, tb, tc_, tc2, g, grid, st);
   if (!a_mn && b_mn) return launch<BLOCK_N, 0, 1, false>(ta, tb, tc_, tc2, g, grid, st);
@@ -488,29 +551,39 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   // kernel is bound by the shared-memory fill: one k-block brings (128 + BN) x 128 B through TMA at ~75 GB/s per SM (the
   // chip-wide L2 -> SM cap of ~6300 B/clk), a work item costs ~2.5 us of pipeline fill + epilogue on top, a CTA runs
   // ceil(items / 148) items in a row, and K-splits pay a second pass over (splits + 1) x M x N floats at ~3 TB/s.
-  const int64_t tm = ceil_div<int64_t>(M, BLOCK_M);
   const int k_blocks = (int)ceil_div<int64_t>(K, BLOCK_K);
   const bool can_split = !fused && k_blocks >= 8;
-  int BN = 64, best_splits = 1;
+  // CTA pairs (cta_group::2): 256-row tiles, each CTA stages 128 rows of A and HALF of the B tile -> (128 + BN/2) x 128 B
+  // per k-block and SM instead of (128 + BN) x 128 B.  Work units are then the 74 pairs.
+  static const int pair_env = env_int("NGB_GEMM_2CTA", -1);
+  int BN = 64, best_splits = 1, ctas = 1;
   {
     double best = 1e30;
-    for (int c = 64; c <= 256; c *= 2) {
-      if (colsum && c > 128) break;                     // two accumulators per stage: 4 x BN TMEM columns <= 512
-      if (c > 64 && c / 2 >= N) break;                  // (a tile more than twice as wide as the problem)
-      const int64_t tiles_c = tm * ceil_div<int64_t>(N, c);
-      const int max_s = can_split ? (k_blocks / 2 < 64 ? k_blocks / 2 : 64) : 1;
-      for (int sp = 1; sp <= max_s; ++sp) {
-        const int kb = (int)ceil_div<int64_t>(k_blocks, sp);
-        const int sp_eff = (int)ceil_div<int64_t>(k_blocks, kb);
-        const double rounds = (double)ceil_div<int64_t>(tiles_c * sp_eff, kNumSMs);
-        double t = rounds * (2.5 + kb * (128.0 + c) * 128.0 / 75e3);
-        if (sp_eff > 1) t += 2.5 + (sp_eff + 1.0) * (double)M * (double)N * 4.0 / 3.0e6;
-        if (t < best) { best = t; BN = c; best_splits = sp_eff; }
+    for (int cg = 1; cg <= 2; ++cg) {
+      if (cg == 2 && (colsum || pair_env != 1 || M <= BLOCK_M)) break;     // (experimental: NGB_GEMM_2CTA=1 enables the pair kernels)
+      if (cg == 1 && pair_env == 1 && !colsum && M > BLOCK_M && N > 64) continue;      // forced on where possible
+      const int64_t tm_c = ceil_div<int64_t>(M, (int64_t)BLOCK_M * cg);
+      const int units = kNumSMs / cg;
+      for (int c = cg == 2 ? 128 : 64; c <= 256; c *= 2) {
+        if (colsum && c > 128) break;                     // two accumulators per stage: 4 x BN TMEM columns <= 512
+        if (c > 64 && c / 2 >= N) break;                  // (a tile more than twice as wide as the problem)
+        const int64_t tiles_c = tm_c * ceil_div<int64_t>(N, c);
+        const int max_s = can_split ? (k_blocks / 2 < 64 ? k_blocks / 2 : 64) : 1;
+        for (int sp = 1; sp <= max_s; ++sp) {
+          const int kb = (int)ceil_div<int64_t>(k_blocks, sp);
+          const int sp_eff = (int)ceil_div<int64_t>(k_blocks, kb);
+          const double rounds = (double)ceil_div<int64_t>(tiles_c * sp_eff, units);
+          double t = rounds * (2.5 + kb * (128.0 + (double)c / cg) * 128.0 / 75e3);
+          if (sp_eff > 1) t += 2.5 + (sp_eff + 1.0) * (double)M * (double)N * 4.0 / 3.0e6;
+          if (t < best) { best = t; BN = c; best_splits = sp_eff; ctas = cg; }
+        }
       }
     }
     const int f = env_int("NGB_GEMM_BN", 0);          // tuning / experiments
     if (f == 64 || f == 128 || (f == 256 && !colsum)) BN = f;
+    if (ctas == 2 && BN < 128) BN = 128;
   }
+  const int64_t tm = ceil_div<int64_t>(M, (int64_t)BLOCK_M * ctas);
 
   CUtensorMap ta, tb;
   // An MN-major operand whose MN extent is a multiple of 32 is described as {32, K, MN/32} (outer stride 128 B) so that a
@@ -533,11 +606,11 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
     if (rc) return rc;
     if (b_3d) {
       dims[0] = 32; dims[1] = K; dims[2] = N / 32; str[0] = (uint64_t)ldb * 4; str[1] = 128;
-      box[0] = 32; box[1] = BLOCK_K; box[2] = (uint32_t)(BN / 32);
+      box[0] = 32; box[1] = BLOCK_K; box[2] = (uint32_t)(BN / ctas / 32);      // (pair: each CTA loads half of the tile's columns)
       rc = make_tmap_f32(&tb, B, 3, dims, str, box, true);
     } else {
       if (b_mn) { dims[0] = N; dims[1] = K; box[0] = 32; box[1] = BLOCK_K; }
-      else { dims[0] = K; dims[1] = N; box[0] = BLOCK_K; box[1] = (uint32_t)BN; }
+      else { dims[0] = K; dims[1] = N; box[0] = BLOCK_K; box[1] = (uint32_t)(BN / ctas); }
       str[0] = (uint64_t)ldb * 4;
       rc = make_tmap_f32(&tb, B, 2, dims, str, box, b_mn);
     }
@@ -574,7 +647,8 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   g.colsum = colsum ? (g.partial ? cs_part : e.colsum) : nullptr;
   g.colsum_accumulate = e.colsum_accumulate;
   const int work = tiles * g.splits;
-  const int grid = work < kNumSMs ? work : kNumSMs;
+  const int units_avail = kNumSMs / ctas;
+  const int grid = (work < units_avail ? work : units_avail) * ctas;
 
   // output tensor maps for the TMA-store epilogue: C itself, or the split partials as {N, M, splits}; C2 likewise
   CUtensorMap tcm, tcm2;
@@ -602,9 +676,9 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
     g.tma_store = ok ? 1 : 0;
   }
   int rc;
-  if (BN == 64) rc = launch_major<64>(a_mn, b_mn, colsum, ta, tb, tcm, tcm2, g, grid, st);
-  else if (BN == 128) rc = launch_major<128>(a_mn, b_mn, colsum, ta, tb, tcm, tcm2, g, grid, st);
-  else rc = launch_major<256>(a_mn, b_mn, colsum, ta, tb, tcm, tcm2, g, grid, st);
+  if (BN == 64) rc = launch_major<64>(a_mn, b_mn, colsum, 1, ta, tb, tcm, tcm2, g, grid, st);
+  else if (BN == 128) rc = launch_major<128>(a_mn, b_mn, colsum, ctas, ta, tb, tcm, tcm2, g, grid, st);
+  else rc = launch_major<256>(a_mn, b_mn, colsum, ctas, ta, tb, tcm, tcm2, g, grid, st);
   if (rc) return rc;
   if (g.splits > 1) {
     if (!colsum) return launch_splitk_reduce(g.partial, g.splits, M, N, C, ldc, accumulate, st);
