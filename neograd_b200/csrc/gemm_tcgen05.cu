@@ -560,8 +560,14 @@ int gemm_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, const float
   {
     double best = 1e30;
     for (int cg = 1; cg <= 2; ++cg) {
-      if (cg == 2 && (colsum || pair_env != 1 || M <= BLOCK_M)) break;     // (experimental: NGB_GEMM_2CTA=1 enables the pair kernels)
-      if (cg == 1 && pair_env == 1 && !colsum && M > BLOCK_M && N > 64) continue;      // forced on where possible
+      // Measured (profiles/r02_gemm_pair.md): the pair kernels win where a CTA streams several tiles back to back (4096^3:
+      // 211 -> 187 us) and lose 2-10 % on one-tile-per-CTA problems, whose time is the load -> MMA -> epilogue latency chain
+      // of a single tile rather than the shared-memory fill; so they are taken from 3 rounds of 128 x 256 tiles up.
+      // NGB_GEMM_2CTA = 0 / 1 forces them off / on (wherever they exist).
+      const bool pair_ok = !colsum && M > BLOCK_M && N > 64;
+      const bool big = ceil_div<int64_t>(M, BLOCK_M) * ceil_div<int64_t>(N, 256) >= 3 * (int64_t)kNumSMs;
+      if (cg == 2 && (!pair_ok || pair_env == 0 || (pair_env != 1 && !big))) break;
+      if (cg == 1 && pair_ok && (pair_env == 1 || (pair_env != 0 && big))) continue;
       const int64_t tm_c = ceil_div<int64_t>(M, (int64_t)BLOCK_M * cg);
       const int units = kNumSMs / cg;
       for (int c = cg == 2 ? 128 : 64; c <= 256; c *= 2) {
