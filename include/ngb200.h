@@ -236,6 +236,14 @@ int ngb_softmax_fwd(const float* x, int64_t outer, int64_t L, int64_t inner, flo
 int ngb_softmax_bwd(const float* x, const float* ug, int64_t outer, int64_t L, int64_t inner, float* dx,
                     int accumulate, ngb_stream_t stream);
 
+/* BCE in one pass: cost = (-1/num_examples) * sum(o * log(t + eps) + (1 - o) * log(1 - t + eps)) -- nn/loss.py:83-84,
+ * with the reference's argument roles as they are (outputs multiply the logs of the targets).  o, t: n elements each. */
+int ngb_bce_fwd(const float* outputs, const float* targets, int64_t n, float inv_num_examples, float epsilon, float* loss,
+                ngb_stream_t stream);
+/* its gradients for an upstream gradient ug (device scalar, NULL = 1): d_outputs and / or d_targets (NULL = not wanted) */
+int ngb_bce_bwd(const float* outputs, const float* targets, const float* ug, int64_t n, float inv_num_examples,
+                float epsilon, float* d_outputs, int accumulate_o, float* d_targets, int accumulate_t, ngb_stream_t stream);
+
 /* ---- optimizers: neograd/nn/optim.py ------------------------------------------------------------------------ */
 /* One fused pass over a flat parameter arena.  g is multiplied by grad_scale first (1/world for data parallel).
  * Hyper-parameters are doubles (the reference computes in float64): 1-beta and the bias corrections are formed in

@@ -105,6 +105,8 @@ SIGNATURES = {
   'ngb_softmax_bwd': ([_P, _P, c_int64, c_int64, c_int64, _P, c_int, _S], c_int),
   'ngb_softmax_ce_fwd': ([_P, _P, c_int64, c_int64, c_int64, c_float, c_float, _P, _S], c_int),
   'ngb_softmax_ce_bwd': ([_P, _P, _P, c_int64, c_int64, c_int64, c_float, _P, c_int, _S], c_int),
+  'ngb_bce_fwd': ([_P, _P, c_int64, c_float, c_float, _P, _S], c_int),
+  'ngb_bce_bwd': ([_P, _P, _P, c_int64, c_float, c_float, _P, c_int, _P, c_int, _S], c_int),
   'ngb_adam_step': ([_P, _P, _P, _P, c_int64] + [c_double] * 4 + [c_int64, c_double, _S], c_int),
   'ngb_adam_step_dev': ([_P, _P, _P, _P, c_int64] + [c_double] * 4 + [_P, c_int, c_double, _S], c_int),
   'ngb_sgd_step': ([_P, _P, c_int64, c_double, c_double, _S], c_int),

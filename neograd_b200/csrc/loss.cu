@@ -99,9 +99,89 @@ __global__ void __launch_bounds__(256) softmax_bwd_kernel(const float* __restric
   }
 }
 
+// BCE as ONE pass (nn/loss.py:69-85 builds it from eleven elementwise ops): entropy = sum(o * log(t + eps) +
+// (1 - o) * log(1 - t + eps)), cost = (-1/n) * entropy -- with the reference's (swapped) argument roles kept as they are
+// (SURVEY A.7).  Same fp32 operations per element as the composite; the reduction is per-block partials summed in a fixed
+// order by the last block to finish.
+__device__ unsigned int g_bce_done[kLanes];
+
+__global__ void __launch_bounds__(256) bce_fwd_kernel(const float* __restrict__ o, const float* __restrict__ t, int64_t n, float eps,
+                                                      float scale, float* __restrict__ partial, float* __restrict__ loss,
+                                                      unsigned int* done) {
+  __shared__ float red[32];
+  __shared__ bool is_last;
+  float acc = 0.f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float ov = o[i], tv = t[i];
+    acc += ov * logf(tv + eps) + (1.f - ov) * logf((1.f - tv) + eps);
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) {
+    partial[blockIdx.x] = acc;
+    __threadfence();
+    is_last = atomicAdd(done, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (is_last) {
+    __threadfence();
+    const volatile float* pp = partial;
+    const int nb = (int)gridDim.x, th = threadIdx.x;          // (grid <= 1024)
+    const float a0 = th < nb ? pp[th] : 0.f, a1 = th + 256 < nb ? pp[th + 256] : 0.f;
+    const float a2 = th + 512 < nb ? pp[th + 512] : 0.f, a3 = th + 768 < nb ? pp[th + 768] : 0.f;
+    const float tot = block_sum((a0 + a1) + (a2 + a3), red);
+    if (th == 0) {
+      *loss = scale * tot;
+      *done = 0;
+    }
+  }
+}
+
+// d cost / d o = scale * ug * (log(t + eps) - log(1 - t + eps));  d cost / d t = scale * ug * (o / (t + eps) - (1 - o) / (1 - t + eps))
+__global__ void __launch_bounds__(256) bce_bwd_kernel(const float* __restrict__ o, const float* __restrict__ t,
+                                                      const float* __restrict__ ug, int64_t n, float eps, float scale,
+                                                      float* __restrict__ d_o, int acc_o, float* __restrict__ d_t, int acc_t) {
+  const float g = scale * (ug ? ug[0] : 1.f);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const float ov = o[i], tv = t[i];
+    if (d_o) {
+      const float v = g * (logf(tv + eps) - logf((1.f - tv) + eps));
+      d_o[i] = acc_o ? d_o[i] + v : v;
+    }
+    if (d_t) {
+      const float v = g * (ov / (tv + eps) - (1.f - ov) / ((1.f - tv) + eps));
+      d_t[i] = acc_t ? d_t[i] + v : v;
+    }
+  }
+}
+
 }  // namespace ngb
 
 using namespace ngb;
+
+extern "C" int ngb_bce_fwd(const float* outputs, const float* targets, int64_t n, float inv_num_examples, float epsilon, float* loss,
+                           ngb_stream_t stream) {
+  NGB_CHECK_ARG(n >= 1 && outputs && targets && loss, "ngb_bce_fwd: bad arguments");
+  int rc = ensure_init();
+  if (rc) return rc;
+  unsigned int* done = nullptr;
+  NGB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&done), g_bce_done));
+  int grid = grid_for(n, 256, 2);
+  if (grid > 1024) grid = 1024;
+  bce_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(outputs, targets, n, epsilon, -inv_num_examples, scratch_ptr(), loss,
+                                                      done + current_lane());
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
+
+extern "C" int ngb_bce_bwd(const float* outputs, const float* targets, const float* ug, int64_t n, float inv_num_examples,
+                           float epsilon, float* d_outputs, int accumulate_o, float* d_targets, int accumulate_t,
+                           ngb_stream_t stream) {
+  NGB_CHECK_ARG(n >= 1 && outputs && targets && (d_outputs || d_targets), "ngb_bce_bwd: bad arguments");
+  bce_bwd_kernel<<<grid_for(n, 256), 256, 0, as_stream(stream)>>>(outputs, targets, ug, n, epsilon, -inv_num_examples, d_outputs,
+                                                                 accumulate_o, d_targets, accumulate_t);
+  NGB_LAUNCH_CHECK();
+  return NGB_OK;
+}
 
 extern "C" int ngb_softmax_fwd(const float* x, int64_t outer, int64_t L, int64_t inner, float* y, ngb_stream_t stream) {
   NGB_CHECK_ARG(outer >= 0 && L >= 1 && inner >= 0, "ngb_softmax_fwd: bad shape");

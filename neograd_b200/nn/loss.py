@@ -28,11 +28,47 @@ class MSE(Loss):
   def __str__(self): return 'MeanSquaredError'
 
 
+class _BCEOp(Operation):
+  """The reference's BCE expression (loss.py:83-84: eleven elementwise ops and a sum) as ONE Operation: one reduction
+  kernel forward, one elementwise kernel backward -- same arithmetic per element, argument roles as the reference has them."""
+
+  def __init__(self, num_examples, epsilon):
+    self.n, self.eps = num_examples, epsilon
+
+  def forward(self, outputs, targets):
+    outputs, targets = self.get_tensors(outputs, targets)
+    loss = D.DeviceArray.empty(())
+    B.check(B.lib.ngb_bce_fwd(outputs.data.ptr, targets.data.ptr, outputs.data.size, 1.0 / self.n, self.eps, loss.ptr, D._st()))
+    return self.get_result_tensor(loss, outputs, targets)
+
+  def get_broadcast_shape(self, *tensors):
+    return None
+
+  def backward(self, outputs, targets):
+    o, t, inv_n, eps = outputs.data, targets.data, 1.0 / self.n, self.eps
+
+    def make(side):
+      def into(ug, dst, acc):
+        if dst is None:
+          dst, acc = D.DeviceArray.empty(o.shape), False
+        ugp = None if D.const_value(ug) == 1.0 else ug.ptr          # loss.backward()'s host-known 1. stays an immediate
+        B.check(B.lib.ngb_bce_bwd(o.ptr, t.ptr, ugp, o.size, inv_n, eps, dst.ptr if side == 0 else None, int(acc),
+                                  dst.ptr if side == 1 else None, int(acc), D._st()))
+        return dst
+      return GradFn(into)
+    outputs.set_grad_fn(make(0))
+    targets.set_grad_fn(make(1))
+
+
 class BCE(Loss):
   """loss.py:66-91."""
 
   def forward(self, outputs, targets, epsilon=1e-9):
+    from ..autograd.tensor import Tensor
     num_examples = self.get_num_examples(outputs.shape)
+    if (D.FUSED_LINEAR and isinstance(outputs, Tensor) and isinstance(targets, Tensor) and outputs.shape == targets.shape
+        and outputs._data is not None and targets._data is not None and outputs.data.size >= 1):
+      return _BCEOp(num_examples, epsilon).forward(outputs, targets)
     entropy = _sum((outputs * log(targets + epsilon)) + ((1 - outputs) * (log(1 - targets + epsilon))))
     return (-1 / num_examples) * entropy
 

@@ -118,6 +118,19 @@ def linear_softmax_ce(x, w, b, t, eps=1e-9):
   return host(z), float(host(loss)[0]), host(dz)
 
 
+def bce(o, t, ug=None, eps=1e-9, want=(True, True)):
+  """(loss, d_outputs, d_targets) of ngb_bce_fwd / ngb_bce_bwd; num_examples = rows of o (loss.py:22-37)"""
+  O, T = dev(o), dev(t)
+  n = o.shape[0] if o.ndim >= 2 else 1
+  loss = torch.full((1,), float('nan'), device='cuda')
+  call('ngb_bce_fwd', ptr(O), ptr(T), O.numel(), 1.0 / n, eps, ptr(loss), st())
+  do = torch.full(O.shape, float('nan'), device='cuda') if want[0] else None
+  dt = torch.full(O.shape, float('nan'), device='cuda') if want[1] else None
+  U = dev(np.reshape(ug, (1,))) if ug is not None else None
+  call('ngb_bce_bwd', ptr(O), ptr(T), ptr(U), O.numel(), 1.0 / n, eps, ptr(do), 0, ptr(dt), 0, st())
+  return float(host(loss)[0]), (host(do) if want[0] else None), (host(dt) if want[1] else None)
+
+
 def conv_fprop(x, w, b, pad, stride):
   N, C, H, W = x.shape
   O, _, KH, KW = w.shape

@@ -462,6 +462,27 @@ def test_linear_softmax_ce_head(U, M, K, N):
   assert loss2 == loss and np.array_equal(dz2, dz)
 
 
+@pytest.mark.parametrize('shape', [(8192, 1), (750, 1), (33, 7), (1000003, 1)])
+def test_bce_single_pass(U, shape):
+  """ngb_bce_fwd / _bwd against the reference's composite expression (loss.py:83-84) evaluated in float64, with the
+  reference's argument roles (outputs multiply the logs of the targets) and gradients for both operands."""
+  rng = np.random.default_rng(shape[0])
+  o = f32(rng.uniform(0.02, 0.98, shape))
+  t = f32(rng.uniform(0.05, 0.95, shape))
+  eps, n = 1e-9, shape[0]
+  want = (-1 / n) * np.sum(o * np.log(t + eps) + (1 - o) * np.log(1 - t + eps))
+  loss, do, dt = U.bce(o, t, ug=0.5)
+  assert abs(loss - want) <= 2e-6 * abs(want), (loss, want)
+  close(do, 0.5 * (-1 / n) * (np.log(t + eps) - np.log(1 - t + eps)), 4 * TOL32)
+  close(dt, 0.5 * (-1 / n) * (o / (t + eps) - (1 - o) / (1 - t + eps)), 4 * TOL32)
+  # hard targets (the GAN's ones / zeros): log(0 + eps) is finite, run-to-run bit-identical
+  ones = np.ones(shape)
+  l1, d1, _ = U.bce(o, ones, want=(True, False))
+  l2, d2, _ = U.bce(o, ones, want=(True, False))
+  assert l1 == l2 and np.array_equal(d1, d2) and np.isfinite(l1)
+  assert abs(l1 - (-1 / n) * np.sum(o * np.log(1 + eps) + (1 - o) * np.log(eps))) <= 1e-5 * abs(l1)
+
+
 def test_no_pipeline_timeouts(U):
   """Runs last in this file's conv / gemm group: no tcgen05 warp gave up on a barrier during the tests above."""
   U.call('ngb_debug_check_pipelines')
