@@ -248,8 +248,8 @@ inline int64_t small_smem(int64_t N, int64_t K) { return K * (nt_for(N) | 1) * (
 inline bool small_ok(int64_t N, int64_t K) { return N >= 1 && N <= kSmallNMax && K >= 1 && small_smem(N, K) <= kSmallSmemMax; }
 
 unsigned int* done_counter() {
-  unsigned int* p = nullptr;
-  cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_done_counter);
+  static unsigned int* p = nullptr;     // (looked up once: cudaGetSymbolAddress is a slow runtime call)
+  if (!p) cudaGetSymbolAddress(reinterpret_cast<void**>(&p), g_done_counter);
   return p + current_lane() * 8;
 }
 

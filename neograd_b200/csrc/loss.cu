@@ -163,8 +163,8 @@ extern "C" int ngb_bce_fwd(const float* outputs, const float* targets, int64_t n
   NGB_CHECK_ARG(n >= 1 && outputs && targets && loss, "ngb_bce_fwd: bad arguments");
   int rc = ensure_init();
   if (rc) return rc;
-  unsigned int* done = nullptr;
-  NGB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&done), g_bce_done));
+  static unsigned int* done = nullptr;   // (looked up once)
+  if (!done) NGB_CUDA(cudaGetSymbolAddress(reinterpret_cast<void**>(&done), g_bce_done));
   int grid = grid_for(n, 256, 2);
   if (grid > 1024) grid = 1024;
   bce_fwd_kernel<<<grid, 256, 0, as_stream(stream)>>>(outputs, targets, n, epsilon, -inv_num_examples, scratch_ptr(), loss,
