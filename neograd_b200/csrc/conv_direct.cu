@@ -23,7 +23,8 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
 
 // conv_small_mma.cu: TF32 mma.sync kernels for small-channel layers (fprop mode 0 / dgrad mode 1, wgrad)
 int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
-                    int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done);
+                    int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done,
+                    uint8_t* pool_idx = nullptr);
 int wgrad_layout_for_tests(int C, int H, int W, int KH, int KW, int pad, int stride, int* out);
 bool conv_sparse_serves(int C, int H, int W, int O, int KH, int KW, int pad, int Ho, int Wo);
 bool conv_fused_fwd_serves(int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo);

@@ -102,9 +102,16 @@ struct GatherGeo {
   int G;                               // images per pass
 };
 
-template <int MT, int NT, bool ACC>
+// POOL (forward only, 16-position tiles that are exactly TWO rows of the output plane as the pool sees it, i.e. the plane's
+// contiguous extent is 8): bias + ReLU + 2x2 / stride-2 max pool in the epilogue -- the convolution's output is never
+// written.  A tile then holds four complete windows; window pw = (rows 2pw, 2pw+1, 2pw+8, 2pw+9) sits in the lane pair
+// gq = 2pw, 2pw+1, which swap their two values with one shuffle each.  Values, argmax bytes and the ReLU flag (bit 2) are
+// those of ngb_conv_fprop followed by ngb_maxpool_relu_fwd (pool.cu: first maximum in window order, flag = max > 0 or
+// first cell >= 0).
+template <int MT, int NT, bool ACC, bool POOL = false>
 __global__ void __launch_bounds__(256, 4) conv_gather_mma_kernel(const float* __restrict__ in, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* __restrict__ out,
+                                                              uint8_t* __restrict__ pool_idx,
                                                               GatherGeo g, FastDiv d_plane, FastDiv d_cols,
                                                               FastDiv d_fdiv, FastDiv d_mti, FastDiv d_npp, FastDiv d_op8,
                                                               FastDiv d_kw, FastDiv d_kk) {
@@ -242,7 +249,7 @@ __global__ void __launch_bounds__(256, 4) conv_gather_mma_kernel(const float* __
     // ---- compute: a warp owns MT m-tiles (16 consecutive outputs of one image each) x all NT channel tiles.
     // All shared-memory operands are addressed by 32-bit BYTE addresses (tables hold byte offsets): one add per load.
     const int units = ng * g.MTI;
-    float* const obase = out + (int64_t)n0 * g.Cout * g.F;
+    float* const obase = POOL ? out : out + (int64_t)n0 * g.Cout * g.F;
     for (int u0 = warp * MT; u0 < units; u0 += nwarps * MT) {
       uint32_t A0[MT], A1[MT];
       int eo[MT], tile_f[MT];                   // element offset of (image, f0 + g) inside this pass's output block; f0
@@ -291,6 +298,41 @@ __global__ void __launch_bounds__(256, 4) conv_gather_mma_kernel(const float* __
           for (int j = 0; j < NT; ++j) mma_tf32(acc[i][j], a[i][0], a[i][1], a[i][2], a[i][3], b[j].x, b[j].y);
       }
 
+      if (POOL) {
+        // pooled plane of one (image, channel): [Wp = F/32... ][Hp]: window (ph = tile within the image, pw = gq / 2) is stored
+        // at flat index pw * Hp + ph (neograd order of the pool's own output), Hp = MTI
+        const int Fp = g.F >> 2;
+#pragma unroll
+        for (int i = 0; i < MT; ++i) {
+          const bool tile_ok = eo[i] >= 0;
+          uint32_t img, tile;
+          d_mti.divmod((uint32_t)(u0 + i), img, tile);
+          const int64_t pbase = ((int64_t)(n0 + (int)img) * g.Cout) * Fp + (gq >> 1) * g.MTI + (int)tile;
+#pragma unroll
+          for (int j = 0; j < NT; ++j) {
+#pragma unroll
+            for (int b2 = 0; b2 < 2; ++b2) {
+              const float v0 = acc[i][j][b2] + bv[j][b2], v1 = acc[i][j][2 + b2] + bv[j][b2];     // rows gq, gq + 8
+              const float p0 = __shfl_xor_sync(0xffffffffu, v0, 4), p1 = __shfl_xor_sync(0xffffffffu, v1, 4);
+              if ((gq & 1) == 0 && tile_ok && cvalid[j][b2]) {
+                // window cells in the pool's row-major order: a = (row 2pw), b = (2pw+1), c = (2pw+8), d = (2pw+9)
+                const float first = v0;
+                const float a = fmaxf(0.f, v0), b = fmaxf(0.f, p0), c = fmaxf(0.f, v1), d = fmaxf(0.f, p1);
+                float best = a;
+                int arg = 0;
+                if (b > best) { best = b; arg = 1; }
+                if (c > best) { best = c; arg = 2; }
+                if (d > best) { best = d; arg = 3; }
+                if (best > 0.f || first >= 0.f) arg |= 4;      // kPoolReluFlag (pool.cu)
+                const int64_t o = pbase + (int64_t)(j * 8 + 2 * t + b2) * Fp;
+                out[o] = best;
+                pool_idx[o] = (uint8_t)arg;
+              }
+            }
+          }
+        }
+        continue;
+      }
       // ---- epilogue: lanes of equal t hold 8 consecutive outputs of one channel -> 32-byte store segments.
       // One 64-bit pointer per (tile, channel column); the stores are PREDICATED (no branch per element).
 #pragma unroll
@@ -347,26 +389,26 @@ static int balance_images(Kernel kernel, int threads, size_t fixed, size_t per_i
   return NGB_OK;
 }
 
-template <int MT, int NT, bool ACC>
+template <int MT, int NT, bool ACC, bool POOL = false>
 static int launch_gather(const float* in, const float* w, const float* bias, float* out, GatherGeo g, int gmax, size_t fixed,
-                         size_t per_img, cudaStream_t st) {
+                         size_t per_img, cudaStream_t st, uint8_t* pool_idx = nullptr) {
   static bool attr = false;
   if (!attr) {
-    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT, ACC>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT, ACC, POOL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
     // maximum shared-memory carveout: a kernel of another lane can only become co-resident on an SM whose L1 / shared split
     // already has room for it -- with the default (smallest fitting) split the second kernel waits for the first to drain
-    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT, ACC>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
+    NGB_CUDA(cudaFuncSetAttribute(conv_gather_mma_kernel<MT, NT, ACC, POOL>, cudaFuncAttributePreferredSharedMemoryCarveout, getenv("NGB_CARVEOUT_DEFAULT") ? cudaSharedmemCarveoutDefault : cudaSharedmemCarveoutMaxShared));
     attr = true;
   }
   int grid = 1;
-  int rc = balance_images(conv_gather_mma_kernel<MT, NT, ACC>, 256, fixed, per_img, g.N, 1, gmax, corun_hint() != 0, &g.G, &grid);
+  int rc = balance_images(conv_gather_mma_kernel<MT, NT, ACC, POOL>, 256, fixed, per_img, g.N, 1, gmax, corun_hint() != 0, &g.G, &grid);
   if (rc) return rc;
   // 8 warps at <= 64 registers: four CTAs (32 warps) per SM.  (9-12 warp blocks tile some pass sizes without an idle
   // tail, but their register footprint drops the SM to two CTAs, which costs more than the tail.)
   const int nwarps = 8;
   const size_t smem = fixed + (size_t)g.G * per_img;
-  conv_gather_mma_kernel<MT, NT, ACC><<<grid, nwarps * 32, smem, st>>>(
-      in, w, bias, out, g, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.fdiv),
+  conv_gather_mma_kernel<MT, NT, ACC, POOL><<<grid, nwarps * 32, smem, st>>>(
+      in, w, bias, out, pool_idx, g, FastDiv((uint32_t)g.raw_plane), FastDiv((uint32_t)g.raw_cols), FastDiv((uint32_t)g.fdiv),
       FastDiv((uint32_t)g.MTI), FastDiv((uint32_t)g.NPp), FastDiv((uint32_t)g.Op8), FastDiv((uint32_t)g.KW),
       FastDiv((uint32_t)(g.KH * g.KW)));
   NGB_LAUNCH_CHECK();
@@ -374,10 +416,13 @@ static int launch_gather(const float* in, const float* w, const float* bias, flo
 }
 
 // mode 0 = fprop (in = x, out = y), mode 1 = dgrad (in = ug, out = dx).  *done tells whether the kernel was launched.
+// pool_idx != nullptr (forward only): `out` is the 2x2-pooled map and pool_idx its argmax bytes (POOL epilogue).
 int conv_mma_gather(const float* in, const float* w, const float* bias, float* out, int N, int C, int H, int W, int O, int KH,
-                    int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done) {
+                    int KW, int pad, int stride, int Ho, int Wo, int mode, int accumulate, cudaStream_t st, bool* done,
+                    uint8_t* pool_idx) {
   *done = false;
   if (g_default_engine.load() == NGB_GEMM_SIMT) return NGB_OK;
+  if (pool_idx && (mode != 0 || accumulate || Ho != 8 || Wo != 8)) return NGB_OK;     // a 16-position tile = two rows of the 8 x 8 plane
   GatherGeo g;
   g.N = N; g.C = C; g.O = O; g.KH = KH; g.KW = KW; g.mode = mode;
   g.Op8 = (O + 7) & ~7;
@@ -427,7 +472,8 @@ int conv_mma_gather(const float* in, const float* w, const float* bias, float* o
   int rc = ensure_init();
   if (rc) return rc;
 #define NGB_GATHER(MT_, NT_)                                                                              \
-  rc = accumulate ? launch_gather<MT_, NT_, true>(in, w, bias, out, g, G, fixed, per_img, st)             \
+  rc = pool_idx ? launch_gather<MT_, NT_, false, true>(in, w, bias, out, g, G, fixed, per_img, st, pool_idx) \
+     : accumulate ? launch_gather<MT_, NT_, true>(in, w, bias, out, g, G, fixed, per_img, st)             \
                   : launch_gather<MT_, NT_, false>(in, w, bias, out, g, G, fixed, per_img, st)
   if (NT == 1) { if (best_mt == 4) NGB_GATHER(4, 1); else NGB_GATHER(2, 1); }
   else if (NT == 2) { if (best_mt == 4) NGB_GATHER(4, 2); else NGB_GATHER(2, 2); }
@@ -1719,8 +1765,20 @@ static int launch_fused_fwd(const float* x, const float* w, const float* bias, f
   return NGB_OK;
 }
 
+// small-channel layers whose output plane is 8 x (even): the tensor-core gather kernel with the pooling epilogue
+static bool gather_pool_serves(int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo) {
+  if (g_default_engine.load() == NGB_GEMM_SIMT || getenv("NGB_NO_FUSED_CONV2_POOL")) return false;
+  if (Ho != 8 || Wo != 8 || O < 4 || O > 32 || C < 2) return false;
+  const int NP = (O + 7) & ~7;
+  if (NP != 8 && NP != 16 && NP != 32) return false;
+  const int spitch = W + 2 * pad + 8, K = C * KH * KW;            // (upper bounds of the staged pitch / table sizes)
+  const size_t fixed = ((size_t)((K + 7) & ~7) * (NP + 4) + ((K + 7) & ~7) + (size_t)Ho * Wo) * 4;
+  return fixed + (size_t)C * (H + 2 * pad) * spitch * 4 <= 96 * 1024 && K <= 4096;
+}
+
 bool conv_fused_fwd_serves(int C, int H, int W, int O, int KH, int KW, int pad, int stride, int Ho, int Wo) {
   if (getenv("NGB_NO_FUSED_CONV_POOL")) return false;
+  if (gather_pool_serves(C, H, W, O, KH, KW, pad, stride, Ho, Wo)) return true;
   if (pad != 0 || stride != 1 || Ho != Wo || (Ho & 1) || (W & 1)) return false;
   return (C == 1 && KH == 5 && KW == 5 && O == 6) || (C == 1 && KH == 3 && KW == 3 && (O == 4 || O == 8));
 }
@@ -1729,6 +1787,8 @@ bool conv_fused_fwd_serves(int C, int H, int W, int O, int KH, int KW, int pad, 
 int conv_fused_relu_pool_fwd(const float* x, const float* w, const float* bias, float* y, uint8_t* idx, int N, int C, int H, int W,
                              int O, int KH, int KW, int pad, int stride, int Ho, int Wo, cudaStream_t st, bool* done) {
   *done = false;
+  if (N >= 1 && !getenv("NGB_NO_FUSED_CONV_POOL") && gather_pool_serves(C, H, W, O, KH, KW, pad, stride, Ho, Wo))
+    return conv_mma_gather(x, w, bias, y, N, C, H, W, O, KH, KW, pad, stride, Ho, Wo, 0, 0, st, done, idx);
   if (N < 1 || !conv_fused_fwd_serves(C, H, W, O, KH, KW, pad, stride, Ho, Wo) || ((uintptr_t)x & 7u)) return NGB_OK;
   FusedFwdGeo g;
   g.N = N; g.H = H; g.W = W; g.Ho = Ho; g.Hp = Ho / 2; g.Fp = (Ho / 2) * (Wo / 2);

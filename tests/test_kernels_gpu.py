@@ -632,11 +632,42 @@ def test_conv_relu_pool_forward_in_one_kernel(U, N, H, O, K):
   close(y2, yo2, 4 * TOL32)
 
 
+@pytest.mark.parametrize('N,C,H,O,K,pad', [(64, 6, 12, 16, 5, 0), (37, 6, 12, 16, 5, 0), (300, 4, 10, 8, 3, 0), (5, 8, 8, 32, 3, 1),
+                                           (4096, 6, 12, 16, 5, 0)])
+def test_conv_relu_pool_forward_small_channel_layers(U, N, C, H, O, K, pad):
+  """The second-layer block (LeNet conv2: 6 -> 16 channels, 8 x 8 output plane) in one kernel: the tensor-core gather kernel
+  with the pooling epilogue.  TF32-representable integer operands make the MMA sums exact, so pooled values, argmax bytes
+  (ties between clamped zeros included) and the ReLU flag in bit 2 must be IDENTICAL to ngb_conv_fprop -> ngb_maxpool_relu_fwd;
+  real-valued operands are bit-identical too (same kernel, same accumulation order) and agree with the oracle to TF32 rounding."""
+  rng = np.random.default_rng(N + C + H + O + K)
+  xi = rng.integers(-3, 4, (N, C, H, H)).astype(np.float64)
+  wi = rng.integers(-2, 3, (O, C, K, K)).astype(np.float64)
+  bi = rng.integers(-2, 3, (O,)).astype(np.float64)
+  xi[0] = 0.0                                             # z == bias everywhere: all-equal windows, exact zeros for bias 0
+  got = U.conv_relu_pool_fwd(xi, wi, bi, pad, 1)
+  assert got is not None
+  y, idx = got
+  z = U.conv_fprop(xi, wi, bi, pad, 1)
+  yr, idxr = U.maxpool_relu_fwd(z, (2, 2), 0, 2)
+  assert np.array_equal(y, yr) and np.array_equal(idx, idxr)
+  zo = ops.conv3d_fwd(xi, wi, bi, pad, 1)
+  yo = ops.maxpool_fwd(np.maximum(zo, 0.0), (2, 2), 0, 2)
+  yo = yo[0] if isinstance(yo, tuple) else yo
+  assert np.array_equal(y, yo.astype(np.float32))
+  xr, wr, br = f32(rng.standard_normal(xi.shape)), f32(rng.standard_normal(wi.shape) / K), f32(rng.standard_normal(O))
+  y2, i2 = U.conv_relu_pool_fwd(xr, wr, br, pad, 1)
+  yr2, ir2 = U.maxpool_relu_fwd(U.conv_fprop(xr, wr, br, pad, 1), (2, 2), 0, 2)
+  assert np.array_equal(y2, yr2) and np.array_equal(i2, ir2)
+  yo2 = ops.maxpool_fwd(np.maximum(ops.conv3d_fwd(xr, wr, br, pad, 1), 0.0), (2, 2), 0, 2)
+  yo2 = yo2[0] if isinstance(yo2, tuple) else yo2
+  close(y2, yo2, TOLTF32)
+
+
 def test_conv_relu_pool_forward_rejects_other_geometries(U):
   x, w, b = np.zeros((2, 1, 12, 12)), np.zeros((6, 1, 5, 5)), np.zeros(6)
   assert U.conv_relu_pool_fwd(x, w, b, 1, 1) is None                                   # padding
   assert U.conv_relu_pool_fwd(np.zeros((2, 1, 13, 13)), w, b, 0, 1) is None            # odd output plane
-  assert U.conv_relu_pool_fwd(np.zeros((2, 3, 12, 12)), np.zeros((6, 3, 5, 5)), b, 0, 1) is None
+  assert U.conv_relu_pool_fwd(np.zeros((2, 3, 14, 14)), np.zeros((6, 3, 5, 5)), b, 0, 1) is None   # 10 x 10 plane: neither kernel
 
 
 def test_maxpool_relu_fused_rejects_other_geometries(U):
