@@ -305,18 +305,33 @@ def call_work(name, a):
     M, N, K = a[3], a[4], a[5]
     return 4 * (M * K + K * N + M * N), 2 * M * N * K
   if name == 'ngb_linear_fwd':
-    # Dot + bias (+ activation) in one kernel: reads x, W, b; writes the pre-activation and (if asked) the activation
-    M, N, K = a[6], a[7], a[8]
-    outs = (1 if a[4] else 0) + (1 if a[5] else 0)
+    # Dot + bias (+ activation) in one kernel: reads x, W, b; writes the pre-activation and / or the activation
+    M, K, N = a[7], a[8], a[9]                      # (x, W, b, z, a, act, alpha, batch, n_in, n_out, stream)
+    outs = (1 if a[3] else 0) + (1 if a[4] else 0)
     return 4 * (M * K + K * N + N + outs * M * N), 2 * M * N * K
   if name == 'ngb_linear_dgrad':
-    # dX = (ug . W^T) * act'(z_prev): reads ug, W, z_prev; writes dX
-    M, N, K = a[4], a[5], a[6]
-    return 4 * (M * K + K * N + (2 if a[2] else 1) * M * N), 2 * M * N * K
+    # dx = (ug . W^T) * act'(z_prev): reads ug, W and (if masked) z_prev; writes dx
+    M, K, N = a[6], a[7], a[8]                      # (ug, W, zprev, dx, act, alpha, batch, n_in, n_out, accumulate, stream)
+    return 4 * (M * N + K * N + (2 if a[2] else 1) * M * K), 2 * M * N * K
   if name == 'ngb_linear_wgrad':
-    # dW = X^T . ug and db = column sums of ug from the same pass
-    M, N, K = a[4], a[5], a[6]      # (in, out, batch)
-    return 4 * (M * K + K * N + M * N + N), 2 * M * N * K + K * N
+    # dW = x^T . ug and db = column sums of ug from the same pass
+    M, K, N = a[4], a[5], a[6]                      # (x, ug, dW, db, batch, n_in, n_out, acc_w, acc_b, stream)
+    return 4 * (M * K + M * N + K * N + N), 2 * M * N * K + M * N
+  if name == 'ngb_linear_softmax_ce':
+    M, K, N = a[7], a[8], a[9]                      # (x, W, b, t, z, loss, dz, batch, n_in, n_out, ...)
+    return 4 * (M * K + K * N + N + 3 * M * N), 2 * M * N * K + 12 * M * N
+  if name in ('ngb_bce_fwd', 'ngb_bce_bwd'):
+    n = a[2] if name == 'ngb_bce_fwd' else a[3]
+    return (8 if name == 'ngb_bce_fwd' else 12) * n, 8 * n
+  if name == 'ngb_xgpu_exchange_update':
+    n, world = a[7], a[3]                           # push to world-1 peers, read world slots, 28 B/element of Adam traffic
+    return (4 * (world - 1) + 4 * world + 28) * n, 12 * n
+  if name == 'ngb_prep_u8_affine':
+    return 5 * a[2], 2 * a[2]
+  if name == 'ngb_prep_one_hot':
+    return 4 * a[2] + 4 * a[2] * a[3], a[2] * a[3]
+  if name == 'ngb_randn':
+    return 4 * a[1], 40 * a[1]
   if name in ('ngb_conv_fprop', 'ngb_conv_dgrad', 'ngb_conv_wgrad'):
     o = 4 if name == 'ngb_conv_fprop' else 3
     N, C, H, W, O, KH, KW, pad, stride = a[o:o + 9]
