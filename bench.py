@@ -747,6 +747,22 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
     grp.update(frac=grp['achieved'] / grp['peak'], calls_per_step=gd['calls'] // reps, share_of_step_kernel_time=gd['ms'] / total_ms)
     roofline['group'] = grp
     out['roofline'] = roofline
+  # the same launch site timed ALONE (backward lanes off: nothing co-runs with it), for comparison with the as-dispatched
+  # figure above -- a kernel that shares the SMs with another lane's kernel is charged its co-run duration there
+  prev_lanes = ng.set_backward_lanes(0)
+  with B.profile_calls() as prof2:
+    for _ in range(reps):
+      torch.cuda._sleep(20_000_000)
+      step()
+  h.barrier()
+  ng.set_backward_lanes(prev_lanes)
+  if rank == 0:
+    ms_alone = [ms for nm, d in prof2.summary().items() if nm == top for a, ms in d['items']
+                if tuple(v for v in a if isinstance(v, int)) == gkey]
+    if ms_alone:
+      alone = _roof(top, g['args'], float(np.mean(ms_alone)) * 1e-3, pk)
+      out['roofline']['alone'] = {k: alone[k] for k in ('achieved', 'frac', 'mean_launch_us')}
+      out['roofline']['alone']['dispatch'] = 'backward lanes off: the kernel has the GPU to itself'
   return out
 
 
