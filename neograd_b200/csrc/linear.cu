@@ -13,8 +13,6 @@
 //     per-block partials, no atomics on data).
 #include "tc_common.cuh"
 
-#include <stdlib.h>
-
 namespace ngb {
 
 int gemm_simt(int transA, int transB, int64_t M, int64_t N, int64_t K, const float* A, int64_t lda, const float* B,
@@ -311,10 +309,6 @@ int launch_small_wgrad(const float* x, const float* ug, float* dW, float* db, in
 }
 
 bool use_tc(int transA, int transB, int64_t M, int64_t N, int64_t K, int64_t lda, int64_t ldb, const void* A, const void* B) {
-  // experiment switch: problems whose reduction dimension is at most NGB_LINEAR_SIMT_MAXK go to the fp32 SIMT kernel (a
-  // tcgen05 launch has a ~6 us floor of descriptor fetch, TMEM allocation, pipeline fill and store drain)
-  static const int simt_maxk = getenv("NGB_LINEAR_SIMT_MAXK") ? atoi(getenv("NGB_LINEAR_SIMT_MAXK")) : 0;
-  if (K <= simt_maxk) return false;
   return g_default_engine.load() == NGB_GEMM_AUTO && tc::gemm_tc_eligible(transA, transB, M, N, K, lda, ldb, N) && aligned16(A) &&
          aligned16(B);
 }
