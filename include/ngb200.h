@@ -56,6 +56,11 @@ int ngb_shutdown(void);
 /* Debug aid: synchronises the device and reports (NGB_ERR_CUDA + ngb_last_error) if a tcgen05 producer / MMA / epilogue
  * warp gave up waiting on a pipeline barrier since the last call (such waits are bounded so a bug cannot hang the GPU). */
 int ngb_debug_check_pipelines(void);
+/* Non-blocking health check for the normal training path (no synchronisation: reads host-mapped words the kernels write):
+ * NGB_ERR_CUDA + ngb_last_error() if a tcgen05 pipeline wait gave up (the kernel left early, its output is incomplete) or
+ * the data-parallel peer exchange failed (ngb_xgpu_status).  neograd_b200 polls it every 16 optimizer steps and every 64
+ * replays of a captured step. */
+int ngb_runtime_status(void);
 /* Host only (no GPU): the bank-conflict-searched shared-memory layout of the small-channel conv weight-gradient tile for a
  * layer: out[0..5] = row stride, column stride, plane pitch, taps-kh-fastest flag, wavefronts per gather load x 1000 with
  * that layout and with the natural one. */

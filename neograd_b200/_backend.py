@@ -51,6 +51,7 @@ SIGNATURES = {
   'ngb_init': ([c_int64], c_int),
   'ngb_shutdown': ([], c_int),
   'ngb_debug_check_pipelines': ([], c_int),
+  'ngb_runtime_status': ([], c_int),
   'ngb_debug_wgrad_layout': ([c_int64] * 7 + [_P], c_int),
   'ngb_workspace_reserve': ([c_int64], c_int),
   'ngb_set_default_engine': ([c_int], c_int),
@@ -292,7 +293,7 @@ class profile_calls:
   `records` is a list of (name, args, start_event, end_event); call `summary()` after the block (it synchronises).
   Used by bench.py for the per-kernel roofline numbers; costs two event records per call, so never leave it on."""
   SKIP = ('ngb_abi_version', 'ngb_last_error', 'ngb_init', 'ngb_shutdown', 'ngb_gemm_query', 'ngb_launch_count',
-          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_set_lane', 'ngb_set_corun', 'ngb_xgpu_check', 'ngb_xgpu_status', 'ngb_xgpu_reset', 'ngb_xgpu_blocks',
+          'ngb_set_default_engine', 'ngb_workspace_reserve', 'ngb_debug_check_pipelines', 'ngb_runtime_status', 'ngb_set_lane', 'ngb_set_corun', 'ngb_xgpu_check', 'ngb_xgpu_status', 'ngb_xgpu_reset', 'ngb_xgpu_blocks',
           'ngb_debug_wgrad_layout', 'ngb_conv_relu_pool_fwd_serves', 'ngb_conv_wbgrad_pooled_is_fused', 'ngb_linear_softmax_ce_serves')
 
   def __enter__(self):

@@ -40,10 +40,10 @@ class CapturedStep:
     self.graph.replay()
     self._replays += 1
     if (self._replays & 63) == 0:
-      # a captured data-parallel step runs with no host involvement: poll the peer exchange's health word now and then
-      # (a host-memory read), so a rank that lost a peer raises instead of replaying no-op updates forever
+      # a captured step runs with no host involvement: poll the library's health words now and then (host-memory reads), so a
+      # rank that lost a peer, or a tcgen05 pipeline that gave up, raises instead of replaying wrong steps forever
       from . import _backend as B
-      B.check(B.lib.ngb_xgpu_status())
+      B.check(B.lib.ngb_runtime_status())
     return self.result
 
   replay = __call__

@@ -800,6 +800,7 @@ int conv_igemm_wgrad(const float* ug, const float* x, float* dw, int64_t N, int6
 }
 
 unsigned long long conv_take_timeout() { return tc::take_mbar_timeout(); }
+int conv_set_host_word(unsigned long long* dev_alias) { return tc::set_mbar_host_word(dev_alias); }
 
 }  // namespace ngb
 

@@ -701,6 +701,7 @@ using namespace ngb;
 namespace ngb {
 std::atomic<int> g_default_engine{NGB_GEMM_AUTO};
 unsigned long long gemm_take_timeout() { return tc::take_mbar_timeout(); }
+int gemm_set_host_word(unsigned long long* dev_alias) { return tc::set_mbar_host_word(dev_alias); }
 }
 
 extern "C" int ngb_set_default_engine(int engine) {

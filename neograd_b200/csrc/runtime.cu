@@ -6,6 +6,10 @@
 
 namespace ngb {
 
+int gemm_set_host_word(unsigned long long* dev_alias);
+int conv_set_host_word(unsigned long long* dev_alias);
+static unsigned long long* g_pipe_host = nullptr;       // host-mapped word the tcgen05 kernels write when a pipeline wait gives up
+
 static thread_local std::string t_last_error;
 std::atomic<int64_t> g_launches{0};
 
@@ -72,6 +76,14 @@ extern "C" int ngb_init(int64_t scratch_bytes) {
     if (l == 0 || had) NGB_CUDA(cudaMalloc(&g_scratch[l], scratch_bytes));
   }
   g_scratch_bytes = scratch_bytes;
+  if (!g_pipe_host) {
+    unsigned long long* dev_alias = nullptr;
+    NGB_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_pipe_host), sizeof(unsigned long long), cudaHostAllocMapped));
+    *g_pipe_host = 0;
+    NGB_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&dev_alias), g_pipe_host, 0));
+    if (gemm_set_host_word(dev_alias) || conv_set_host_word(dev_alias))
+      return fail(NGB_ERR_CUDA, "ngb_init: could not publish the pipeline status word");
+  }
   return NGB_OK;
 }
 
@@ -100,6 +112,21 @@ unsigned long long gemm_take_timeout();
 unsigned long long conv_take_timeout();
 }
 
+extern "C" int ngb_xgpu_status(void);
+
+// Non-blocking health check of everything that can fail asynchronously on the device: a tcgen05 pipeline wait that gave
+// up (the kernel left early: its output is incomplete) and the data-parallel peer exchange (ngb_xgpu_status).  Reads
+// host-mapped words only -- cheap enough to poll every few training steps; NGB_ERR_CUDA + ngb_last_error() on failure.
+extern "C" int ngb_runtime_status(void) {
+  if (g_pipe_host) {
+    const unsigned long long v = *reinterpret_cast<volatile unsigned long long*>(g_pipe_host);
+    if (v)
+      return fail(NGB_ERR_CUDA, "a tcgen05 pipeline wait timed out (tag %llu, block %llu, thread %llu): the kernel left early and its "
+                  "output is incomplete", (v >> 48) & 0x7fff, (v >> 16) & 0xffffffffull, v & 0xffff);
+  }
+  return ngb_xgpu_status();
+}
+
 // Hint for persistent kernels: 1 = the calling thread's next launches are expected to run BESIDE another lane's kernels
 // (leave part of every SM free so the other lane's kernels can become resident), 0 (default) = they have the GPU to
 // themselves.  Returns the previous value.
@@ -116,6 +143,7 @@ extern "C" int ngb_debug_check_pipelines(void) {
   NGB_CUDA(cudaDeviceSynchronize());
   const unsigned long long a = gemm_take_timeout(), b = conv_take_timeout();
   if (a | b) {
+    if (g_pipe_host) *g_pipe_host = 0;
     const unsigned long long v = a ? a : b;
     return fail(NGB_ERR_CUDA, "tcgen05 pipeline timeout in %s kernel: wait tag %llu, block %llu, thread %llu", a ? "gemm" : "conv",
                 (v >> 48) & 0x7fff, (v >> 16) & 0xffffffffull, v & 0xffff);

@@ -67,17 +67,28 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
 // On timeout the waiter records (tag, block, thread) in a per-translation-unit device word and leaves the kernel with
 // `exit` (its peers time out the same way), so a pipeline bug ends as a reported error, not a wedged or poisoned context.
 static __device__ unsigned long long g_mbar_timeout = 0;
+// Host-mapped mirror of the word above (set once per translation unit by set_mbar_host_word): the normal training path
+// polls it without synchronising (ngb_runtime_status), so a pipeline that gave up never goes unnoticed.
+static __device__ unsigned long long* g_mbar_host = nullptr;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, uint32_t tag = 0) {
   if (mbar_try_wait(bar, parity)) return;
   const uint64_t t0 = global_timer_ns();
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
     if ((++spins & 0x3FF) == 0 && global_timer_ns() - t0 > 1000000000ull) {
-      atomicCAS(&g_mbar_timeout, 0ull,
-                (1ull << 63) | ((unsigned long long)tag << 48) | ((unsigned long long)blockIdx.x << 16) | threadIdx.x);
+      const unsigned long long code =
+          (1ull << 63) | ((unsigned long long)tag << 48) | ((unsigned long long)blockIdx.x << 16) | threadIdx.x;
+      atomicCAS(&g_mbar_timeout, 0ull, code);
+      if (g_mbar_host) {
+        *reinterpret_cast<volatile unsigned long long*>(g_mbar_host) = code;
+        __threadfence_system();
+      }
       asm volatile("exit;");
     }
   }
+}
+inline int set_mbar_host_word(unsigned long long* dev_alias) {
+  return cudaMemcpyToSymbol(g_mbar_host, &dev_alias, sizeof(dev_alias)) == cudaSuccess ? 0 : 1;
 }
 // Host side: reads and clears this translation unit's timeout word (0 = no timeout).
 inline unsigned long long take_mbar_timeout() {

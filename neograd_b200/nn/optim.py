@@ -181,6 +181,15 @@ class Optimizer:
     if 'iter' in state and hasattr(self, 'iter'):
       self.iter = state['iter']
 
+  _polls = 0
+
+  @staticmethod
+  def _poll_health():
+    """Every 16th optimizer step: non-blocking check that no tcgen05 pipeline gave up and no peer exchange failed."""
+    Optimizer._polls += 1
+    if (Optimizer._polls & 15) == 0:
+      B.check(B.lib.ngb_runtime_status())
+
   def zero_grad(self, all_members=False):
     if all_members:
       get_graph().zero_grad()
@@ -191,6 +200,7 @@ class Optimizer:
     """Data parallel without peer memory: one NCCL allreduce of the flat gradient buffer in place; returns grad_scale.
     (With peer memory the exchange happens inside the update kernel: _fused_exchange.)"""
     a = self.arena
+    self._poll_health()
     D.flush_lazy()           # deferred arrays somebody still holds are produced before the weights change
     a.prepare_grads()
     if dist.is_initialized() and dist.world_size() > 1:
