@@ -1,0 +1,23 @@
+"""Replacement for the reference's tests/_setup.py when ITS test files run unchanged against the device backend
+(tests/test_reference_tests_unchanged_gpu.py).  Same two helpers, same signatures (reference: tests/_setup.py:7-42); the
+documented override: the probe width and pass threshold are the device's -- eps 1e-3, dist < 1e-2 -- whatever the caller
+passes, because the reference's 1e-7 / 1e-7 (3e-7 for Linear) is below fp32 resolution.  NumPy's
+global RNG is seeded here: the reference's test modules draw their operands from it at import time, unseeded."""
+import numpy as np
+
+import neograd as ng
+from neograd.autograd.utils import process_data, fn_grad_check  # noqa: F401
+
+np.random.seed(1234)
+DEVICE_EPSILON, DEVICE_TOLERANCE = 1e-3, 1e-2
+
+
+def to_tensors(operands):
+  return [ng.tensor(operand.astype(float), requires_grad=True) for operand in operands]
+
+
+def execute(fn, operands, params=None, epsilon=1e-7, tolerance=1e-7, **kwargs):
+  tensors = to_tensors(operands)
+  params_to_be_tested = tensors if params is None else (params + tensors)
+  dist = fn_grad_check(fn, tensors, params_to_be_tested, epsilon=DEVICE_EPSILON, print_vals=False, **kwargs)
+  assert dist < max(tolerance, DEVICE_TOLERANCE), dist
