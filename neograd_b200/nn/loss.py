@@ -97,7 +97,17 @@ class SoftmaxCE(Operation, Loss):
   def forward(self, outputs, targets, epsilon=1e-9):
     outputs, targets = self.get_tensors(outputs, targets)
     if outputs.shape != targets.shape:
-      raise ValueError(f"operands could not be broadcast together with shapes {outputs.shape} {targets.shape}")
+      # loss.py:155 / 170 multiply and subtract with NumPy broadcasting (the reference's own test passes one target row for
+      # the whole batch): targets that broadcast TO the logits' shape are expanded on the device
+      import numpy as np
+      try:
+        ok = np.broadcast_shapes(outputs.shape, targets.shape) == tuple(outputs.shape)
+      except ValueError:
+        ok = False
+      if not ok:
+        raise ValueError(f"operands could not be broadcast together with shapes {outputs.shape} {targets.shape}")
+      from ..autograd.tensor import Tensor
+      targets = Tensor(D.broadcast_to(targets.data, outputs.shape), requires_grad=targets.requires_grad)
     n = self.get_num_examples(outputs.shape)
     outer, L, inner = _split_axis(outputs.shape, self.axis)
     loss = D.DeviceArray.empty(())
