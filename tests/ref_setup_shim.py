@@ -19,5 +19,6 @@ def to_tensors(operands):
 def execute(fn, operands, params=None, epsilon=1e-7, tolerance=1e-7, **kwargs):
   tensors = to_tensors(operands)
   params_to_be_tested = tensors if params is None else (params + tensors)
-  dist = fn_grad_check(fn, tensors, params_to_be_tested, epsilon=DEVICE_EPSILON, print_vals=False, **kwargs)
+  dist = fn_grad_check(fn, tensors, params_to_be_tested, epsilon=DEVICE_EPSILON, print_vals=False, **kwargs)   # (the library
+  # itself would also widen an explicit 1e-7: autograd/utils.py:_device_epsilon)
   assert dist < max(tolerance, DEVICE_TOLERANCE), dist
