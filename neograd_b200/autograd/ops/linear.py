@@ -46,7 +46,10 @@ class LinearPending:
       if not zlazy.pending:                       # somebody read z in the meantime: plain elementwise kernel
         return D.unary(op, zlazy, alpha)
       shape = (self.M, self.n_out)
-      z = D.DeviceArray.empty(shape) if self.track else None
+      # LeakyReLU with a positive slope preserves the sign (and the zero) of its input, so its backward mask z >= 0 can be
+      # read off the OUTPUT: the pre-activation is then not written at all (it stays deferred for whoever asks for it)
+      need_z = self.track and not (op == B.LEAKY_RELU and alpha > 0)
+      z = D.DeviceArray.empty(shape) if need_z else None
       a = D.DeviceArray.empty(shape)
       self.launch(z, a, op, alpha)
       if z is not None:
