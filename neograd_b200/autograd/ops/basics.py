@@ -105,7 +105,8 @@ class _Unary(Operation):
       # epilogue writes both) when this activation is first used
       out = D.LazyArray(x.shape, x.args.act_thunk(x, op, alpha), 'linear_act', None)
       D.register_lazy(out, x.args.sources())
-      self._out = out                               # (backward may take its mask from the output: see `mask_src` below)
+      if x.args.act_out is None:
+        x.args.act_out = (op, alpha, out)           # (backward may take its mask from this output, see below)
     elif op == B.RELU and D.LAZY_FUSION:
       # produced on first use: a MaxPool that follows reads x itself (maxpool(relu(x)) in one kernel, conv.py here)
       out = D.LazyArray(x.shape, lambda: D.unary(op, x, alpha), 'relu', x)
@@ -116,12 +117,12 @@ class _Unary(Operation):
 
   def backward(self, tens):
     op, alpha, x = self.OP, self.alpha, tens.data
-    y = getattr(self, '_out', None)
-    if (op == B.LEAKY_RELU and alpha > 0 and y is not None and isinstance(x, D.LazyArray) and x.pending
-        and not (isinstance(y, D.LazyArray) and y.pending)):
+    if op == B.LEAKY_RELU and alpha > 0 and isinstance(x, D.LazyArray) and x.pending and x.tag == 'linear':
       # the fused Linear + LeakyReLU kernel wrote only the activation: sign(y) == sign(x) and y == 0 <=> x == 0, so the
       # reference's mask x >= 0 (activations.py:216) is y >= 0 -- the deferred pre-activation is never produced
-      x = y
+      fused = x.args.act_out
+      if fused is not None and fused[0] == op and fused[1] == alpha and not fused[2].pending:
+        x = fused[2]
 
     def into(ug, dst, accumulate):
       if op in _LINEAR_ACTS and isinstance(ug, D.LazyArray) and ug.pending and ug.tag == 'linear_dgrad':

@@ -18,10 +18,11 @@ from .operation import Operation
 
 class LinearPending:
   """What a still-deferred Linear output stands for (args of a LazyArray tagged 'linear')."""
-  __slots__ = ('x', 'W', 'b', 'M', 'n_in', 'n_out', 'track')
+  __slots__ = ('x', 'W', 'b', 'M', 'n_in', 'n_out', 'track', 'act_out')
 
   def __init__(self, x, W, b, track):
     self.x, self.W, self.b, self.track = x, W, b, track
+    self.act_out = None                           # (op, alpha, deferred act(z)) of the activation fused onto this layer
     self.M, self.n_in = x.shape
     self.n_out = W.shape[1]
 

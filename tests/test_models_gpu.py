@@ -488,8 +488,12 @@ def test_forward_only_and_late_reads_of_fused_linear(ng):
   z = lin(x)
   a = act(z)
   assert isinstance(z.data, D.LazyArray) and z.data.pending and a.data.pending
-  assert dist(a.data.numpy(), want_a) < 1e-3 and not z.data.pending       # one kernel produced both
+  # LeakyReLU's backward mask is read off its output, so the pre-activation stays deferred; a ReLU keeps it (z == 0 case)
+  assert dist(a.data.numpy(), want_a) < 1e-3 and z.data.pending
   assert dist(z.data.numpy(), want_z) < 1e-3
+  zr = lin(x)
+  ar = ng.nn.ReLU()(zr)
+  assert dist(ar.data.numpy(), np.maximum(want_z, 0)) < 1e-3 and not zr.data.pending   # one kernel produced both
   ng._NG_GRAPH.reset_graph()
   with ng.no_track():
     z2 = lin(x)
