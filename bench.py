@@ -270,25 +270,35 @@ class ClockSampler(threading.Thread):
              'hw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonHwThermalSlowdown', 0x40),
              'sw_thermal_slowdown': getattr(nv, 'nvmlClocksEventReasonSwThermalSlowdown', 0x20),
              'sw_power_cap': getattr(nv, 'nvmlClocksEventReasonSwPowerCap', 0x4)}
+    self.names = names
     while not self.stop_flag:
+      self.sample()
+      time.sleep(0.005)
+
+  def sample(self):
+    nv = self.nv
+    try:
+      self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
       try:
-        self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
-        try:
-          r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-        except Exception:
-          r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-        for k, bit in names.items():
-          if r & bit:
-            self.reasons.add(k)
+        r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
       except Exception:
-        pass
-      time.sleep(0.05)
+        r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+      for k, bit in self.names.items():
+        if r & bit:
+          self.reasons.add(k)
+    except Exception:
+      pass
 
   def result(self):
+    """Called right after the timed region's closing synchronize: one more sample is taken here so that a region shorter
+    than an NVML query (20 steps of 0.2 ms) is still bracketed by a sample on each side."""
     self.stop_flag = True
+    if self.nv is not None and hasattr(self, 'names'):
+      self.sample()
     if not self.samples:
       return {'sm_mhz': None, 'sm_max_mhz': self.max_mhz, 'reasons': []}
-    return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons)}
+    return {'sm_mhz': float(np.median(self.samples)), 'sm_max_mhz': self.max_mhz, 'reasons': sorted(self.reasons),
+            'samples': len(self.samples)}
 
 
 # --------------------------------------------------------------------------------------------- algorithmic work per call
@@ -589,6 +599,10 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
   clocks = ClockSampler(clocks_index) if clocks_index is not None else None
   if clocks:
     clocks.start()
+    for _ in range(2000):                 # keep the GPU under the same load until the sampler has its first reading
+      if clocks.samples or clocks.nv is None:
+        break
+      captured()
   graph_ms = h.max_over_ranks(h.timed(captured, args.steps))
   clk = clocks.result() if clocks else None
   total_samples = batch * world * args.steps

@@ -1,9 +1,14 @@
+# The round's measurement records in one GPU call (outputs under gpurun_out/, copied to profiles/ afterwards).
 set -x
-python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
-python bench.py > gpurun_out/bench32.json 2> gpurun_out/bench32.err
-python bench.py --impl reference > gpurun_out/bench32_ref.json 2> gpurun_out/bench32_ref.err
-python tools/timeline.py > gpurun_out/timeline32.txt 2>&1
-ncu --metrics gpu__time_duration.sum --clock-control none -c 900 --csv --log-file gpurun_out/launches_r1i.csv python bench.py --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_launch_r1i.log 2>&1
-timeout 200 ncu --set full --clock-control none --import-source on -k regex:"conv_relu_pool_fwd|conv_gather_mma|conv_dgrad_rows|conv_wgrad_mma|sparse|maxpool2x2_fwd|conv_bgrad" --launch-skip 30 -c 8 -f -o gpurun_out/r1i_full python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_full_r1i.log 2>&1
-ls -la gpurun_out/r1i_full.ncu-rep
+python bench.py --steps 20 --warmup 5 > gpurun_out/r02_bench_n1.json 2> gpurun_out/r02_bench_n1.err
+python bench.py --workload gan784 --steps 20 --warmup 5 > gpurun_out/r02_bench_n1_gan784.json 2> gpurun_out/r02_bench_n1_gan784.err
+python bench.py --impl reference > gpurun_out/r02_bench_reference_arm.json 2> gpurun_out/r02_ref.err
+python tools/timeline.py --workload lenet_b > gpurun_out/r02_timeline_lenet_b.txt 2>/dev/null
+python tools/timeline.py --workload gan784 > gpurun_out/r02_timeline_gan784.txt 2>/dev/null
+python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline > /dev/null 2>&1 && ncu --metrics gpu__time_duration.sum --clock-control none -c 1600 --csv --log-file gpurun_out/r02_launches_bench.csv python bench.py --steps 2 --warmup 1 --no-extra --no-cpu-baseline > gpurun_out/ncu_l.log 2>&1
+for w in lenet_b gan784; do
+  python tools/one_step.py $w 1 && ncu --set full --clock-control none -o /tmp/r02_$w python tools/one_step.py $w 1 > gpurun_out/ncu_$w.log 2>&1
+  python tools/ncu_summary.py full /tmp/r02_$w.ncu-rep > gpurun_out/r02_${w}_kernels.md
+  ncu -i /tmp/r02_$w.ncu-rep --page raw --csv --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum > gpurun_out/r02_${w}_traffic.csv
+done
+du -sh gpurun_out
