@@ -149,15 +149,16 @@ template <int NT>
 __global__ void __launch_bounds__(256) linear_smalln_dgrad_kernel(const float* __restrict__ ug, const float* __restrict__ W,
                                                                   const float* __restrict__ zprev, float* __restrict__ dx,
                                                                   int act, float alpha, int64_t M, int N, int K,
-                                                                  int accumulate) {
+                                                                  int accumulate, FastDiv dK) {
   extern __shared__ float smem_lin[];
   constexpr int NP = NT | 1;
   float* Ws = smem_lin;
   stage_w<NT>(Ws, W, K, N);
   __syncthreads();
   const int64_t total = M * K;
+  const bool small = total < (int64_t(1) << 32);       // (the usual case: one multiply-shift instead of a 64-bit divide per element)
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-    const int64_t m = i / K;
+    const int64_t m = small ? (int64_t)dK.div((uint32_t)i) : i / K;
     const int k = (int)(i - m * K);
     const float* ur = ug + m * N;
     const float* wr = Ws + k * NP;
@@ -240,6 +241,59 @@ __global__ void __launch_bounds__(256) linear_smalln_wgrad_kernel(const float* _
   }
 }
 
+// The same gradients for n_in <= 256 and a batch worth spreading over the chip: a block owns a SLAB of rows and a thread one
+// column k of 256 / K rows in flight, so consecutive threads read consecutive words of x (rows are K contiguous floats) and
+// the ug row is a broadcast; sums over the rows in flight in shared memory (fixed order), one row of K*N + N partials per
+// block, summed across blocks in a fixed order by the second pass (launch_sum_partials2).  The kernel above walks the whole
+// batch with K / KB + 1 blocks (33 for the GAN's 256 -> 1 head: 18 - 25 us for an 8 MB read); this one takes 4 + 3 us.
+template <int NT>
+__global__ void __launch_bounds__(256) linear_smalln_wgrad_slab_kernel(const float* __restrict__ x, const float* __restrict__ ug,
+                                                                       float* __restrict__ part, int64_t M, int N, int K,
+                                                                       int rows_per_block, int R) {
+  __shared__ float red[256 * NT];
+  __shared__ float redb[256];            // [R][NT] bias partials (R * NT <= 256 is checked by the host)
+  const int tid = threadIdx.x;
+  const int r = tid / K, k = tid - r * K;
+  const bool live = r < R;
+  float acc[NT], accb[NT];
+#pragma unroll
+  for (int n = 0; n < NT; ++n) acc[n] = accb[n] = 0.f;
+  const int64_t m0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t m1 = m0 + rows_per_block < M ? m0 + rows_per_block : M;
+  if (live) {
+#pragma unroll 4
+    for (int64_t m = m0 + r; m < m1; m += R) {
+      const float xv = x[m * K + k];
+      const float* ur = ug + m * N;
+#pragma unroll
+      for (int n = 0; n < NT; ++n) {
+        const float u = n < N ? ur[n] : 0.f;
+        acc[n] = fmaf(xv, u, acc[n]);
+        accb[n] += u;                     // (used by the k == 0 thread of the row only)
+      }
+    }
+  }
+#pragma unroll
+  for (int n = 0; n < NT; ++n) red[tid * NT + n] = live ? acc[n] : 0.f;
+  if (live && k == 0) {
+#pragma unroll
+    for (int n = 0; n < NT; ++n) redb[r * NT + n] = accb[n];
+  }
+  __syncthreads();
+  float* prow = part + (int64_t)blockIdx.x * (K * N + N);
+  for (int e = tid; e < K * N + N; e += 256) {
+    float sum = 0.f;
+    if (e < K * N) {
+      const int kk = e / N, n = e - kk * N;
+      for (int rr = 0; rr < R; ++rr) sum += red[(rr * K + kk) * NT + n];
+    } else {
+      const int n = e - K * N;
+      for (int rr = 0; rr < R; ++rr) sum += redb[rr * NT + n];
+    }
+    prow[e] = sum;
+  }
+}
+
 constexpr int kSmallNMax = 32;
 constexpr int64_t kSmallSmemMax = 96 * 1024;
 
@@ -293,7 +347,7 @@ int launch_small_dgrad(const float* ug, const float* W, const float* zprev, floa
   const int64_t smem = small_smem(N, K);
   int rc = set_smem(kern, smem);
   if (rc) return rc;
-  kern<<<grid_for(M * K, 256, 4), 256, smem, st>>>(ug, W, zprev, dx, act, alpha, M, (int)N, (int)K, accumulate);
+  kern<<<grid_for(M * K, 256, 4), 256, smem, st>>>(ug, W, zprev, dx, act, alpha, M, (int)N, (int)K, accumulate, FastDiv((uint32_t)K));
   NGB_LAUNCH_CHECK();
   return NGB_OK;
 }
@@ -301,6 +355,24 @@ int launch_small_dgrad(const float* ug, const float* W, const float* zprev, floa
 template <int NT>
 int launch_small_wgrad(const float* x, const float* ug, float* dW, float* db, int64_t M, int64_t N, int64_t K, int acc_w, int acc_b,
                        cudaStream_t st) {
+  const int R = K <= 256 ? (int)(256 / K) : 0;              // rows in flight per block of the slab kernel
+  if (db != nullptr && K <= 256 && R * NT <= 256 && M >= 1024) {      // (weight gradient alone: the single-pass kernel below)
+    int rc = ensure_init();
+    if (rc) return rc;
+    const int64_t row_floats = K * N + N;
+    int64_t grid = ceil_div<int64_t>(M, (int64_t)R * 4);    // at least four rows per thread
+    if (grid > 2 * kNumSMs) grid = 2 * kNumSMs;
+    const int64_t cap = scratch_bytes() / (int64_t)sizeof(float) / row_floats;
+    if (grid > cap) grid = cap;
+    if (grid >= 1) {
+      const int rows_per_block = (int)ceil_div<int64_t>(M, grid);
+      grid = ceil_div<int64_t>(M, rows_per_block);
+      float* part = scratch_ptr();
+      linear_smalln_wgrad_slab_kernel<NT><<<(int)grid, 256, 0, st>>>(x, ug, part, M, (int)N, (int)K, rows_per_block, R);
+      NGB_LAUNCH_CHECK();
+      return launch_sum_partials2(part, (int)grid, K * N, dW, acc_w, N, db, acc_b, st);
+    }
+  }
   constexpr int KB = NT <= 4 ? 8 : (NT <= 16 ? 4 : 2);       // KB x NT <= 64 accumulators per thread
   const int blocks = (int)ceil_div<int64_t>(K, KB) + 1;      // + the bias block
   linear_smalln_wgrad_kernel<NT, KB><<<blocks, 256, 0, st>>>(x, ug, dW, db, M, (int)N, (int)K, acc_w, acc_b);
