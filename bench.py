@@ -599,10 +599,8 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
   clocks = ClockSampler(clocks_index) if clocks_index is not None else None
   if clocks:
     clocks.start()
-    for _ in range(2000):                 # keep the GPU under the same load until the sampler has its first reading
-      if clocks.samples or clocks.nv is None:
-        break
-      captured()
+  for _ in range(64):                     # the same load while the sampler takes its first readings -- a FIXED count on every
+    captured()                            # rank: a replay contains the gradient exchange, so ranks must stay in step
   graph_ms = h.max_over_ranks(h.timed(captured, args.steps))
   clk = clocks.result() if clocks else None
   total_samples = batch * world * args.steps
