@@ -68,6 +68,7 @@ class PeerExchange:
   exchanges in the same order).  `create` returns None when symmetric memory is unavailable (gloo / CPU, single process,
   NGB_NO_P2P=1): the caller then uses the NCCL allreduce followed by the plain update kernel."""
   MAX_BLOCKS = 148
+  LL_MAX_FLOATS = 148 * 256 * 4      # kLLMaxFloats in csrc/xgpu.cu
   KIND = {'adam': 0, 'sgd': 1, 'momentum': 2, 'rmsprop': 3}
 
   def __init__(self, stride, recv, recv_ptrs, flags, flag_ptrs, epoch, handles):
@@ -96,6 +97,8 @@ class PeerExchange:
         pass
       w = world_size()
       stride = max((int(numel) + 3) & ~3, 4)
+      if stride <= PeerExchange.LL_MAX_FLOATS:
+        stride *= 2          # room for {value, epoch} words: small arenas use the low-latency protocol (csrc/xgpu.cu)
       recv = sm.empty(2 * w * stride, dtype=torch.float32, device='cuda')
       recv.zero_()
       hr = sm.rendezvous(recv, group)
