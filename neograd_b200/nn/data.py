@@ -47,7 +47,11 @@ class DeviceLoader:
   PIN_LIMIT = 2 << 30     # datasets up to this many bytes are page-locked as a whole: batches then go host -> device straight
                           # from the dataset (no per-batch staging copy on the host)
 
-  def __init__(self, inputs, targets=None, batch_size=None, normalize=None, num_classes=None, drop_last=False):
+  def __init__(self, inputs, targets=None, batch_size=None, normalize=None, num_classes=None, drop_last=False,
+               prepare_ahead=False):
+    # prepare_ahead: the normalisation / one-hot kernels of a batch run on the COPY stream right behind its host -> device
+    # copy, i.e. beside the previous batch's compute, instead of on the consumer's stream when the batch is asked for
+    self.prepare_ahead = bool(prepare_ahead)
     t = torch()
     B.ensure_runtime()
     inputs = np.asarray(inputs)
@@ -142,6 +146,8 @@ class DeviceLoader:
       if src_y is not None:
         self._raw_y[slot][:rows].copy_(src_y, non_blocking=True)
       self._staged[slot].record(self._copy_stream)
+      if self.prepare_ahead:
+        self.prepare(slot, rows)                            # (current stream = the copy stream here)
       self._copied[slot].record(self._copy_stream)
     self._staged_valid[slot] = True
     self._cursor = start + rows
@@ -185,7 +191,7 @@ class DeviceLoader:
     slot, rows = self._issued.pop(0)
     self._stage()                                            # prefetch: overlaps this batch's compute
     torch().cuda.current_stream().wait_event(self._copied[slot])
-    if prepare:
+    if prepare and not self.prepare_ahead:
       self.prepare(slot, rows)
     X, Y = self.slots[slot]
     if rows < self.batch_size:

@@ -69,12 +69,14 @@ def test_randn_is_standard_normal_and_counter_based(ng):
   assert odd.shape == (7,) and np.isfinite(odd).all()
 
 
-def test_device_loader_epochs(ng):
+@pytest.mark.parametrize('ahead', [False, True])
+def test_device_loader_epochs(ng, ahead):
+  """ahead: the normalisation / one-hot kernels run on the copy stream behind each batch's H2D copy (prepare_ahead)."""
   rng = np.random.default_rng(1)
   n, bs = 1000, 256
   imgs = rng.integers(0, 256, (n, 1, 28, 28), dtype=np.uint8)
   labels = rng.integers(0, 10, n)
-  loader = ng.nn.DeviceLoader(imgs, labels, bs, normalize=(1 / 255.0, -0.5), num_classes=10)
+  loader = ng.nn.DeviceLoader(imgs, labels, bs, normalize=(1 / 255.0, -0.5), num_classes=10, prepare_ahead=ahead)
   assert len(loader) == 4 and loader.bytes_per_batch == bs * 784 + bs * 4
   for _ in range(2):                                   # two epochs over the same loader
     seen = 0
@@ -88,7 +90,7 @@ def test_device_loader_epochs(ng):
     assert seen == n                                   # the last batch is short (1000 = 3 * 256 + 232), as with get_batches
   # per-sample standardisation of float inputs, float targets copied as they are, no one-hot (digits.ipynb cells 5-6)
   xs, ys = rng.standard_normal((300, 8, 8)) * 3 + 1, rng.standard_normal((300, 10))
-  loader = ng.nn.DeviceLoader(xs, ys, 128, normalize='per_sample')
+  loader = ng.nn.DeviceLoader(xs, ys, 128, normalize='per_sample', prepare_ahead=ahead)
   flat = xs.reshape(300, 64)
   want = ((flat - flat.mean(axis=1, keepdims=True)) / flat.std(axis=1, keepdims=True)).reshape(300, 8, 8)
   seen = 0
