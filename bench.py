@@ -635,6 +635,8 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
   loss_host = [torch.empty(n_loss, dtype=torch.float32).pin_memory() for _ in range(2)]
   loss_dev = [torch.empty(n_loss, device='cuda', dtype=torch.float32) for _ in range(2)]
   step_done = [torch.cuda.Event() for _ in range(2)]
+  loss_read = [torch.cuda.Event() for _ in range(2)]
+  loss_stream = torch.cuda.Stream()
   main = torch.cuda.current_stream()
 
   def e2e_run(nsteps):
@@ -648,16 +650,22 @@ def measure_workload(h, ng, B, name, batch, args, pk, full=True, clocks_index=No
       losses = steps2[slot]()
       loader.release(slot)
       b_ = i & 1
-      if n_loss == 1:
-        loss_host[b_].copy_(losses[0].data.t.view(1), non_blocking=True)
-      else:
-        for j, l in enumerate(losses):
-          loss_dev[b_][j:j + 1].copy_(l.data.t.view(1), non_blocking=True)
-        loss_host[b_].copy_(loss_dev[b_], non_blocking=True)
+      # the loss read-back rides on its own stream behind the step (each of the two captured steps owns its loss buffers, so
+      # the copy of step i is long finished when step i+2 overwrites them): the next step does not queue behind a D2H copy
       step_done[b_].record(main)
+      loss_stream.wait_event(step_done[b_])
+      with torch.cuda.stream(loss_stream):
+        if n_loss == 1:
+          loss_host[b_].copy_(losses[0].data.t.view(1), non_blocking=True)
+        else:
+          for j, l in enumerate(losses):
+            loss_dev[b_][j:j + 1].copy_(l.data.t.view(1), non_blocking=True)
+          loss_host[b_].copy_(loss_dev[b_], non_blocking=True)
+        loss_read[b_].record(loss_stream)
       if i >= 1:
-        step_done[(i - 1) & 1].synchronize()              # loss of the previous step is now on the host
+        loss_read[(i - 1) & 1].synchronize()              # loss of the previous step is now on the host
         float(loss_host[(i - 1) & 1][0])
+    loss_stream.synchronize()
     main.synchronize()
     return [float(v) for v in loss_host[(nsteps - 1) & 1]]
 
