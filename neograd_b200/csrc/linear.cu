@@ -356,7 +356,8 @@ template <int NT>
 int launch_small_wgrad(const float* x, const float* ug, float* dW, float* db, int64_t M, int64_t N, int64_t K, int acc_w, int acc_b,
                        cudaStream_t st) {
   const int R = K <= 256 ? (int)(256 / K) : 0;              // rows in flight per block of the slab kernel
-  if (db != nullptr && K <= 256 && R * NT <= 256 && M >= 1024) {      // (weight gradient alone: the single-pass kernel below)
+  // (x of at least 4 MB: below that the single-pass kernel is as fast and one launch fewer; weight gradient alone: likewise)
+  if (db != nullptr && K <= 256 && R * NT <= 256 && M * K >= (int64_t(1) << 20)) {
     int rc = ensure_init();
     if (rc) return rc;
     const int64_t row_floats = K * N + N;

@@ -351,6 +351,8 @@ LINEAR_CASES = [   # batch, n_in, n_out : which engine serves it in 'tf32' mode
   (8192, 784, 512),    # GAN: tcgen05 BN = 256
   (1024, 256, 784),    # GAN last generator layer
   (2048, 256, 1),      # GAN discriminator head: small-N, one output
+  (8192, 256, 1),      # ... at the BASELINE batch: the slab-parallel weight gradient (x >= 4 MB)
+  (16384, 84, 10),     # a classifier head large enough for the slab kernel (three rows in flight per block)
   (200, 36, 10),       # digits CNN head
   (750, 2, 100),       # README MLP first layer: SIMT (K = 2)
   (333, 50, 25),       # notebook-scale GAN layer: SIMT (unaligned leading dimensions)
